@@ -1,0 +1,92 @@
+"""CPU: the numpy oracle vs fixtures produced by the unmodified reference (tests/golden)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import scgrhc_oracle as orc
+from tests import helpers as H
+
+
+def test_intervals_match_reference():
+  cases = H.load_json('intervals.json')
+  for name, case in cases.items():
+    for chamber, want in case['intervals'].items():
+      got = orc.chamber_intervals(case['meta'], chamber)
+      assert [list(x) for x in got] == want, (name, chamber)
+
+
+def test_predicates_match_reference():
+  g = np.load(os.path.join(H.GOLDEN, 'predicates.npz'))
+  names, ys = H.predicate_inputs()
+  assert H.sha(ys) == str(g['inputs_sha']), 'synthetic generator drifted from the fixture inputs'
+  assert ((orc.flat_count(ys) >= 2) == g['flat']).all()
+  assert (orc.is_straight_line(ys) == g['straight']).all()
+  assert (~orc.below_floor(ys, -50) == g['in_range']).all()
+  assert (np.array([orc.has_noise(y, -50) for y in ys]) == g['has_noise']).all()
+  # the closed form tracks sklearn's R^2 far inside the decision margin
+  ok = g['r2'] > 1e-6
+  assert np.abs(orc.r_squared(ys)[ok] - g['r2'][ok]).max() < 1e-12
+  # API parity of the quirky segment list
+  segs = json.loads(str(g['adv_segments']))
+  for want, y in zip(segs, ys):
+    assert [tuple(s) for s in want] == orc.flat_segments(y)
+
+
+def test_flat_quirk_needs_two_positions():
+  names, ys = H.predicate_inputs()
+  by = dict(zip(names, ys))
+  assert orc.flat_count(by['run50@350']) == 1 and not (orc.flat_count(by['run50@350']) >= 2)
+  assert orc.flat_count(by['run51@350']) == 2
+  assert orc.flat_count(by['run49@350']) == 0
+
+
+def test_nonfinite_raises_like_reference():
+  y = np.linspace(0, 30, 750) ** 1.5 + np.sin(np.arange(750))
+  y[10] = np.nan
+  with pytest.raises(ValueError):
+    orc.has_noise(y, -50)
+  y[100:200] = 3.0          # flat line short-circuits before sklearn sees the NaN
+  assert orc.has_noise(y, -50) is True
+
+
+@pytest.mark.parametrize('cfg', ['waveform_06', 'waveform_10', 'waveform_11', 'waveform_23', 'waveform_19', 'waveform_15'])
+def test_record_small_bit_exact(cfg):
+  g = np.load(os.path.join(H.GOLDEN, 'record_small.npz'))
+  sig, p, meta = H.small_record()
+  c = H.effective_config(cfg)
+  rw = orc.scan_record(p, sig, meta, c['in_channels'], c['chamber'], c['segment_size'], c['min_RHC'])
+  k = np.nonzero(rw.keep)[0]
+  assert (rw.rel_start[k] == g[cfg + '.start']).all()
+  assert (rw.rel_start[k] + rw.W == g[cfg + '.stop']).all()
+  scg, rhc, mm = orc.normalise_record(p, sig, c['in_channels'], rw)
+  assert (mm == g[cfg + '.minmax']).all()
+  assert scg.tobytes() == g[cfg + '.scg'].tobytes()
+  assert rhc.tobytes() == g[cfg + '.rhc'].tobytes()
+
+
+def test_records_full_all_configs():
+  full = H.load_json('records_full.json')
+  table = H.configs()
+  recs = {('rec%d' % r): H.full_record(r) for r in (0, 1)}
+  for name, (sig, p, meta) in recs.items():
+    assert H.sha(p) == full['record_sha'][name]
+  assert len(full['configs']) == 36
+  for cfg, entry in full['configs'].items():
+    c = H.effective_config(cfg, table)
+    scans = {n: orc.scan_record(p, sig, meta, c['in_channels'], c['chamber'], c['segment_size'], c['min_RHC'])
+             for n, (sig, p, meta) in recs.items()}
+    gmm = None
+    if c['use_global_min_max']:
+      gmm = orc.global_minmax(np.concatenate([rw.minmax[rw.keep] for rw in scans.values()]))
+      assert [float(v).hex() for v in gmm] == entry['global_minmax_hex']
+    for n, (sig, p, meta) in recs.items():
+      rw, want = scans[n], entry['records'][n]
+      k = np.nonzero(rw.keep)[0]
+      assert rw.rel_start[k].tolist() == want['start'], (cfg, n)
+      assert (rw.rel_start[k] + rw.W).tolist() == want['stop'], (cfg, n)
+      scg, rhc, mm = orc.normalise_record(p, sig, c['in_channels'], rw, gmm)
+      assert H.sha(mm) == want['minmax_sha'], (cfg, n)
+      assert H.sha(scg) == want['scg_sha'], (cfg, n)
+      assert H.sha(rhc) == want['rhc_sha'], (cfg, n)
