@@ -1,0 +1,173 @@
+/*
+ * scgrhc.h — C ABI of the B200-native SCG/RHC window-preparation library (libscgrhc.so).
+ *
+ * The reference (jwang6174/scg-rhc-waveform) is pure Python and has no FFI; its boundary is the
+ * set of module-level Python functions other scripts import.  Each entry point
+ * below names the reference interface it replaces (paths relative to the reference root).  The
+ * Python drop-in modules in scg-rhc-waveform_b200/ (recordutil.py, waveform_noise.py, …) bind
+ * these symbols with ctypes and keep the reference's signatures; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns an scgrhc_status (0 = ok, negative = error); the message of the last
+ *     error on a context is available from scgrhc_last_error().  No C++ exception crosses the ABI.
+ *   - a context is bound to one CUDA device and is not thread-safe; distinct contexts are independent.
+ *   - "device" pointers are CUDA device pointers on the context's device; the library never owns
+ *     record or output memory (the caller allocates, e.g. with torch.empty).
+ *   - all device work is enqueued on the cudaStream_t passed as `void* stream` (NULL = legacy
+ *     default stream) and is asynchronous to the host unless stated otherwise.
+ */
+#ifndef SCGRHC_H_
+#define SCGRHC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCGRHC_ABI_VERSION 1
+#define SCGRHC_MAX_C 4          /* SCG channels per window (reference configs use 1..4) */
+#define SCGRHC_MAX_NSIG 64      /* signals per record row */
+#define SCGRHC_SAMPLE_FREQ 500  /* recordutil.py:19 */
+#define SCGRHC_FLAT_WIN 50      /* int(0.1*500), waveform_noise.py:7 */
+
+typedef enum {
+  SCGRHC_OK = 0,
+  SCGRHC_ERR_BAD_ARG = -1,
+  SCGRHC_ERR_MISSING_CHANNEL = -2, /* maps to ValueError from list.index, recordutil.py:117 */
+  SCGRHC_ERR_NONFINITE_RHC = -3,   /* maps to sklearn's ValueError, waveform_noise.py:32 */
+  SCGRHC_ERR_CUDA = -4,
+  SCGRHC_ERR_UNSUPPORTED = -5,
+  SCGRHC_ERR_NO_DEVICE = -6
+} scgrhc_status;
+
+/* reason bits written per candidate window (why has_noise() was true, waveform_noise.py:44-49) */
+#define SCGRHC_REASON_FLAT      1u  /* get_flat_lines non-empty  (>= 2 positions, waveform_noise.py:13-26) */
+#define SCGRHC_REASON_STRAIGHT  2u  /* R^2 > 0.8                 (waveform_noise.py:34) */
+#define SCGRHC_REASON_FLOOR     4u  /* a sample < min_RHC        (waveform_noise.py:38-40) */
+#define SCGRHC_REASON_NONFINITE 8u  /* NaN/Inf reached the regression -> reference raises */
+#define SCGRHC_REASON_AMBIGUOUS 16u /* |R^2 - 0.8| < 1e-12: closed form vs lstsq could disagree */
+
+/* job flags */
+#define SCGRHC_OUT_F64        1u  /* write fp64 windows instead of fp32 (torch.float32 at recordutil.py:53) */
+#define SCGRHC_PREDICATES_ONLY 2u /* keep/reason/minmax only, no window tensors (get_segments, pass A of global mode) */
+#define SCGRHC_USE_KEPT_LIST  4u  /* iterate kept_idx[0..n_items) instead of all candidates; skip predicates;
+                                     slot = list position (dense output).  Pass B of use_global_min_max. */
+#define SCGRHC_NORM_GLOBAL    8u  /* normalise with job->global_minmax instead of per-window pairs (recordutil.py:58-59) */
+#define SCGRHC_KEEP_ALL      16u  /* evaluate the predicates (reason bits) but keep and normalise every window:
+                                     SCGDataset(segments, ...) on caller-chosen segments, no has_noise, no error */
+
+/* One chamber interval of one record, in arena coordinates (recordutil.py:107-109,138-141). */
+typedef struct {
+  int64_t row0;   /* first arena row of the (clamped) interval: record base row + slice start */
+  int64_t cand0;  /* index of its first candidate window = exclusive prefix sum of n_win */
+  int32_t n_win;  /* L // W, recordutil.py:141 */
+  int32_t rec_id; /* caller's record number, reported back per kept window */
+} scgrhc_interval;
+
+typedef struct {
+  /* input records: (arena_rows, nsig) row-major fp64, like wfdb's p_signal (recordutil.py:118) */
+  const double* arena;          /* device */
+  int64_t arena_rows;
+  int64_t arena_capacity_bytes; /* bytes readable from `arena` (>= arena_rows*nsig*8) */
+  int32_t nsig;
+  int32_t W;                    /* window length in samples = int(segment_size*500), recordutil.py:136 */
+  int32_t C;                    /* number of SCG channels, len(params.in_channels) */
+  int32_t scg_cols[SCGRHC_MAX_C]; /* sig_name.index(name) per in_channel, recordutil.py:117 */
+  int32_t rhc_col;              /* sig_name.index('RHC_pressure'), recordutil.py:140 */
+  uint32_t flags;
+  const scgrhc_interval* intervals; /* device, sorted by cand0 */
+  int32_t n_intervals;
+  int32_t reserved0;
+  int64_t n_cand;               /* total candidate windows = sum n_win */
+  double min_rhc;               /* params.min_RHC, waveform_noise.py:39 */
+  double flat_threshold;        /* 1e-3, waveform_noise.py:6 */
+  double global_minmax[4];      /* scg_min, scg_max, rhc_min, rhc_max when SCGRHC_NORM_GLOBAL */
+  const int64_t* kept_list;     /* device, when SCGRHC_USE_KEPT_LIST */
+  int64_t n_items;              /* length of kept_list when SCGRHC_USE_KEPT_LIST */
+} scgrhc_job;
+
+typedef struct {
+  void* scg_out;     /* device (slots, C, W) fp32|fp64; slot = candidate index (or list position) */
+  void* rhc_out;     /* device (slots, 1, W) */
+  double* minmax;    /* device (n_cand, 4): scg_min, scg_max, rhc_min, rhc_max  (recordutil.py:58-59) */
+  uint8_t* keep;     /* device (n_cand): 1 = not has_noise */
+  uint8_t* reason;   /* device (n_cand): SCGRHC_REASON_* bits */
+  int32_t* cand_win; /* device (n_cand): i, the window number inside its interval (start_idx = i*W, recordutil.py:143) */
+  int32_t* cand_rec; /* device (n_cand): rec_id */
+} scgrhc_outputs;
+
+typedef struct {
+  int64_t* kept_idx;  /* device (n_cand): candidate indices of kept windows, ascending = reference order */
+  int64_t* start_idx; /* device (n_cand): per kept window, relative to its interval (recordutil.py:143) */
+  int64_t* stop_idx;  /* device (n_cand): start_idx + W (recordutil.py:144) */
+  int32_t* rec_id;    /* device (n_cand) */
+  int64_t* n_kept;    /* device (1) */
+} scgrhc_compact;
+
+typedef struct scgrhc_ctx scgrhc_ctx;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int scgrhc_abi_version(void);
+int scgrhc_ctx_create(int device, scgrhc_ctx** out);
+void scgrhc_ctx_destroy(scgrhc_ctx* ctx);
+const char* scgrhc_last_error(const scgrhc_ctx* ctx); /* ctx may be NULL: last create error */
+/* tuning knobs (0 = library default): CTAs per SM and bulk-copy stages per CTA of the window kernel */
+int scgrhc_ctx_set_tuning(scgrhc_ctx* ctx, int ctas_per_sm, int stages);
+int scgrhc_ctx_sm_count(const scgrhc_ctx* ctx);
+
+/* ---- host planner: recordutil.get_chamber_intervals + the window count of get_segments ------
+ * recordutil.py:104-109 — events in dict order with 'END' last, stable sort by time, every event
+ * but the last whose key prefix matched emits (int(t*500), int(t_next*500)), truncation toward
+ * zero; recordutil.py:118,141 — Python slice clamping against T rows, n_win = L // W.
+ * event_time[i] in seconds (double), event_match[i] != 0 iff key.split('_')[0] == chamber.
+ * Writes up to out_cap intervals (also the empty ones are skipped) and the raw (a,b) sample
+ * bounds of every matching event to bounds[2*k] (may be NULL).  cand_base seeds cand0. */
+int scgrhc_plan_record(const double* event_time, const uint8_t* event_match, int n_events,
+                       int64_t T, int32_t W, int64_t rec_base_row, int32_t rec_id, int64_t cand_base,
+                       scgrhc_interval* out, int out_cap, int* n_out, int64_t* n_cand,
+                       int64_t* bounds, int bounds_cap, int* n_bounds);
+
+/* ---- the hot path: has_noise + SCGDataset.init_segments fused (recordutil.py:141-148,55-66;
+ *      waveform_noise.py:6-49).  Asynchronous. */
+int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, const scgrhc_outputs* out, void* stream);
+
+/* ---- ordered list of kept windows (the order of the list get_segments returns, recordutil.py:148) */
+int scgrhc_compact_kept(scgrhc_ctx* ctx, const uint8_t* keep, const int32_t* cand_win, const int32_t* cand_rec,
+                        int64_t n_cand, int32_t W, const scgrhc_compact* out, void* stream);
+
+/* ---- get_global_minmax_vals over kept windows (recordutil.py:152-169): device reduction of the
+ *      (n_cand,4) pairs to mm_out[4] (device).  Cross-GPU: allreduce MIN of {min,-max} by the caller. */
+int scgrhc_global_minmax(scgrhc_ctx* ctx, const double* minmax, const uint8_t* keep, int64_t n_cand,
+                         double* mm_out, void* stream);
+
+/* ---- error word of the last process call: synchronises `stream`; returns SCGRHC_ERR_NONFINITE_RHC
+ *      and the first offending candidate when a non-finite RHC sample reached the regression. */
+int scgrhc_check_errors(scgrhc_ctx* ctx, void* stream, int64_t* first_bad_cand);
+
+/* ---- batch collate (default_collate of recordutil.py:198): out[b] = store[slot[b]] ---------- */
+int scgrhc_gather_windows(scgrhc_ctx* ctx, const void* store, const int64_t* slots, int64_t n,
+                          int64_t window_bytes, void* out, void* stream);
+
+/* ---- standalone predicate helpers for API parity of waveform_noise.get_flat_lines with
+ *      non-default arguments: flags[p] = (rolling range over m samples ending at p) < threshold */
+int scgrhc_rolling_range_lt(scgrhc_ctx* ctx, const double* y, int64_t n, int32_t m, double threshold,
+                            uint8_t* flags, void* stream);
+
+/* ---- synthetic cohort generator: records rec0..rec0+n_rec-1 of cohort `seed`,
+ *      each (T, nsig) fp64 row-major, written back to back into `out` (device). */
+int scgrhc_synth_records(scgrhc_ctx* ctx, uint64_t seed, int64_t rec0, int64_t n_rec, int64_t T,
+                         int32_t nsig, const int32_t* kinds, int32_t defect_scale, int32_t grid,
+                         double* out, void* stream);
+
+/* ---- diagnostics: compares the kernel's reciprocal-based division (Markstein correction) with
+ *      IEEE division on n hashed operand pairs; counts (device, 3 x uint64): fp64 mismatches,
+ *      mismatches after the fp32 cast, pairs evaluated.  mode 0: operands shaped like the
+ *      normalisation (0 <= a < d, d in [1e-4, 1e3]); mode 1: |exponents| up to 400. */
+int scgrhc_selftest_div(scgrhc_ctx* ctx, uint64_t seed, int64_t n, int32_t mode, uint64_t* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCGRHC_H_ */

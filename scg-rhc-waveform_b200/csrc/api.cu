@@ -1,0 +1,346 @@
+// C ABI of libscgrhc (declared in include/scgrhc.h): context, host planner, kernel launchers.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "window_kernel.cuh"
+
+using namespace scgrhc;
+
+struct scgrhc_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int ctas_per_sm = 0;  // 0 = from occupancy
+  int stages = 0;       // 0 = default
+  unsigned long long* err_dev = nullptr;  // 2 words
+  int* block_counts = nullptr;
+  long long* block_offsets = nullptr;
+  long long scan_cap = 0;
+  double* mm_partial = nullptr;
+  std::string last_error;
+};
+
+static std::string g_create_error;
+
+static int fail(scgrhc_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->last_error = buf; else g_create_error = buf;
+  return code;
+}
+#define CUDA_TRY(ctx, expr)                                                                         \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess) return fail(ctx, SCGRHC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" int scgrhc_abi_version(void) { return SCGRHC_ABI_VERSION; }
+
+extern "C" const char* scgrhc_last_error(const scgrhc_ctx* ctx) {
+  return ctx ? ctx->last_error.c_str() : g_create_error.c_str();
+}
+
+extern "C" int scgrhc_ctx_create(int device, scgrhc_ctx** out) {
+  if (!out) return fail(nullptr, SCGRHC_ERR_BAD_ARG, "scgrhc_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(nullptr, SCGRHC_ERR_NO_DEVICE, "no CUDA device available (libscgrhc has no CPU fallback)");
+  }
+  if (device < 0 || device >= n) return fail(nullptr, SCGRHC_ERR_BAD_ARG, "device %d out of range (0..%d)", device, n - 1);
+  scgrhc_ctx* ctx = new (std::nothrow) scgrhc_ctx();
+  if (!ctx) return fail(nullptr, SCGRHC_ERR_CUDA, "out of host memory");
+  ctx->device = device;
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    delete ctx;
+    return fail(nullptr, SCGRHC_ERR_UNSUPPORTED, "device %d is sm_%d%d; libscgrhc is built for sm_100a only", device, prop.major, prop.minor);
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(nullptr, cudaMalloc(&ctx->err_dev, 2 * sizeof(unsigned long long)));
+  CUDA_TRY(nullptr, cudaMalloc(&ctx->mm_partial, GMM_BLOCKS * 4 * sizeof(double)));
+  *out = ctx;
+  return SCGRHC_OK;
+}
+
+extern "C" void scgrhc_ctx_destroy(scgrhc_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaFree(ctx->err_dev);
+  cudaFree(ctx->mm_partial);
+  cudaFree(ctx->block_counts);
+  cudaFree(ctx->block_offsets);
+  delete ctx;
+}
+
+extern "C" int scgrhc_ctx_set_tuning(scgrhc_ctx* ctx, int ctas_per_sm, int stages) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (ctas_per_sm < 0 || ctas_per_sm > 32 || stages < 0 || stages > kMaxStages)
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "tuning out of range: ctas_per_sm=%d stages=%d", ctas_per_sm, stages);
+  ctx->ctas_per_sm = ctas_per_sm;
+  ctx->stages = stages;
+  return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_ctx_sm_count(const scgrhc_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+// ---- host planner (recordutil.py:104-109,118,141) -------------------------------------------------
+static int64_t py_trunc(double v) { return (int64_t)std::trunc(v); }
+
+// Python's slice(a, b).indices(T) for step 1.
+static void slice_indices(int64_t a, int64_t b, int64_t T, int64_t* lo, int64_t* hi) {
+  auto clamp = [T](int64_t v) {
+    if (v < 0) { v += T; if (v < 0) v = 0; }
+    else if (v > T) v = T;
+    return v;
+  };
+  *lo = clamp(a);
+  *hi = clamp(b);
+}
+
+extern "C" int scgrhc_plan_record(const double* event_time, const uint8_t* event_match, int n_events, int64_t T,
+                                  int32_t W, int64_t rec_base_row, int32_t rec_id, int64_t cand_base,
+                                  scgrhc_interval* out, int out_cap, int* n_out, int64_t* n_cand, int64_t* bounds,
+                                  int bounds_cap, int* n_bounds) {
+  if (!n_out || !n_cand || W <= 0 || T < 0 || n_events < 0 || (n_events && (!event_time || !event_match)))
+    return SCGRHC_ERR_BAD_ARG;
+  std::vector<int> order(n_events);
+  for (int i = 0; i < n_events; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return event_time[a] < event_time[b]; });
+  int k = 0, nb = 0;
+  int64_t cand = cand_base;
+  for (int i = 0; i + 1 < n_events; ++i) {
+    const int e = order[i];
+    if (!event_match[e]) continue;
+    const int64_t a = py_trunc(event_time[e] * (double)SCGRHC_SAMPLE_FREQ);
+    const int64_t b = py_trunc(event_time[order[i + 1]] * (double)SCGRHC_SAMPLE_FREQ);
+    if (bounds && nb < bounds_cap) { bounds[2 * nb] = a; bounds[2 * nb + 1] = b; }
+    ++nb;
+    int64_t lo, hi;
+    slice_indices(a, b, T, &lo, &hi);
+    const int64_t L = hi > lo ? hi - lo : 0;
+    const int64_t nw = L / W;
+    if (nw <= 0) continue;
+    if (nw > INT32_MAX) return SCGRHC_ERR_BAD_ARG;
+    if (out && k < out_cap) {
+      out[k].row0 = rec_base_row + lo;
+      out[k].cand0 = cand;
+      out[k].n_win = (int32_t)nw;
+      out[k].rec_id = rec_id;
+    }
+    ++k;
+    cand += nw;
+  }
+  *n_out = k;
+  *n_cand = cand - cand_base;
+  if (n_bounds) *n_bounds = nb;
+  if ((out && k > out_cap) || (bounds && nb > bounds_cap)) return SCGRHC_ERR_BAD_ARG;
+  return SCGRHC_OK;
+}
+
+// ---- hot path launcher -------------------------------------------------------------------------------
+template <int C, bool NSIG4, typename OutT, int R>
+static int launch_window(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
+  auto kern = window_kernel<C, NSIG4, OutT, R>;
+  const size_t smem = ((sizeof(Scratch<R>) + 127) & ~size_t(127)) + (size_t)P.stages * P.stage_elems * sizeof(double);
+  CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+  if (occ < 1) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "window of %d samples x %d signals does not fit in shared memory (%zu B/CTA)", P.job.W, P.job.nsig, smem);
+  if (ctx->ctas_per_sm > 0) occ = std::min(occ, ctx->ctas_per_sm);
+  long long grid = std::min<long long>(items, (long long)ctx->sm_count * occ);
+  kern<<<(unsigned)grid, NT, smem, st>>>(P);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
+template <int C, bool NSIG4, typename OutT>
+static int dispatch_r(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
+  if (P.job.W <= 6 * NT) return launch_window<C, NSIG4, OutT, 6>(ctx, P, items, st);
+  return launch_window<C, NSIG4, OutT, 8>(ctx, P, items, st);
+}
+template <int C, bool NSIG4>
+static int dispatch_out(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
+  if (P.job.flags & SCGRHC_OUT_F64) return dispatch_r<C, NSIG4, double>(ctx, P, items, st);
+  return dispatch_r<C, NSIG4, float>(ctx, P, items, st);
+}
+template <int C>
+static int dispatch_nsig(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
+  if (P.job.nsig == 4) return dispatch_out<C, true>(ctx, P, items, st);
+  return dispatch_out<C, false>(ctx, P, items, st);
+}
+
+extern "C" int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, const scgrhc_outputs* out, void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (!job || !out) return fail(ctx, SCGRHC_ERR_BAD_ARG, "job/out is NULL");
+  const scgrhc_job& J = *job;
+  const bool use_list = J.flags & SCGRHC_USE_KEPT_LIST;
+  const bool pred_only = J.flags & SCGRHC_PREDICATES_ONLY;
+  if (J.C < 1 || J.C > SCGRHC_MAX_C) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "C=%d SCG channels (supported 1..%d)", J.C, SCGRHC_MAX_C);
+  if (J.nsig < 1 || J.nsig > SCGRHC_MAX_NSIG) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "nsig=%d (supported 1..%d)", J.nsig, SCGRHC_MAX_NSIG);
+  if (J.W < 2 || J.W > 8 * NT) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "window of %d samples (supported 2..%d)", J.W, 8 * NT);
+  if (J.rhc_col < 0 || J.rhc_col >= J.nsig) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "RHC column %d outside 0..%d", J.rhc_col, J.nsig - 1);
+  for (int c = 0; c < J.C; ++c)
+    if (J.scg_cols[c] < 0 || J.scg_cols[c] >= J.nsig) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "SCG column %d outside 0..%d", J.scg_cols[c], J.nsig - 1);
+  if (J.n_cand < 0 || J.n_intervals < 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "negative counts");
+  if (J.arena_capacity_bytes < J.arena_rows * (int64_t)J.nsig * 8) return fail(ctx, SCGRHC_ERR_BAD_ARG, "arena_capacity_bytes smaller than the arena");
+  if ((reinterpret_cast<uintptr_t>(J.arena) & 15) != 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "arena must be 16-byte aligned");
+  const long long items = use_list ? J.n_items : J.n_cand;
+  if (use_list && pred_only) return fail(ctx, SCGRHC_ERR_BAD_ARG, "USE_KEPT_LIST and PREDICATES_ONLY are exclusive");
+  if (use_list && !J.kept_list && items) return fail(ctx, SCGRHC_ERR_BAD_ARG, "kept_list is NULL");
+  if (!use_list && (!out->keep || !out->reason || !out->minmax || !out->cand_win || !out->cand_rec) && items)
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "keep/reason/minmax/cand_win/cand_rec outputs are required");
+  if (use_list && !(J.flags & SCGRHC_NORM_GLOBAL) && !out->minmax && items) return fail(ctx, SCGRHC_ERR_BAD_ARG, "minmax input required");
+  if (!pred_only && (!out->scg_out || !out->rhc_out) && items) return fail(ctx, SCGRHC_ERR_BAD_ARG, "scg_out/rhc_out are required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->err_dev, 0, sizeof(unsigned long long), st));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->err_dev + 1, 0xFF, sizeof(unsigned long long), st));
+  if (items == 0) return SCGRHC_OK;
+  if (!J.intervals || J.n_intervals == 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "candidates without intervals");
+
+  KParams P;
+  P.job = J;
+  P.out = *out;
+  P.err = ctx->err_dev;
+  P.stages = ctx->stages > 0 ? ctx->stages : 2;
+  P.stage_elems = (int)(((long long)J.W * J.nsig + 2 + 1) & ~1LL);
+  P.arena_elems_cap = J.arena_capacity_bytes / 8;
+  switch (J.C) {
+    case 1: return dispatch_nsig<1>(ctx, P, items, st);
+    case 2: return dispatch_nsig<2>(ctx, P, items, st);
+    case 3: return dispatch_nsig<3>(ctx, P, items, st);
+    default: return dispatch_nsig<4>(ctx, P, items, st);
+  }
+}
+
+extern "C" int scgrhc_check_errors(scgrhc_ctx* ctx, void* stream, int64_t* first_bad_cand) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long h[2] = {0, 0};
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->err_dev, sizeof h, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  if (first_bad_cand) *first_bad_cand = (h[0] & 1ull) ? (int64_t)h[1] : -1;
+  if (h[0] & 1ull)
+    return fail(ctx, SCGRHC_ERR_NONFINITE_RHC, "Input y contains NaN. (candidate window %lld; waveform_noise.py:32)", (long long)h[1]);
+  return SCGRHC_OK;
+}
+
+// ---- ordered compaction ----------------------------------------------------------------------------
+static int ensure_scan(scgrhc_ctx* ctx, long long nblocks) {
+  if (nblocks <= ctx->scan_cap) return SCGRHC_OK;
+  cudaFree(ctx->block_counts);
+  cudaFree(ctx->block_offsets);
+  ctx->block_counts = nullptr; ctx->block_offsets = nullptr; ctx->scan_cap = 0;
+  const long long cap = std::max<long long>(nblocks, 1024);
+  CUDA_TRY(ctx, cudaMalloc(&ctx->block_counts, cap * sizeof(int)));
+  CUDA_TRY(ctx, cudaMalloc(&ctx->block_offsets, cap * sizeof(long long)));
+  ctx->scan_cap = cap;
+  return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_compact_kept(scgrhc_ctx* ctx, const uint8_t* keep, const int32_t* cand_win, const int32_t* cand_rec,
+                                   int64_t n_cand, int32_t W, const scgrhc_compact* out, void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (!out || !out->n_kept || n_cand < 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "compact: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n_cand == 0) { CUDA_TRY(ctx, cudaMemsetAsync(out->n_kept, 0, sizeof(int64_t), st)); return SCGRHC_OK; }
+  if (!keep || !out->kept_idx || (out->start_idx && (!cand_win || !out->stop_idx)) || (out->rec_id && !cand_rec))
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "compact: NULL array");
+  const long long nblocks = (n_cand + CTILE - 1) / CTILE;
+  if (nblocks > INT32_MAX) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "too many candidates");
+  int rc = ensure_scan(ctx, nblocks);
+  if (rc) return rc;
+  count_kept_kernel<<<(unsigned)nblocks, CB, 0, st>>>(keep, n_cand, ctx->block_counts);
+  scan_blocks_kernel<<<1, 1024, 0, st>>>(ctx->block_counts, (int)nblocks, ctx->block_offsets,
+                                         reinterpret_cast<long long*>(out->n_kept));
+  scatter_kept_kernel<<<(unsigned)nblocks, CB, 0, st>>>(keep, cand_win, cand_rec, n_cand, W, ctx->block_offsets, *out);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_global_minmax(scgrhc_ctx* ctx, const double* minmax, const uint8_t* keep, int64_t n_cand,
+                                    double* mm_out, void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (!mm_out || n_cand < 0 || (n_cand && (!minmax || !keep))) return fail(ctx, SCGRHC_ERR_BAD_ARG, "global_minmax: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int blocks = (int)std::min<long long>(GMM_BLOCKS, std::max<long long>(1, (n_cand + 255) / 256));
+  minmax_partial_kernel<<<blocks, 256, 0, st>>>(minmax, keep, n_cand, ctx->mm_partial);
+  minmax_final_kernel<<<1, 32, 0, st>>>(ctx->mm_partial, blocks, mm_out);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_gather_windows(scgrhc_ctx* ctx, const void* store, const int64_t* slots, int64_t n,
+                                     int64_t window_bytes, void* out, void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (n < 0 || window_bytes <= 0 || (window_bytes & 7) || (n && (!store || !slots || !out)))
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "gather: bad arguments (window_bytes must be a positive multiple of 8)");
+  if (n == 0) return SCGRHC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const unsigned grid = (unsigned)std::min<long long>(n, (long long)ctx->sm_count * 8);
+  gather_windows_kernel<<<grid, 256, 0, st>>>(static_cast<const unsigned char*>(store),
+                                              reinterpret_cast<const long long*>(slots), n, window_bytes,
+                                              static_cast<unsigned char*>(out));
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_rolling_range_lt(scgrhc_ctx* ctx, const double* y, int64_t n, int32_t m, double threshold,
+                                       uint8_t* flags, void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (n < 0 || m < 1 || (n && (!y || !flags))) return fail(ctx, SCGRHC_ERR_BAD_ARG, "rolling_range_lt: bad arguments");
+  if (n == 0) return SCGRHC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  rolling_range_lt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y, n, m, threshold, flags);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_synth_records(scgrhc_ctx* ctx, uint64_t seed, int64_t rec0, int64_t n_rec, int64_t T, int32_t nsig,
+                                    const int32_t* kinds, int32_t defect_scale, int32_t grid, double* out, void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (n_rec < 0 || T < 0 || nsig < 1 || nsig > SCGRHC_MAX_NSIG || !kinds || grid < 1 || (n_rec * T && !out))
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "synth: bad arguments");
+  if (n_rec * T == 0) return SCGRHC_OK;
+  SynthParams P;
+  P.seed = seed; P.rec0 = rec0; P.n_rec = n_rec; P.T = T; P.nsig = nsig; P.defect_scale = defect_scale; P.grid = grid;
+  for (int i = 0; i < SCGRHC_MAX_NSIG; ++i) P.kinds[i] = i < nsig ? kinds[i] : 0;
+  P.out = out;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const long long total = n_rec * T * nsig;
+  const unsigned gridDim = (unsigned)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16);
+  synth_kernel<<<gridDim, 256, 0, st>>>(P);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_selftest_div(scgrhc_ctx* ctx, uint64_t seed, int64_t n, int32_t mode, uint64_t* counts, void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (n < 0 || !counts) return fail(ctx, SCGRHC_ERR_BAD_ARG, "selftest_div: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, 3 * sizeof(uint64_t), st));
+  if (n == 0) return SCGRHC_OK;
+  selftest_div_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(seed, n, mode, reinterpret_cast<unsigned long long*>(counts));
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}

@@ -1,0 +1,292 @@
+// Small kernels around the hot path: ordered compaction of kept windows, dataset-global min/max,
+// batch gather, the standalone rolling-range predicate and the synthetic cohort generator.
+#pragma once
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace scgrhc {
+
+// ---- ordered compaction (the order of the list get_segments returns, recordutil.py:148) ---------
+constexpr int CB = 256;              // threads per block
+constexpr int CITEMS = 8;            // flags per thread
+constexpr int CTILE = CB * CITEMS;   // flags per block
+
+__global__ void __launch_bounds__(CB) count_kept_kernel(const uint8_t* __restrict__ keep, long long n,
+                                                        int* __restrict__ block_counts) {
+  const long long base = (long long)blockIdx.x * CTILE;
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < CITEMS; ++i) {
+    const long long j = base + (long long)i * CB + threadIdx.x;
+    if (j < n) c += keep[j] ? 1 : 0;
+  }
+  __shared__ int ws[CB / 32];
+  for (int m = 16; m; m >>= 1) c += __shfl_xor_sync(kFull, c, m);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < CB / 32; ++w) t += ws[w];
+    block_counts[blockIdx.x] = t;
+  }
+}
+
+// single block: exclusive scan of block_counts -> block_offsets, total -> n_kept
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(const int* __restrict__ block_counts, int nblocks,
+                                                           long long* __restrict__ block_offsets,
+                                                           long long* __restrict__ n_kept) {
+  __shared__ long long ws[32];
+  __shared__ long long carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int j = base + threadIdx.x;
+    const long long v = j < nblocks ? block_counts[j] : 0;
+    long long incl = v;
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long o = __shfl_up_sync(kFull, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      long long w = ws[lane];
+      for (int d = 1; d < 32; d <<= 1) {
+        const long long o = __shfl_up_sync(kFull, w, d);
+        if (lane >= d) w += o;
+      }
+      ws[lane] = w;
+    }
+    __syncthreads();
+    const long long carry = carry_s;
+    const long long warp_off = warp ? ws[warp - 1] : 0;
+    if (j < nblocks) block_offsets[j] = carry + warp_off + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_off + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_kept = carry_s;
+}
+
+__global__ void __launch_bounds__(CB) scatter_kept_kernel(const uint8_t* __restrict__ keep,
+                                                          const int32_t* __restrict__ cand_win,
+                                                          const int32_t* __restrict__ cand_rec, long long n, int W,
+                                                          const long long* __restrict__ block_offsets,
+                                                          scgrhc_compact out) {
+  // thread t owns CITEMS consecutive flags so that ranks follow candidate order
+  const long long base = (long long)blockIdx.x * CTILE + (long long)threadIdx.x * CITEMS;
+  int flags[CITEMS], c = 0;
+#pragma unroll
+  for (int i = 0; i < CITEMS; ++i) {
+    const long long j = base + i;
+    flags[i] = (j < n && keep[j]) ? 1 : 0;
+    c += flags[i];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = c;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(kFull, incl, d);
+    if (lane >= d) incl += o;
+  }
+  __shared__ int ws[CB / 32];
+  if (lane == 31) ws[warp] = incl;
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += ws[w];
+  long long r = block_offsets[blockIdx.x] + woff + incl - c;
+#pragma unroll
+  for (int i = 0; i < CITEMS; ++i) {
+    if (flags[i]) {
+      const long long j = base + i;
+      out.kept_idx[r] = j;
+      if (out.start_idx) {
+        const long long st = (long long)cand_win[j] * W;
+        out.start_idx[r] = st;
+        out.stop_idx[r] = st + W;
+      }
+      if (out.rec_id) out.rec_id[r] = cand_rec[j];
+      ++r;
+    }
+  }
+}
+
+// ---- get_global_minmax_vals (recordutil.py:152-169): min/max over kept windows' pairs -----------
+constexpr int GMM_BLOCKS = 296;
+__global__ void __launch_bounds__(256) minmax_partial_kernel(const double* __restrict__ minmax,
+                                                             const uint8_t* __restrict__ keep, long long n,
+                                                             double* __restrict__ partial /* (grid,4) */) {
+  double v0 = CUDART_INF, v1 = -CUDART_INF, v2 = CUDART_INF, v3 = -CUDART_INF;
+  bool nan_s = false;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    if (keep[j]) {
+      const double2 a = reinterpret_cast<const double2*>(minmax + 4 * j)[0];
+      const double2 b = reinterpret_cast<const double2*>(minmax + 4 * j)[1];
+      nan_s |= (a.x != a.x);
+      v0 = fmin(v0, a.x); v1 = fmax(v1, a.y); v2 = fmin(v2, b.x); v3 = fmax(v3, b.y);
+    }
+  }
+  v0 = warp_min(v0); v1 = warp_max(v1); v2 = warp_min(v2); v3 = warp_max(v3);
+  const int any_nan = __syncthreads_or(nan_s ? 1 : 0);
+  __shared__ double ws[8][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { ws[warp][0] = v0; ws[warp][1] = v1; ws[warp][2] = v2; ws[warp][3] = v3; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      v0 = fmin(v0, ws[w][0]); v1 = fmax(v1, ws[w][1]); v2 = fmin(v2, ws[w][2]); v3 = fmax(v3, ws[w][3]);
+    }
+    if (any_nan) v0 = v1 = __longlong_as_double(0x7ff8000000000000LL);
+    partial[4 * blockIdx.x + 0] = v0; partial[4 * blockIdx.x + 1] = v1;
+    partial[4 * blockIdx.x + 2] = v2; partial[4 * blockIdx.x + 3] = v3;
+  }
+}
+__global__ void minmax_final_kernel(const double* __restrict__ partial, int nparts, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double v0 = CUDART_INF, v1 = -CUDART_INF, v2 = CUDART_INF, v3 = -CUDART_INF;
+  bool nan_s = false;
+  for (int p = 0; p < nparts; ++p) {
+    const double a = partial[4 * p];
+    nan_s |= (a != a);
+    v0 = fmin(v0, a); v1 = fmax(v1, partial[4 * p + 1]);
+    v2 = fmin(v2, partial[4 * p + 2]); v3 = fmax(v3, partial[4 * p + 3]);
+  }
+  if (nan_s) v0 = v1 = __longlong_as_double(0x7ff8000000000000LL);
+  out[0] = v0; out[1] = v1; out[2] = v2; out[3] = v3;
+}
+
+// ---- batch collate: out[b] = store[slot[b]], window_bytes a multiple of 8 -------------------------
+__global__ void __launch_bounds__(256) gather_windows_kernel(const unsigned char* __restrict__ store,
+                                                             const long long* __restrict__ slots, long long n,
+                                                             long long window_bytes, unsigned char* __restrict__ out) {
+  const long long words = window_bytes >> 3;
+  for (long long b = blockIdx.x; b < n; b += gridDim.x) {
+    const uint2* src = reinterpret_cast<const uint2*>(store + slots[b] * window_bytes);
+    uint2* dst = reinterpret_cast<uint2*>(out + b * window_bytes);
+    for (long long i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldcs(src + i);
+  }
+}
+
+// ---- standalone rolling range (API parity of get_flat_lines with non-default arguments) ------------
+__global__ void rolling_range_lt_kernel(const double* __restrict__ y, long long n, int m, double thr,
+                                        uint8_t* __restrict__ flags) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  uint8_t f = 0;
+  if (p >= m - 1) {
+    double mx = -CUDART_INF, mn = CUDART_INF;
+    bool bad = false;
+    for (int i = 0; i < m; ++i) {
+      const double v = y[p - i];
+      bad |= (v != v);
+      mx = fmax(mx, v); mn = fmin(mn, v);
+    }
+    f = (!bad && (__dsub_rn(mx, mn) < thr)) ? 1 : 0;
+  }
+  flags[p] = f;
+}
+
+// ---- Markstein division self-test --------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  unsigned long long z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// ---- synthetic cohort generator; bit-identical twin of oracle/synth_ref.py ------------------------
+struct SynthParams {
+  unsigned long long seed;
+  long long rec0, n_rec, T;
+  int nsig, defect_scale, grid;
+  int kinds[SCGRHC_MAX_NSIG];
+  double* out;
+};
+
+__device__ __forceinline__ unsigned long long syn_h(unsigned long long key, unsigned stream, unsigned long long idx) {
+  return mix64(key ^ ((unsigned long long)stream << 48) ^ idx);
+}
+__device__ __forceinline__ double syn_u01(unsigned long long h) { return (double)(h >> 11) * 0x1p-53; }
+__device__ __forceinline__ double syn_noise(unsigned long long key, int kind, long long t) {
+  const unsigned long long h = syn_h(key, 16 + kind, (unsigned long long)t);
+  const long long s = (long long)((h & 0xFFFF) + ((h >> 16) & 0xFFFF) + ((h >> 32) & 0xFFFF) + (h >> 48));
+  return __dmul_rn((double)(s - 131070), 2.6429e-05);
+}
+__device__ __forceinline__ double syn_shape(unsigned long long phase) {
+  const double p = (double)phase * 0x1p-32;
+  const double u = __dadd_rn(__dmul_rn(2.0, p), -1.0);
+  return __dmul_rn(4.0, __dmul_rn(u, __dadd_rn(1.0, -fabs(u))));
+}
+__device__ __forceinline__ unsigned long long syn_phase(unsigned long long ph0, long long t, unsigned long long step) {
+  return (ph0 + (unsigned long long)t * step) & 0xFFFFFFFFull;
+}
+__device__ __forceinline__ double syn_rhc_base(unsigned long long key, unsigned long long finc, long long t) {
+  const unsigned long long ph1 = syn_phase(syn_h(key, 0, 1 + 3) & 0xFFFFFFFFull, t, finc);
+  const unsigned long long ph2 = (ph1 * 2ull + 0x14000000ull) & 0xFFFFFFFFull;
+  const double s1 = syn_shape(ph1), s2 = syn_shape(ph2), n = syn_noise(key, 3, t);
+  return __dadd_rn(__dadd_rn(__dadd_rn(25.0, __dmul_rn(12.0, s1)), __dmul_rn(3.0, s2)), __dmul_rn(0.3, n));
+}
+
+__device__ double syn_channel(unsigned long long key, unsigned long long finc, int kind, long long t, int defect_scale,
+                              int grid) {
+  if (kind >= 0 && kind <= 2) {
+    const unsigned long long mult = kind == 0 ? 9 : (kind == 1 ? 13 : 17);
+    const unsigned long long ph = syn_phase(syn_h(key, 0, 1 + kind) & 0xFFFFFFFFull, t, finc * mult);
+    return __dadd_rn(__dmul_rn(0.02, syn_shape(ph)), __dmul_rn(0.005, syn_noise(key, kind, t)));
+  }
+  if (kind == 4) {
+    const unsigned long long ph = syn_phase(syn_h(key, 0, 1 + 4) & 0xFFFFFFFFull, t, finc);
+    const double s = syn_shape(ph);
+    return __dadd_rn(__dmul_rn(0.8, __dmul_rn(s, fabs(s))), __dmul_rn(0.02, syn_noise(key, 4, t)));
+  }
+  if (kind != 3) return __dmul_rn(0.1, syn_noise(key, kind, t));
+  double y = syn_rhc_base(key, finc, t);
+  if (defect_scale <= 0) return y;
+  const long long j = t / grid;
+  const long long tp = t - j * grid;
+  const unsigned long long d = syn_h(key, 2, (unsigned long long)j);
+  const int r = (int)(d % 10000ull);
+  const int c0 = 500 * defect_scale / 16, c1 = 1000 * defect_scale / 16, c2 = 1500 * defect_scale / 16,
+            c3 = 2000 * defect_scale / 16, c4 = 2300 * defect_scale / 16, c5 = 2600 * defect_scale / 16;
+  if (r >= c5) return y;
+  const int sel = (int)((d >> 8) & 3ull);
+  const long long a = 100 + (long long)((d >> 16) % 400ull);
+  const double tpf = (double)tp;
+  if (r < c0) {
+    const int L = sel == 0 ? 49 : (sel == 1 ? 50 : (sel == 2 ? 51 : 200));
+    if (tp >= a && tp < a + L) y = syn_rhc_base(key, finc, j * grid + a);
+  } else if (r < c1) {
+    y = __dadd_rn(__dadd_rn(10.0, __dmul_rn(0.04, tpf)), __dmul_rn(0.05, syn_noise(key, 3, t)));
+  } else if (r < c2) {
+    if (tp >= 300 && tp < 310) y = -60.0;
+  } else if (r < c3) {
+    if (tp == 375) y = -50.0;
+  } else if (r < c4) {
+    const double A = __dadd_rn(1.5, __dmul_rn(1.5, syn_u01(syn_h(key, 3, (unsigned long long)j))));
+    y = __dadd_rn(__dadd_rn(5.0, __dmul_rn(0.02, tpf)), __dmul_rn(A, syn_noise(key, 3, t)));
+  } else {
+    if (tp >= a && tp < a + 120) {
+      const double amp = __dadd_rn(0.6e-3, __dmul_rn(0.8e-3, syn_u01(syn_h(key, 3, (unsigned long long)j))));
+      y = __dadd_rn(syn_rhc_base(key, finc, j * grid + a), __dmul_rn(amp, syn_u01(syn_h(key, 4, (unsigned long long)t))));
+    }
+  }
+  return y;
+}
+
+__global__ void __launch_bounds__(256) synth_kernel(const __grid_constant__ SynthParams P) {
+  const long long total = P.n_rec * P.T * P.nsig;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % P.nsig);
+    const long long row = e / P.nsig;
+    const long long rec = row / P.T;
+    const long long t = row - rec * P.T;
+    const unsigned long long key = mix64(mix64(P.seed) ^ ((unsigned long long)(P.rec0 + rec) * 0xD1342543DE82EF95ull));
+    const unsigned long long finc = 7730941ull + syn_h(key, 0, 0) % 7730942ull;
+    P.out[e] = syn_channel(key, finc, P.kinds[ch], t, P.defect_scale, P.grid);
+  }
+}
+
+}  // namespace scgrhc

@@ -1,0 +1,241 @@
+"""Host side of the hot path: planning (which windows exist) and driving the device ops.
+
+  plan_record / plan_cohort   recordutil.get_chamber_intervals + window enumeration of get_segments
+                              (recordutil.py:93-110,138-146), via the C planner scgrhc_plan_record
+  prepare_windows             has_noise + SCGDataset.init_segments for every candidate window of a
+                              device-resident cohort (recordutil.py:141-148,55-66,152-169)
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from datetime import datetime
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import ops
+
+SAMPLE_FREQ = 500
+FLAT_THRESHOLD = 1e-3
+RHC_NAME = 'RHC_pressure'
+
+INTERVAL_DTYPE = np.dtype([('row0', '<i8'), ('cand0', '<i8'), ('n_win', '<i4'), ('rec_id', '<i4')])
+
+
+def event_table(meta, chamber):
+  """Event times in dict order with 'END' appended (recordutil.py:100-104) and the per-event
+  chamber match ``key.split('_')[0] == chamber`` (:108).  None when ChamEvents_in_s is not a dict
+  (:103 -> no intervals)."""
+  t0 = datetime.strptime(meta['MacStTime'].split()[1], '%H:%M:%S')
+  t1 = datetime.strptime(meta['MacEndTime'].split()[1], '%H:%M:%S')
+  events = meta['ChamEvents_in_s']
+  if not isinstance(events, dict):
+    return None
+  events = dict(events)
+  events['END'] = (t1 - t0).total_seconds()
+  keys = list(events.keys())
+  times = np.array([float(events[k]) for k in keys], dtype=np.float64)
+  match = np.array([k.split('_')[0] == chamber for k in keys], dtype=np.uint8)
+  return times, match
+
+
+def plan_record(meta, chamber, T, W, rec_base_row=0, rec_id=0, cand_base=0):
+  """(intervals structured array, n_cand, bounds) for one record via the C planner."""
+  tab = event_table(meta, chamber)
+  if tab is None or len(tab[0]) < 2:
+    return np.zeros(0, dtype=INTERVAL_DTYPE), 0, []
+  times, match = tab
+  n = len(times)
+  out = (N.Interval * n)()
+  bounds = (C.c_int64 * (2 * n))()
+  n_out, n_b, n_cand = C.c_int(0), C.c_int(0), C.c_int64(0)
+  rc = N.lib().scgrhc_plan_record(times.ctypes.data_as(C.POINTER(C.c_double)),
+                                  match.ctypes.data_as(C.POINTER(C.c_uint8)), n, int(T), int(W),
+                                  int(rec_base_row), int(rec_id), int(cand_base), out, n,
+                                  C.byref(n_out), C.byref(n_cand), bounds, n, C.byref(n_b))
+  if rc != N.OK:
+    raise N.ScgrhcError(rc, 'scgrhc_plan_record failed')
+  iv = np.frombuffer(out, dtype=INTERVAL_DTYPE, count=n_out.value).copy()
+  b = [(bounds[2 * k], bounds[2 * k + 1]) for k in range(n_b.value)]
+  return iv, n_cand.value, b
+
+
+@dataclass
+class Plan:
+  """Candidate windows of a cohort laid out in one (rows, nsig) arena."""
+  intervals: np.ndarray            # INTERVAL_DTYPE, cand0 ascending
+  n_cand: int
+  W: int
+  record_names: List[str] = field(default_factory=list)
+  _dev: Optional[torch.Tensor] = None
+
+  def device_intervals(self, device):
+    if self._dev is None or self._dev.device != torch.device(device):
+      host = torch.from_numpy(self.intervals.view(np.int64).reshape(-1, 3).copy()) if len(self.intervals) else \
+          torch.zeros((0, 3), dtype=torch.int64)
+      self._dev = host.to(device)
+    return self._dev
+
+
+def plan_cohort(metas, chamber, T_rows, W, record_names=None):
+  """Plan for records stored back to back in the arena; ``T_rows[r]`` rows each."""
+  ivs, base, cand = [], 0, 0
+  for r, meta in enumerate(metas):
+    iv, n, _ = plan_record(meta, chamber, T_rows[r], W, base, r, cand)
+    ivs.append(iv)
+    base += int(T_rows[r])
+    cand += n
+  iv = np.concatenate(ivs) if ivs else np.zeros(0, dtype=INTERVAL_DTYPE)
+  return Plan(iv, cand, W, list(record_names) if record_names is not None else [])
+
+
+def plan_uniform(meta, chamber, T, W, n_rec, rec0=0):
+  """Every record shares one side-car (synthetic cohorts): plan record 0 in C, replicate with offsets."""
+  iv0, n0, _ = plan_record(meta, chamber, T, W, 0, 0, 0)
+  k = len(iv0)
+  iv = np.tile(iv0, n_rec)
+  r = np.repeat(np.arange(n_rec, dtype=np.int64), k)
+  iv['row0'] += r * T
+  iv['cand0'] += r * n0
+  iv['rec_id'] = (r + rec0).astype(np.int32)
+  return Plan(iv, n0 * n_rec, W)
+
+
+@dataclass
+class WindowStore:
+  """Device-resident result of the hot path.  Window tensors are *slot*-addressed: slot == candidate
+  index when ``dense`` is False (rejected candidates leave unwritten holes), list position when True.
+  ``kept_idx`` lists the kept candidates in the reference's order."""
+  scg: Optional[torch.Tensor]        # (slots, C, W)
+  rhc: Optional[torch.Tensor]        # (slots, 1, W)
+  minmax: torch.Tensor               # (n_cand, 4) fp64: scg_min, scg_max, rhc_min, rhc_max
+  keep: torch.Tensor                 # (n_cand,) uint8
+  reason: torch.Tensor               # (n_cand,) uint8
+  kept_idx: torch.Tensor             # (n_kept,) int64
+  start_idx: torch.Tensor            # (n_kept,) int64, relative to the interval (recordutil.py:143)
+  stop_idx: torch.Tensor             # (n_kept,) int64
+  rec_id: torch.Tensor               # (n_kept,) int32
+  n_kept: int
+  n_cand: int
+  dense: bool
+  global_minmax: Optional[torch.Tensor] = None   # (4,) fp64 when use_global_min_max
+
+  def slots(self):
+    return torch.arange(self.n_kept, device=self.kept_idx.device) if self.dense else self.kept_idx
+
+  def kept_minmax(self):
+    if self.global_minmax is not None:
+      return self.global_minmax.unsqueeze(0).expand(self.n_kept, 4)
+    return self.minmax[self.kept_idx]
+
+  def gather(self, positions):
+    """(scg, rhc) of the kept windows at list positions ``positions`` (int64 device tensor)."""
+    slots = positions if self.dense else self.kept_idx[positions]
+    n = slots.numel()
+    scg = torch.empty((n,) + tuple(self.scg.shape[1:]), dtype=self.scg.dtype, device=self.scg.device)
+    rhc = torch.empty((n,) + tuple(self.rhc.shape[1:]), dtype=self.rhc.dtype, device=self.rhc.device)
+    if n:
+      ops.gather_windows(self.scg, slots.contiguous(), scg)
+      ops.gather_windows(self.rhc, slots.contiguous(), rhc)
+    return scg, rhc
+
+  def materialise(self):
+    """Dense (n_kept, C, W) / (n_kept, 1, W) tensors in the reference's order."""
+    if self.dense:
+      return self.scg[:self.n_kept], self.rhc[:self.n_kept]
+    return self.gather(torch.arange(self.n_kept, device=self.kept_idx.device))
+
+
+def resolve_columns(sig_name, in_channels):
+  """`sig_name.index(name)` for every channel (recordutil.py:117); ValueError if absent, as there."""
+  sig_name = list(sig_name)
+  return [sig_name.index(n) for n in in_channels], sig_name.index(RHC_NAME)
+
+
+def prepare_windows(arena, plan, scg_cols, rhc_col, min_rhc, use_global_min_max=False, out_dtype=torch.float32,
+                    predicates_only=False, keep_all=False, flat_threshold=FLAT_THRESHOLD, group=None,
+                    check=True, buffers=None):
+  """Run the hot path over every candidate window of ``plan``.
+
+  Local normalisation (default): ONE fused kernel pass — predicates, min/max, normalise, transpose,
+  cast — then the ordered compaction of the keep flags.  ``use_global_min_max``: pass A (predicates
+  + per-window pairs), device reduction (+ MIN all-reduce of {min, -max} over ``group`` when
+  torch.distributed is initialised, recordutil.py:152-169 seen across shards), pass B over the kept
+  list writing dense outputs.
+  """
+  if not arena.is_cuda:
+    raise RuntimeError('prepare_windows needs a CUDA arena (no CPU fallback)')
+  dev = arena.device
+  n, W, Cn = plan.n_cand, plan.W, len(scg_cols)
+  iv = plan.device_intervals(dev)
+  f64 = out_dtype == torch.float64
+  base_flags = (N.OUT_F64 if f64 else 0) | (N.KEEP_ALL if keep_all else 0)
+  b = buffers or {}
+
+  def buf(name, shape, dtype):
+    t = b.get(name)
+    if t is None or t.shape != torch.Size(shape) or t.dtype != dtype:
+      t = torch.empty(shape, dtype=dtype, device=dev)
+      if buffers is not None:
+        buffers[name] = t
+    return t
+
+  minmax = buf('minmax', (n, 4), torch.float64)
+  keep = buf('keep', (n,), torch.uint8)
+  reason = buf('reason', (n,), torch.uint8)
+  cand_win = buf('cand_win', (n,), torch.int32)
+  cand_rec = buf('cand_rec', (n,), torch.int32)
+  kept_idx = buf('kept_idx', (n,), torch.int64)
+  start_idx = buf('start_idx', (n,), torch.int64)
+  stop_idx = buf('stop_idx', (n,), torch.int64)
+  rec_id = buf('rec_id', (n,), torch.int32)
+  n_kept_t = buf('n_kept', (1,), torch.int64)
+  two_pass = use_global_min_max and not predicates_only
+  scg = rhc = None
+  if not predicates_only and not two_pass:
+    scg = buf('scg', (n, Cn, W), out_dtype)
+    rhc = buf('rhc', (n, 1, W), out_dtype)
+  flags = base_flags | (N.PREDICATES_ONLY if (predicates_only or two_pass) else 0)
+  ops.process_windows(arena, iv, n, W, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
+                      [0.0] * 4, None, 0, scg, rhc, minmax, keep, reason, cand_win, cand_rec)
+  ops.compact_kept(keep, cand_win, cand_rec, n, W, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
+  gmm = None
+  if use_global_min_max:
+    gmm = buf('gmm', (4,), torch.float64)
+    ops.global_minmax(minmax, keep, n, gmm)
+    gmm = allreduce_minmax(gmm, group)
+  if check:
+    ops.check_errors(dev.index)
+  n_kept = int(n_kept_t.item())
+  dense = False
+  if two_pass:
+    scg = buf('scg', (n_kept, Cn, W), out_dtype)
+    rhc = buf('rhc', (n_kept, 1, W), out_dtype)
+    if n_kept:
+      ops.process_windows(arena, iv, n, W, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold),
+                          base_flags | N.USE_KEPT_LIST | N.NORM_GLOBAL, gmm.cpu().tolist(), kept_idx, n_kept,
+                          scg, rhc, minmax, None, None, None, None)
+    dense = True
+  return WindowStore(scg, rhc, minmax, keep, reason, kept_idx[:n_kept], start_idx[:n_kept], stop_idx[:n_kept],
+                     rec_id[:n_kept], n_kept, n, dense, gmm)
+
+
+def allreduce_minmax(gmm, group=None):
+  """Dataset-level (scg_min, scg_max, rhc_min, rhc_max) across record shards: one MIN all-reduce of
+  {min, -max} (exact and order independent, so bit-identical to the unsharded reference value).
+  A rank whose shard kept nothing contributes (+inf, -inf)."""
+  import torch.distributed as dist
+  if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    return gmm
+  sign = torch.tensor([1.0, -1.0, 1.0, -1.0], dtype=gmm.dtype, device=gmm.device)
+  v = gmm * sign
+  dist.all_reduce(v, op=dist.ReduceOp.MIN, group=group)
+  return v * sign
+
+
+def shard_records(n_rec, rank, world):
+  """Contiguous block of record indices owned by ``rank`` (records are independent, recordutil.py:131-132)."""
+  lo = n_rec * rank // world
+  hi = n_rec * (rank + 1) // world
+  return lo, hi

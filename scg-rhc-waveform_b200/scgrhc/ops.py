@@ -1,0 +1,189 @@
+"""PyTorch custom ops (namespace ``scgrhc``) over the C ABI of libscgrhc.so.
+
+Only CUDA implementations are registered: calling an op on CPU tensors raises, there is no
+fallback.  torch supplies device memory and the current stream; all arithmetic is in the library.
+"""
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _native as N
+
+_ctx = {}
+
+
+def ctx(device_index):
+  """One library context per CUDA device (created on first use)."""
+  c = _ctx.get(device_index)
+  if c is None:
+    L = N.lib()
+    h = C.c_void_p()
+    rc = L.scgrhc_ctx_create(int(device_index), C.byref(h))
+    if rc != N.OK:
+      raise N.ScgrhcError(rc, (L.scgrhc_last_error(None) or b'').decode())
+    c = _ctx[device_index] = h
+  return c
+
+
+def set_tuning(device_index, ctas_per_sm=0, stages=0):
+  N.check(ctx(device_index), N.lib().scgrhc_ctx_set_tuning(ctx(device_index), int(ctas_per_sm), int(stages)))
+
+
+def sm_count(device_index):
+  return N.lib().scgrhc_ctx_sm_count(ctx(device_index))
+
+
+def _dev(t):
+  if not t.is_cuda:
+    raise RuntimeError('scgrhc ops need CUDA tensors (no CPU fallback)')
+  return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _stream(dev):
+  return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t):
+  return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _contig(t, dtype, name):
+  if t is None:
+    return
+  if t.dtype != dtype or not t.is_contiguous():
+    raise ValueError('%s must be a contiguous %s tensor' % (name, dtype))
+
+
+@torch.library.custom_op('scgrhc::process_windows',
+                         mutates_args=('scg_out', 'rhc_out', 'minmax', 'keep', 'reason', 'cand_win', 'cand_rec'),
+                         device_types='cuda')
+def process_windows(arena: Tensor, intervals: Tensor, n_cand: int, W: int, scg_cols: Sequence[int], rhc_col: int,
+                    min_rhc: float, flat_threshold: float, flags: int, global_minmax: Sequence[float],
+                    kept_list: Optional[Tensor], n_items: int, scg_out: Optional[Tensor], rhc_out: Optional[Tensor],
+                    minmax: Optional[Tensor], keep: Optional[Tensor], reason: Optional[Tensor],
+                    cand_win: Optional[Tensor], cand_rec: Optional[Tensor]) -> None:
+  """has_noise + SCGDataset.init_segments fused (recordutil.py:141-148,55-66; waveform_noise.py:6-49)."""
+  dev = _dev(arena)
+  if arena.dim() != 2:
+    raise ValueError('arena must be (rows, nsig)')
+  _contig(arena, torch.float64, 'arena')
+  _contig(intervals, torch.int64, 'intervals')
+  out_dtype = torch.float64 if flags & N.OUT_F64 else torch.float32
+  _contig(scg_out, out_dtype, 'scg_out'); _contig(rhc_out, out_dtype, 'rhc_out')
+  _contig(minmax, torch.float64, 'minmax'); _contig(keep, torch.uint8, 'keep'); _contig(reason, torch.uint8, 'reason')
+  _contig(cand_win, torch.int32, 'cand_win'); _contig(cand_rec, torch.int32, 'cand_rec')
+  _contig(kept_list, torch.int64, 'kept_list')
+  if len(scg_cols) > N.MAX_C:
+    raise N.ScgrhcError(N.ERR_UNSUPPORTED, 'at most %d SCG channels' % N.MAX_C)
+  j = N.Job()
+  j.arena = arena.data_ptr()
+  j.arena_rows = arena.shape[0]
+  j.arena_capacity_bytes = arena.numel() * 8
+  j.nsig = arena.shape[1]
+  j.W = W
+  j.C = len(scg_cols)
+  for i, c in enumerate(scg_cols):
+    j.scg_cols[i] = c
+  j.rhc_col = rhc_col
+  j.flags = flags
+  j.intervals = intervals.data_ptr()
+  j.n_intervals = intervals.shape[0]
+  j.n_cand = n_cand
+  j.min_rhc = min_rhc
+  j.flat_threshold = flat_threshold
+  for i in range(4):
+    j.global_minmax[i] = global_minmax[i] if len(global_minmax) == 4 else 0.0
+  j.kept_list = kept_list.data_ptr() if kept_list is not None else None
+  j.n_items = n_items
+  slots = n_items if flags & N.USE_KEPT_LIST else n_cand
+  if not flags & N.PREDICATES_ONLY and slots:
+    if scg_out is None or rhc_out is None or scg_out.numel() < slots * j.C * W or rhc_out.numel() < slots * W:
+      raise ValueError('scg_out/rhc_out too small for %d slots' % slots)
+  for t, nm in ((minmax, 4), (keep, 1), (reason, 1), (cand_win, 1), (cand_rec, 1)):
+    if t is not None and t.numel() < n_cand * nm:
+      raise ValueError('per-candidate output too small')
+  o = N.Outputs(_ptr(scg_out), _ptr(rhc_out), _ptr(minmax), _ptr(keep), _ptr(reason), _ptr(cand_win), _ptr(cand_rec))
+  c = ctx(dev)
+  N.check(c, N.lib().scgrhc_process_windows(c, C.byref(j), C.byref(o), _stream(dev)))
+
+
+@torch.library.custom_op('scgrhc::compact_kept', mutates_args=('kept_idx', 'start_idx', 'stop_idx', 'rec_id', 'n_kept'),
+                         device_types='cuda')
+def compact_kept(keep: Tensor, cand_win: Tensor, cand_rec: Tensor, n_cand: int, W: int, kept_idx: Tensor,
+                 start_idx: Tensor, stop_idx: Tensor, rec_id: Tensor, n_kept: Tensor) -> None:
+  """Ordered list of kept windows = the order of the list get_segments returns (recordutil.py:148)."""
+  dev = _dev(keep)
+  _contig(keep, torch.uint8, 'keep'); _contig(cand_win, torch.int32, 'cand_win'); _contig(cand_rec, torch.int32, 'cand_rec')
+  for t, nm in ((kept_idx, 'kept_idx'), (start_idx, 'start_idx'), (stop_idx, 'stop_idx'), (n_kept, 'n_kept')):
+    _contig(t, torch.int64, nm)
+  _contig(rec_id, torch.int32, 'rec_id')
+  co = N.Compact(_ptr(kept_idx), _ptr(start_idx), _ptr(stop_idx), _ptr(rec_id), _ptr(n_kept))
+  c = ctx(dev)
+  N.check(c, N.lib().scgrhc_compact_kept(c, _ptr(keep), _ptr(cand_win), _ptr(cand_rec), n_cand, W, C.byref(co), _stream(dev)))
+
+
+@torch.library.custom_op('scgrhc::global_minmax', mutates_args=('mm_out',), device_types='cuda')
+def global_minmax(minmax: Tensor, keep: Tensor, n_cand: int, mm_out: Tensor) -> None:
+  """get_global_minmax_vals over the kept windows (recordutil.py:152-169)."""
+  dev = _dev(minmax)
+  _contig(minmax, torch.float64, 'minmax'); _contig(keep, torch.uint8, 'keep'); _contig(mm_out, torch.float64, 'mm_out')
+  c = ctx(dev)
+  N.check(c, N.lib().scgrhc_global_minmax(c, _ptr(minmax), _ptr(keep), n_cand, _ptr(mm_out), _stream(dev)))
+
+
+@torch.library.custom_op('scgrhc::gather_windows', mutates_args=('out',), device_types='cuda')
+def gather_windows(store: Tensor, slots: Tensor, out: Tensor) -> None:
+  """Batch collate (default_collate at recordutil.py:198): out[b] = store[slots[b]]."""
+  dev = _dev(store)
+  _contig(slots, torch.int64, 'slots')
+  if not store.is_contiguous() or not out.is_contiguous() or store.dtype != out.dtype:
+    raise ValueError('store/out must be contiguous and of one dtype')
+  wb = store[0].numel() * store.element_size()
+  if out.numel() * out.element_size() < wb * slots.numel():
+    raise ValueError('out too small')
+  c = ctx(dev)
+  N.check(c, N.lib().scgrhc_gather_windows(c, _ptr(store), _ptr(slots), slots.numel(), wb, _ptr(out), _stream(dev)))
+
+
+@torch.library.custom_op('scgrhc::rolling_range_lt', mutates_args=('flags',), device_types='cuda')
+def rolling_range_lt(y: Tensor, m: int, threshold: float, flags: Tensor) -> None:
+  """flags[p] = rolling(m).max - rolling(m).min < threshold (waveform_noise.py:10-13)."""
+  dev = _dev(y)
+  _contig(y, torch.float64, 'y'); _contig(flags, torch.uint8, 'flags')
+  c = ctx(dev)
+  N.check(c, N.lib().scgrhc_rolling_range_lt(c, _ptr(y), y.numel(), m, threshold, _ptr(flags), _stream(dev)))
+
+
+@torch.library.custom_op('scgrhc::synth_records', mutates_args=('out',), device_types='cuda')
+def synth_records(out: Tensor, seed: int, rec0: int, n_rec: int, T: int, kinds: Sequence[int], defect_scale: int,
+                  grid: int) -> None:
+  """Synthetic cohort generator, bit-identical to oracle/synth_ref.py."""
+  dev = _dev(out)
+  _contig(out, torch.float64, 'out')
+  nsig = len(kinds)
+  if out.numel() < n_rec * T * nsig:
+    raise ValueError('out too small')
+  arr = (C.c_int32 * nsig)(*kinds)
+  c = ctx(dev)
+  N.check(c, N.lib().scgrhc_synth_records(c, C.c_uint64(seed), rec0, n_rec, T, nsig, arr, defect_scale, grid,
+                                          _ptr(out), _stream(dev)))
+
+
+def check_errors(device_index):
+  """Synchronises the current stream; raises ValueError like the reference when a non-finite RHC
+  sample reached the regression (waveform_noise.py:32 via sklearn)."""
+  c = ctx(device_index)
+  bad = C.c_int64(-1)
+  rc = N.lib().scgrhc_check_errors(c, _stream(device_index), C.byref(bad))
+  if rc == N.ERR_NONFINITE_RHC:
+    raise ValueError('Input y contains NaN.')
+  N.check(c, rc)
+
+
+def selftest_div(device_index, seed, n, mode):
+  counts = torch.zeros(3, dtype=torch.int64, device='cuda:%d' % device_index)
+  c = ctx(device_index)
+  N.check(c, N.lib().scgrhc_selftest_div(c, C.c_uint64(seed), n, mode, _ptr(counts), _stream(device_index)))
+  return counts.cpu().tolist()

@@ -1,0 +1,253 @@
+"""GPU parity tests: the CUDA path (through the torch ops -> C ABI) vs golden fixtures produced by the
+unmodified reference and vs the numpy oracle on the same seeded inputs.
+
+Bar: keep/reject decisions, window indices, min/max pairs and fp32/fp64 samples are all BIT-EXACT
+(the device evaluates the reference's fp64 operations with the same roundings), which is stricter
+than the rel 1e-5 (fp32) / 1e-10 (fp64) tolerance BASELINE.json asks for.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import scgrhc_oracle as orc
+from oracle import synth_ref
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+import scgrhc  # noqa: E402
+from scgrhc import _native as N  # noqa: E402
+from scgrhc import ops  # noqa: E402
+
+DEV = 'cuda:0'
+
+
+def run_record(p, sig, meta, c, out_dtype=torch.float32, global_mm=False, keep_all=False):
+  W = int(c['segment_size'] * 500)
+  cols, rcol = scgrhc.resolve_columns(sig, c['in_channels'])
+  plan = scgrhc.plan_cohort([meta], c['chamber'], [p.shape[0]], W)
+  arena = torch.from_numpy(np.ascontiguousarray(p)).to(DEV)
+  return plan, scgrhc.prepare_windows(arena, plan, cols, rcol, c['min_RHC'], use_global_min_max=global_mm,
+                                      out_dtype=out_dtype, keep_all=keep_all)
+
+
+def test_synth_matches_numpy_twin_bit_for_bit():
+  for sig in (synth_ref.DEFAULT_SIG_NAMES, synth_ref.SIG_NAMES_5, ['a', 'RHC_pressure', 'b']):
+    kinds = synth_ref.kinds_for(sig)
+    T, n_rec = 6000, 3
+    out = torch.empty((n_rec * T, len(kinds)), dtype=torch.float64, device=DEV)
+    ops.synth_records(out, H.SEED, 5, n_rec, T, list(kinds), 16, 750)
+    got = out.cpu().numpy()
+    want = np.concatenate([synth_ref.gen_record(H.SEED, 5 + r, T, kinds=kinds) for r in range(n_rec)])
+    assert got.tobytes() == want.tobytes()
+
+
+def test_division_by_reciprocal_is_correctly_rounded():
+  for mode in (0, 1):
+    bad64, bad32, n = ops.selftest_div(0, 1234 + mode, 1 << 28, mode)
+    assert n == 1 << 28
+    assert bad64 == 0 and bad32 == 0, (mode, bad64, bad32)
+
+
+def test_predicates_match_reference_golden():
+  g = np.load(os.path.join(H.GOLDEN, 'predicates.npz'))
+  names, ys = H.predicate_inputs()
+  assert H.sha(ys) == str(g['inputs_sha'])
+  n = len(ys)
+  arena = torch.from_numpy(ys.reshape(-1, 1).copy()).to(DEV)      # nsig = 1: the RHC column is also the SCG column
+  plan = scgrhc.Plan(np.array([(0, 0, n, 0)], dtype=scgrhc.engine.INTERVAL_DTYPE), n, 750)
+  st = scgrhc.prepare_windows(arena, plan, [0], 0, -50.0, predicates_only=True, check=False)
+  reason = st.reason.cpu().numpy()
+  keep = st.keep.cpu().numpy().astype(bool)
+  assert (((reason & N.REASON_FLAT) != 0) == g['flat']).all()
+  # exactly-constant windows: sklearn's R^2 is rounding noise (0.0 or 1.0); they are always flat-rejected
+  const = ys.max(axis=1) == ys.min(axis=1)
+  assert ((((reason & N.REASON_STRAIGHT) != 0) == g['straight']) | const).all()
+  assert (((reason & N.REASON_FLOOR) == 0) == g['in_range']).all()
+  assert (keep == ~g['has_noise']).all()
+  assert (reason & N.REASON_AMBIGUOUS).sum() == 0
+  mm = st.minmax.cpu().numpy()
+  assert (mm[:, 2] == ys.min(axis=1)).all() and (mm[:, 3] == ys.max(axis=1)).all()
+
+
+@pytest.mark.parametrize('cfg', ['waveform_06', 'waveform_10', 'waveform_11', 'waveform_23', 'waveform_19', 'waveform_15'])
+def test_record_small_golden_bit_exact(cfg):
+  g = np.load(os.path.join(H.GOLDEN, 'record_small.npz'))
+  sig, p, meta = H.small_record()
+  c = H.effective_config(cfg)
+  plan, st = run_record(p, sig, meta, c)
+  assert st.start_idx.cpu().numpy().tolist() == g[cfg + '.start'].tolist()
+  assert st.stop_idx.cpu().numpy().tolist() == g[cfg + '.stop'].tolist()
+  assert (st.kept_minmax().cpu().numpy() == g[cfg + '.minmax']).all()
+  scg, rhc = st.materialise()
+  assert scg.cpu().numpy().tobytes() == g[cfg + '.scg'].tobytes()
+  assert rhc.cpu().numpy().tobytes() == g[cfg + '.rhc'].tobytes()
+
+
+def test_records_full_golden_all_configs():
+  full = H.load_json('records_full.json')
+  table = H.configs()
+  recs = {('rec%d' % r): H.full_record(r) for r in (0, 1)}
+  sig = recs['rec0'][0]
+  metas = [recs['rec0'][2], recs['rec1'][2]]
+  arena = torch.from_numpy(np.concatenate([recs['rec0'][1], recs['rec1'][1]])).to(DEV)
+  for cfg, entry in full['configs'].items():
+    c = H.effective_config(cfg, table)
+    W = int(c['segment_size'] * 500)
+    cols, rcol = scgrhc.resolve_columns(sig, c['in_channels'])
+    plan = scgrhc.plan_cohort(metas, c['chamber'], [300000, 300000], W)
+    st = scgrhc.prepare_windows(arena, plan, cols, rcol, c['min_RHC'], use_global_min_max=c['use_global_min_max'])
+    if c['use_global_min_max']:
+      assert [float(v).hex() for v in st.global_minmax.cpu().tolist()] == entry['global_minmax_hex']
+    scg, rhc = st.materialise()
+    scg, rhc = scg.cpu().numpy(), rhc.cpu().numpy()
+    rec_id = st.rec_id.cpu().numpy()
+    start, stop = st.start_idx.cpu().numpy(), st.stop_idx.cpu().numpy()
+    mm = st.kept_minmax().cpu().numpy()
+    for r, name in enumerate(('rec0', 'rec1')):
+      want = entry['records'][name]
+      m = rec_id == r
+      assert start[m].tolist() == want['start'], (cfg, name)
+      assert stop[m].tolist() == want['stop'], (cfg, name)
+      assert H.sha(mm[m]) == want['minmax_sha'], (cfg, name)
+      assert H.sha(scg[m]) == want['scg_sha'], (cfg, name)
+      assert H.sha(rhc[m]) == want['rhc_sha'], (cfg, name)
+
+
+@pytest.mark.parametrize('nsig,out_dtype', [(4, torch.float32), (4, torch.float64), (5, torch.float32), (7, torch.float64)])
+def test_cohort_vs_oracle(nsig, out_dtype):
+  """20 seeded records: device cohort generated on the GPU, oracle on the numpy twin."""
+  sig = (synth_ref.SIG_NAMES_5 + ['x5', 'x6'])[:nsig] if nsig != 4 else synth_ref.DEFAULT_SIG_NAMES
+  kinds = synth_ref.kinds_for(sig)
+  n_rec, T = 20, 60000
+  meta = synth_ref.record_meta(120, events={'RA_1': 0, 'PA_1': 10.002, 'RV_1': 50, 'PA_2': 70.5})
+  chans = ['patch_ACC_dv', 'patch_ACC_lat'] if nsig != 4 else ['patch_ACC_lat', 'patch_ACC_hf', 'patch_ACC_dv']
+  cols, rcol = scgrhc.resolve_columns(sig, chans)
+  arena = torch.empty((n_rec * T, nsig), dtype=torch.float64, device=DEV)
+  ops.synth_records(arena, 99, 0, n_rec, T, list(kinds), 16, 750)
+  plan = scgrhc.plan_uniform(meta, 'PA', T, 750, n_rec)
+  st = scgrhc.prepare_windows(arena, plan, cols, rcol, -50.0, out_dtype=out_dtype)
+  scg, rhc = st.materialise()
+  scg, rhc = scg.cpu().numpy(), rhc.cpu().numpy()
+  rec_id, start = st.rec_id.cpu().numpy(), st.start_idx.cpu().numpy()
+  mm = st.kept_minmax().cpu().numpy()
+  npdt = np.float64 if out_dtype == torch.float64 else np.float32
+  total = 0
+  for r in range(n_rec):
+    p = synth_ref.gen_record(99, r, T, kinds=kinds)
+    rw = orc.scan_record(p, sig, meta, chans, 'PA', 1.5, -50.0)
+    k = np.nonzero(rw.keep)[0]
+    m = rec_id == r
+    assert start[m].tolist() == rw.rel_start[k].tolist(), r
+    s_o, r_o, mm_o = orc.normalise_record(p, sig, chans, rw, out_dtype=npdt)
+    assert (mm[m] == mm_o).all()
+    assert scg[m].tobytes() == s_o.tobytes(), r
+    assert rhc[m].tobytes() == r_o.tobytes(), r
+    total += len(k)
+  assert total == st.n_kept and 0 < total < plan.n_cand
+
+
+def test_capacity_edge_uses_fallback_loads():
+  """Odd number of arena elements: the last window cannot be bulk-copied with 16-byte granularity."""
+  sig = synth_ref.SIG_NAMES_5
+  T = 7501
+  p = synth_ref.gen_record(H.SEED, 11, T, kinds=synth_ref.kinds_for(sig), defect_scale=0)
+  meta = synth_ref.record_meta(20, events={'PA_1': 0.002})
+  c = dict(in_channels=['patch_ACC_lat', 'patch_ECG'], chamber='PA', segment_size=1.5, min_RHC=-50)
+  plan, st = run_record(p, sig, meta, c)
+  assert plan.n_cand == 10 and plan.intervals['row0'][0] == 1
+  rw = orc.scan_record(p, sig, meta, c['in_channels'], 'PA', 1.5, -50)
+  s_o, r_o, _ = orc.normalise_record(p, sig, c['in_channels'], rw)
+  scg, rhc = st.materialise()
+  assert scg.cpu().numpy().tobytes() == s_o.tobytes() and rhc.cpu().numpy().tobytes() == r_o.tobytes()
+
+
+def test_nonfinite_rhc_raises_like_reference_unless_flat():
+  sig = synth_ref.DEFAULT_SIG_NAMES
+  p = synth_ref.gen_record(H.SEED, 21, 3000, kinds=synth_ref.kinds_for(sig), defect_scale=0)
+  meta = synth_ref.record_meta(6, events={'PA_1': 0})
+  c = dict(in_channels=sig[:3], chamber='PA', segment_size=1.5, min_RHC=-50)
+  q = p.copy(); q[800, 3] = np.nan
+  with pytest.raises(ValueError):
+    run_record(q, sig, meta, c)
+  q[900:1000, 3] = 5.0                                  # flat line short-circuits before the regression
+  plan, st = run_record(q, sig, meta, c)
+  assert st.keep.cpu().tolist()[1] == 0
+  assert st.reason.cpu().tolist()[1] & N.REASON_FLAT
+  q = p.copy(); q[100, 0] = np.nan                      # NaN in an SCG channel: np.min/np.max propagate it
+  plan, st = run_record(q, sig, meta, c)
+  mm = st.minmax.cpu().numpy()
+  assert np.isnan(mm[0, 0]) and np.isnan(mm[0, 1]) and st.keep.cpu().tolist()[0] == 1
+  assert np.isnan(st.materialise()[0][0].cpu().numpy()).all()
+
+
+def test_keep_all_normalises_rejected_windows_too():
+  sig, p, meta = H.small_record()
+  c = H.effective_config('waveform_06')
+  plan, st = run_record(p, sig, meta, c, keep_all=True)
+  assert st.n_kept == plan.n_cand
+  rw = orc.scan_record(p, sig, meta, c['in_channels'], c['chamber'], 1.5, c['min_RHC'])
+  want = rw.keep.copy()
+  rw.keep[:] = True
+  s_o, r_o, _ = orc.normalise_record(p, sig, c['in_channels'], rw)
+  scg, rhc = st.materialise()
+  assert scg.cpu().numpy().tobytes() == s_o.tobytes()
+  reason = st.reason.cpu().numpy()
+  assert ((reason & 15) == 0).tolist() == want.tolist()
+
+
+def test_empty_and_ragged_inputs():
+  sig = synth_ref.DEFAULT_SIG_NAMES
+  p = synth_ref.gen_record(H.SEED, 2, 2000, kinds=synth_ref.kinds_for(sig))
+  c = dict(in_channels=sig[:3], chamber='PCW', segment_size=1.5, min_RHC=-50)
+  plan, st = run_record(p, sig, synth_ref.record_meta(4, events={'PA_1': 0}), c)       # chamber never visited
+  assert plan.n_cand == 0 and st.n_kept == 0
+  c['chamber'] = 'PA'
+  plan, st = run_record(p, sig, synth_ref.record_meta(4, events={'PA_1': 3.5}), c)     # interval shorter than a window
+  assert plan.n_cand == 0 and st.n_kept == 0
+  plan, st = run_record(p, sig, synth_ref.record_meta(60, events={'PA_1': 0.1}), c)    # interval runs past the record: clamped
+  assert plan.n_cand == (2000 - 50) // 750
+  with pytest.raises(ValueError):
+    scgrhc.resolve_columns(sig, ['patch_ECG'])
+
+
+def test_full_size_properties_1000_records():
+  """BASELINE config 2 shape (1,000 x 10-min records, waveform_06): size-independent properties."""
+  n_rec, T = 1000, 300000
+  kinds = synth_ref.kinds_for(synth_ref.DEFAULT_SIG_NAMES)
+  arena = torch.empty((n_rec * T, 4), dtype=torch.float64, device=DEV)
+  ops.synth_records(arena, H.SEED, 0, n_rec, T, list(kinds), 16, 750)
+  meta = synth_ref.record_meta(600)
+  plan = scgrhc.plan_uniform(meta, 'PA', T, 750, n_rec)
+  assert plan.n_cand == 200 * n_rec
+  st = scgrhc.prepare_windows(arena, plan, [0, 1, 2], 3, -50.0)
+  keep = st.keep.bool()
+  assert int(keep.sum()) == st.n_kept
+  k = st.kept_idx
+  assert bool((k[1:] > k[:-1]).all()) and bool(keep[k].all())
+  # records 0 and 1 of this cohort are the golden 5-signal records minus the ECG column
+  full = H.load_json('records_full.json')['configs']['waveform_06']['records']
+  for r in (0, 1):
+    m = st.rec_id == r
+    assert st.start_idx[m].cpu().tolist() == full['rec%d' % r]['start']
+  # every kept window: min sample normalises to exactly 0, max to (mx-mn)/(mx-mn+1e-4) < 1
+  pos = torch.arange(0, st.n_kept, 37, device=DEV)
+  scg, rhc = st.gather(pos)
+  assert float(scg.amin()) == 0.0 and float(rhc.amin()) == 0.0
+  assert bool((scg.amin(dim=(1, 2)) == 0).all()) and bool((rhc.amin(dim=(1, 2)) == 0).all())
+  mm = st.kept_minmax()[pos]
+  top = ((mm[:, 1] - mm[:, 0]) / (mm[:, 1] - mm[:, 0] + 0.0001)).float()
+  assert bool((scg.amax(dim=(1, 2)) == top).all())
+  # idempotence: a second run is byte-identical
+  st2 = scgrhc.prepare_windows(arena, plan, [0, 1, 2], 3, -50.0)
+  assert torch.equal(st2.keep, st.keep) and torch.equal(st2.minmax, st.minmax)
+  scg2, rhc2 = st2.gather(pos)
+  assert torch.equal(scg2, scg) and torch.equal(rhc2, rhc)
+  # shard invariance: the second half of the cohort processed alone gives the same windows
+  half = scgrhc.plan_uniform(meta, 'PA', T, 750, n_rec // 2, rec0=n_rec // 2)
+  sth = scgrhc.prepare_windows(arena[(n_rec // 2) * T:], half, [0, 1, 2], 3, -50.0)
+  m = st.rec_id >= n_rec // 2
+  assert torch.equal(sth.start_idx, st.start_idx[m]) and torch.equal(sth.rec_id, st.rec_id[m])
+  assert torch.equal(sth.kept_minmax(), st.kept_minmax()[m])
