@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the SCG/RHC window-preparation hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A *step* is one pass of the hot path over one synthetic cohort per GPU: BASELINE.json configs[1],
+1,000 synthetic 10-min records x 4 signals (3-axis SCG + RHC pressure) with the waveform_06 params
+(waveform_01, which BASELINE names, has no `chamber` key and cannot be run by the reference either —
+SURVEY.md §0; waveform_06 is the first config the reference loads and has the same 3-axis shape).
+
+  value      kept windows/s, records resident in HBM when the timed region starts (whole job, all GPUs)
+  e2e        the same metric through the public host API (pinned host records -> H2D -> hot path ->
+             D2H of the kept-window count/indices); windows stay device-resident by design
+  roofline   algorithmic bytes of the window kernel / its CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline  oracle/ref_port.py (per-window pandas + sklearn, the reference's cost profile) on
+             host cores, bounded sample; the reference arm (--impl reference) runs it on all cores
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'scg-rhc-waveform_b200')
+for _p in (ROOT, PKG):
+  if _p not in sys.path:
+    sys.path.insert(0, _p)
+
+SEED = 0x5C6
+T_ROWS = 300000                      # 10 min @ 500 Hz
+SIG = ['patch_ACC_lat', 'patch_ACC_hf', 'patch_ACC_dv', 'RHC_pressure']
+KINDS = [0, 1, 2, 3]
+IN_CHANNELS = SIG[:3]                # waveform_06
+W = 750
+MIN_RHC = -50.0
+EVENTS = {'PA_1': 0}                 # one full-length PA interval -> 400 candidate windows / record
+METRIC = 'preprocessed windows/sec'
+UNIT = 'windows/s'
+
+
+def meta():
+  return {'MacStTime': '1/1/2020 10:00:00', 'MacEndTime': '1/1/2020 10:10:00', 'ChamEvents_in_s': dict(EVENTS)}
+
+
+def workload_name(n_rec):
+  return ('%d synthetic 10-min records x 4 signals (3-axis SCG + RHC, fp64) x waveform_06 params '
+          '(PA, C=3, W=750, min_RHC=-50, local min-max) -> fp32 windows; 400 candidate windows/record' % n_rec)
+
+
+def algorithmic_bytes(n_cand, n_kept, C, out_bytes):
+  """candidate = RHC read 6000 B + 1 B flag; kept additionally SCG read, outputs, 52 B metadata."""
+  return n_cand * (W * 8 + 1) + n_kept * (W * C * 8 + W * (C + 1) * out_bytes + 52)
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons sampled while the GPU is under load."""
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+       'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+       'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, device):
+    self.samples, self.proc, self.device = [], None, device
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                    '-lms', '50', '-i', str(self.device)], stdout=subprocess.PIPE,
+                                   stderr=subprocess.DEVNULL, text=True)
+    except OSError:
+      return
+    def reader():
+      for line in self.proc.stdout:
+        f = [x.strip() for x in line.split(',')]
+        if len(f) >= 8:
+          self.samples.append((time.time(), f))
+    threading.Thread(target=reader, daemon=True).start()
+
+  def stop(self):
+    if self.proc:
+      self.proc.terminate()
+
+  def summary(self, windows):
+    """windows: list of (t0, t1) host-time intervals during which the GPU was under our load."""
+    sel = [f for (t, f) in self.samples if any(a <= t <= b for a, b in windows)] or [f for _, f in self.samples]
+    if not sel:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+    def num(x):
+      try:
+        return float(x)
+      except ValueError:
+        return None
+    sm = [num(f[1]) for f in sel if num(f[1]) is not None]
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    reasons = [n for i, n in enumerate(names) if any(f[4 + i].lower().startswith('active') for f in sel)]
+    pw = [num(f[3]) for f in sel if num(f[3]) is not None]
+    return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': num(sel[0][2]), 'reasons': reasons,
+            'samples': len(sel), 'power_w_max': max(pw) if pw else None}
+
+
+def measured_peak():
+  try:
+    with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+      return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)'
+  except Exception:
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arms (oracle port)
+# ------------------------------------------------------------------------------------------
+_worker_cache = {}
+
+
+def _cpu_worker_init():
+  try:
+    from threadpoolctl import threadpool_limits
+    threadpool_limits(1)
+  except Exception:
+    pass
+  import torch
+  torch.set_num_threads(1)
+
+
+def _cpu_gen(rec):
+  from oracle import synth_ref
+  if rec not in _worker_cache:
+    _worker_cache[rec] = synth_ref.gen_record(SEED, rec, T_ROWS, kinds=tuple(KINDS))
+  return rec
+
+
+def _cpu_gen_return(rec):
+  from oracle import synth_ref
+  return rec, synth_ref.gen_record(SEED, rec, T_ROWS, kinds=tuple(KINDS))
+
+
+def _cpu_run(rec):
+  from oracle import ref_port
+  p = _worker_cache.get(rec)
+  if p is None:
+    _cpu_gen(rec)
+    p = _worker_cache[rec]
+  out, n_cand = ref_port.prepare_record(p, SIG, meta(), IN_CHANNELS, 'PA', 1.5, MIN_RHC)
+  return len(out), n_cand
+
+
+def cpu_single_core(n_rec):
+  """oracle/ref_port.py on one core over n_rec records (records generated outside the timed region)."""
+  _cpu_worker_init()
+  for r in range(n_rec):
+    _cpu_gen(r)
+  t0 = time.perf_counter()
+  kept = cand = 0
+  for r in range(n_rec):
+    k, c = _cpu_run(r)
+    kept += k; cand += c
+  dt = time.perf_counter() - t0
+  return kept, cand, dt
+
+
+def cpu_fast(n_rec, threads):
+  """The C restatement (oracle/_build/liboracle.so, OpenMP) — the best host implementation we have."""
+  import numpy as np
+  from oracle import c_oracle, synth_ref
+  arena = np.concatenate([synth_ref.gen_record(SEED, r, T_ROWS, kinds=tuple(KINDS)) for r in range(n_rec)])
+  rs = np.arange(0, n_rec * T_ROWS, W, dtype=np.int64)
+  c_oracle.process_windows(arena[:T_ROWS], W, [0, 1, 2], 3, rs[:400], MIN_RHC, threads=threads)   # warm
+  t0 = time.perf_counter()
+  keep = c_oracle.process_windows(arena, W, [0, 1, 2], 3, rs, MIN_RHC, threads=threads)[0]
+  dt = time.perf_counter() - t0
+  return int(keep.sum()), len(rs), dt
+
+
+def run_reference(args):
+  """Reference arm: the reference's CPU implementation of the path (its port, oracle/ref_port.py —
+  /root/reference is Python and cannot travel to the GPU box) on all host cores, sharded by record."""
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  import multiprocessing as mp
+  cores = os.cpu_count() or 1
+  per_step = max(cores, 8) * 2                       # records per step: ~1-2 s of wall clock per step
+  ctx = mp.get_context('fork')
+  recs = list(range(per_step))
+  with ctx.Pool(min(cores, 32), initializer=_cpu_worker_init) as pool:      # generate the inputs in parallel ...
+    for rec, arr in pool.imap_unordered(_cpu_gen_return, recs, chunksize=1):
+      _worker_cache[rec] = arr
+  with ctx.Pool(cores, initializer=_cpu_worker_init) as pool:               # ... and fork the timed workers after,
+    for _ in range(args.warmup):                                            # so every worker sees every record (copy-on-write)
+      pool.map(_cpu_run, recs, chunksize=1)
+    t0 = time.perf_counter()
+    kept = cand = 0
+    for _ in range(args.steps):
+      for k, c in pool.map(_cpu_run, recs, chunksize=1):
+        kept += k; cand += c
+    dt = time.perf_counter() - t0
+  value = kept / dt
+  sample = '%d records/step (%d candidate windows) of the %d-record workload, %d steps' % (per_step, per_step * 400, args.records, args.steps)
+  line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+          'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+          'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+          'config': {'workload': workload_name(args.records), 'note': 'bounded sample per step; host records resident in RAM'},
+          'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
+                           'what': 'oracle/ref_port.py: per-window pandas rolling + sklearn OLS + numpy/torch normalise, multiprocessing by record'},
+          'candidate_windows_per_s': cand / dt,
+          'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+          'gpu_launches': 0}
+  print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+  import torch
+  import torch.distributed as dist
+  import scgrhc
+  from scgrhc import ops, _native as N
+  from scgrhc.engine import HostIngest
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  if not torch.cuda.is_available():
+    raise RuntimeError('bench.py needs a CUDA device: the hot path has no CPU fallback')
+  torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  if args.ctas_per_sm or args.stages:
+    ops.set_tuning(local, args.ctas_per_sm, args.stages)
+
+  n_rec = args.records
+  C = len(IN_CHANNELS)
+  cols, rcol = scgrhc.resolve_columns(SIG, IN_CHANNELS)
+  lo = rank * n_rec                                           # weak scaling: every rank owns n_rec records
+  arena = torch.empty((n_rec * T_ROWS, len(SIG)), dtype=torch.float64, device=dev)
+  ops.synth_records(arena, SEED, lo, n_rec, T_ROWS, KINDS, 16, W)
+  plan = scgrhc.plan_uniform(meta(), 'PA', T_ROWS, W, n_rec, rec0=lo)
+  n = plan.n_cand
+  iv = plan.device_intervals(dev)
+  out_dtype = torch.float64 if args.out_f64 else torch.float32
+  out_bytes = 8 if args.out_f64 else 4
+  flags = N.OUT_F64 if args.out_f64 else 0
+  scg = torch.empty((n, C, W), dtype=out_dtype, device=dev)
+  rhc = torch.empty((n, 1, W), dtype=out_dtype, device=dev)
+  minmax = torch.empty((n, 4), dtype=torch.float64, device=dev)
+  keep = torch.empty(n, dtype=torch.uint8, device=dev)
+  reason = torch.empty(n, dtype=torch.uint8, device=dev)
+  cand_win = torch.empty(n, dtype=torch.int32, device=dev)
+  cand_rec = torch.empty(n, dtype=torch.int32, device=dev)
+  kept_idx, start_idx, stop_idx = (torch.empty(n, dtype=torch.int64, device=dev) for _ in range(3))
+  rec_id = torch.empty(n, dtype=torch.int32, device=dev)
+  n_kept_t = torch.zeros(1, dtype=torch.int64, device=dev)
+  gmm = torch.empty(4, dtype=torch.float64, device=dev)
+
+  def kernel_step():
+    ops.process_windows(arena, iv, n, W, cols, rcol, MIN_RHC, 1e-3, flags, [0.0] * 4, None, 0,
+                        scg, rhc, minmax, keep, reason, cand_win, cand_rec)
+
+  def tail_step():
+    ops.compact_kept(keep, cand_win, cand_rec, n, W, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
+    if args.global_minmax:   # BASELINE configs[3]: dataset-level min/max statistics + all-reduce
+      ops.global_minmax(minmax, keep, n, gmm)
+      scgrhc.allreduce_minmax(gmm)
+
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for _ in range(max(args.warmup, 3)):
+    kernel_step(); tail_step()
+  barrier()
+  ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  t_host0 = time.time()
+  e0.record()
+  for k in range(args.steps):
+    ev[k][0].record()
+    kernel_step()
+    ev[k][1].record()
+    tail_step()
+  e1.record()
+  barrier()
+  t_host1 = time.time()
+  ms_total = e0.elapsed_time(e1)
+  ms_kernel = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+  n_kept = int(n_kept_t.item())
+  tt = torch.tensor([ms_total, float(n_kept), float(n), ms_kernel], dtype=torch.float64, device=dev)
+  if world > 1:
+    mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    ms_total, kept_all, cand_all, ms_kernel_max = float(mx[0]), float(sm[1]), float(sm[2]), float(mx[3])
+  else:
+    kept_all, cand_all, ms_kernel_max = float(n_kept), float(n), ms_kernel
+  ms_step = ms_total / args.steps
+  value = kept_all / (ms_step * 1e-3)
+
+  # ---- roofline of the dominant kernel (this rank's window kernel) ----
+  peak, peak_src = measured_peak()
+  alg = algorithmic_bytes(n, n_kept, C, out_bytes)
+  achieved = alg / (ms_kernel * 1e-3) / 1e9
+  traffic = None
+  try:
+    with open(os.path.join(ROOT, 'profiles', 'window_kernel_traffic.json')) as f:
+      traffic = json.load(f).get('dram_bytes_per_launch')
+  except Exception:
+    pass
+  roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+              'traffic': traffic, 'kernel': 'scgrhc::window_kernel<C=3,NSIG4,float,R=6>', 'kernel_ms': ms_kernel,
+              'algorithmic_bytes_per_launch': alg, 'peak_source': peak_src,
+              'bytes_per_kept_window': W * C * 8 + W * 8 + W * (C + 1) * out_bytes + 53}
+
+  # ---- end to end through the host API: pinned host records -> H2D -> hot path -> D2H result ----
+  e2e = None
+  windows = [(t_host0, t_host1)]
+  if not args.no_e2e:
+    host = torch.empty(arena.shape, dtype=torch.float64, pin_memory=True)
+    host.copy_(arena)
+    torch.cuda.synchronize()
+    ing = HostIngest(plan, [T_ROWS] * n_rec, len(SIG), dev, chunk_records=args.chunk_records)
+    bufs = dict(scg=scg, rhc=rhc, minmax=minmax, keep=keep, reason=reason, cand_win=cand_win, cand_rec=cand_rec,
+                kept_idx=kept_idx, start_idx=start_idx, stop_idx=stop_idx, rec_id=rec_id, n_kept=n_kept_t)
+    k_e2e = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+      st = ing.run(host, cols, rcol, MIN_RHC, out_dtype=out_dtype, buffers=bufs)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    th0 = time.time()
+    a.record()
+    d2h = 0
+    for _ in range(k_e2e):
+      st = ing.run(host, cols, rcol, MIN_RHC, out_dtype=out_dtype, buffers=bufs)
+      meta_host = (st.kept_idx.cpu(), st.start_idx.cpu(), st.rec_id.cpu())     # the step's result crosses to the host
+      d2h = 8 + sum(t.numel() * t.element_size() for t in meta_host)
+    b.record()
+    barrier()
+    th1 = time.time()
+    windows.append((th0, th1))
+    ms_e2e = a.elapsed_time(b) / k_e2e
+    t2 = torch.tensor([ms_e2e, float(st.n_kept)], dtype=torch.float64, device=dev)
+    if world > 1:
+      m2 = t2.clone(); dist.all_reduce(m2, op=dist.ReduceOp.MAX)
+      s2 = t2.clone(); dist.all_reduce(s2, op=dist.ReduceOp.SUM)
+      ms_e2e, kept_e2e = float(m2[0]), float(s2[1])
+    else:
+      kept_e2e = float(st.n_kept)
+    assert st.n_kept == n_kept, 'host-ingest path kept a different number of windows'
+    e2e = {'value': kept_e2e / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': ing.h2d_bytes,
+           'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e, 'steps': k_e2e,
+           'api': 'scgrhc.engine.HostIngest.run (pinned host fp64 records, %d-record chunks, copy/compute overlap)' % args.chunk_records,
+           'h2d_gbs': ing.h2d_bytes / (ms_e2e * 1e-3) / 1e9}
+    del host
+
+  if rank == 0:
+    sampler.stop()
+  clocks = sampler.summary(windows) if rank == 0 else None
+
+  cpu = cpu_fast_d = None
+  if rank == 0 and world == 1 and not args.no_cpu:
+    kept_c, cand_c, dt = cpu_single_core(args.cpu_records)
+    cpu = {'value': kept_c / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+           'sample': '%d of the %d records (%d candidate windows), %.1f s' % (args.cpu_records, n_rec, cand_c, dt),
+           'what': 'oracle/ref_port.py single process = the reference as shipped (no parallelism in the reference)',
+           'host_cores_available': os.cpu_count()}
+    try:
+      th = os.cpu_count() or 1
+      kf, cf, dtf = cpu_fast(min(64, n_rec), th)
+      cpu_fast_d = {'value': kf / dtf, 'unit': UNIT, 'cores': th, 'kind': 'port',
+                    'what': 'oracle/scgrhc_oracle.c (O(W) C restatement, OpenMP) on %d records' % min(64, n_rec)}
+    except Exception as e:  # the C oracle is optional
+      cpu_fast_d = {'error': str(e)[:200]}
+
+  if rank == 0:
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': workload_name(n_rec), 'records_per_gpu': n_rec, 'candidate_windows_per_step': int(cand_all),
+                       'kept_windows_per_step': int(kept_all), 'out_dtype': 'f64' if args.out_f64 else 'f32',
+                       'global_minmax_allreduce': bool(args.global_minmax),
+                       'l2': 'inputs %.1f GB + outputs %.1f GB per step per GPU, far larger than the 126 MB L2: no flush needed'
+                             % (arena.numel() * 8 / 1e9, (scg.numel() + rhc.numel()) * out_bytes / 1e9)},
+            'candidate_windows_per_s': cand_all / (ms_step * 1e-3),
+            'roofline': roofline, 'cpu_baseline': cpu, 'cpu_baseline_fast': cpu_fast_d, 'e2e': e2e,
+            'gpu_launches': args.steps * (4 + (2 if args.global_minmax else 0)),
+            'launches_per_step': 'window_kernel + count_kept + scan_blocks + scatter_kept',
+            'clocks': clocks}
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=200)
+  ap.add_argument('--warmup', type=int, default=5)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--records', type=int, default=1000, help='records per GPU (BASELINE configs[1]: 1,000)')
+  ap.add_argument('--out-f64', action='store_true')
+  ap.add_argument('--global-minmax', action='store_true')
+  ap.add_argument('--no-e2e', action='store_true')
+  ap.add_argument('--no-cpu', action='store_true')
+  ap.add_argument('--e2e-steps', type=int, default=5)
+  ap.add_argument('--chunk-records', type=int, default=50)
+  ap.add_argument('--cpu-records', type=int, default=24)
+  ap.add_argument('--ctas-per-sm', type=int, default=0)
+  ap.add_argument('--stages', type=int, default=0)
+  args = ap.parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_b200(args)
+
+
+if __name__ == '__main__':
+  main()

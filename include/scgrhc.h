@@ -155,6 +155,11 @@ int scgrhc_gather_windows(scgrhc_ctx* ctx, const void* store, const int64_t* slo
 int scgrhc_rolling_range_lt(scgrhc_ctx* ctx, const double* y, int64_t n, int32_t m, double threshold,
                             uint8_t* flags, void* stream);
 
+/* ---- is_straight_line / in_rhc_range on waveforms of any length (waveform_noise.py:29-41), one
+ *      waveform per row of y (n_wave, L); stats (n_wave, 6) = {R^2, min, max, below_floor, nonfinite, sum} */
+int scgrhc_waveform_stats(scgrhc_ctx* ctx, const double* y, int64_t n_wave, int64_t L, double min_rhc,
+                          double* stats, void* stream);
+
 /* ---- synthetic cohort generator: records rec0..rec0+n_rec-1 of cohort `seed`,
  *      each (T, nsig) fp64 row-major, written back to back into `out` (device). */
 int scgrhc_synth_records(scgrhc_ctx* ctx, uint64_t seed, int64_t rec0, int64_t n_rec, int64_t T,

@@ -151,10 +151,10 @@ extern "C" int scgrhc_plan_record(const double* event_time, const uint8_t* event
 }
 
 // ---- hot path launcher -------------------------------------------------------------------------------
-template <int C, bool NSIG4, typename OutT, int R>
+template <int C, bool NSIG4, bool IDENT, typename OutT, int WCT>
 static int launch_window(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
-  auto kern = window_kernel<C, NSIG4, OutT, R>;
-  const size_t smem = ((sizeof(Scratch<R>) + 127) & ~size_t(127)) + (size_t)P.stages * P.stage_elems * sizeof(double);
+  auto kern = window_kernel<C, NSIG4, IDENT, OutT, WCT>;
+  const size_t smem = ((sizeof(Scratch) + 127) & ~size_t(127)) + (size_t)P.stages * P.stage_elems * sizeof(double);
   CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
@@ -166,20 +166,27 @@ static int launch_window(scgrhc_ctx* ctx, const KParams& P, long long items, cud
   return SCGRHC_OK;
 }
 
-template <int C, bool NSIG4, typename OutT>
-static int dispatch_r(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
-  if (P.job.W <= 6 * NT) return launch_window<C, NSIG4, OutT, 6>(ctx, P, items, st);
-  return launch_window<C, NSIG4, OutT, 8>(ctx, P, items, st);
+template <int C, bool NSIG4, bool IDENT, typename OutT>
+static int dispatch_w(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
+  if (P.job.W == 750) return launch_window<C, NSIG4, IDENT, OutT, 750>(ctx, P, items, st);  // int(1.5 * 500): all 37 configs
+  return launch_window<C, NSIG4, IDENT, OutT, 0>(ctx, P, items, st);
 }
-template <int C, bool NSIG4>
+template <int C, bool NSIG4, bool IDENT>
 static int dispatch_out(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
-  if (P.job.flags & SCGRHC_OUT_F64) return dispatch_r<C, NSIG4, double>(ctx, P, items, st);
-  return dispatch_r<C, NSIG4, float>(ctx, P, items, st);
+  if (P.job.flags & SCGRHC_OUT_F64) return dispatch_w<C, NSIG4, IDENT, double>(ctx, P, items, st);
+  return dispatch_w<C, NSIG4, IDENT, float>(ctx, P, items, st);
 }
 template <int C>
 static int dispatch_nsig(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
-  if (P.job.nsig == 4) return dispatch_out<C, true>(ctx, P, items, st);
-  return dispatch_out<C, false>(ctx, P, items, st);
+  const scgrhc_job& J = P.job;
+  if (J.nsig == 4) {
+    if constexpr (C == 3) {
+      if (J.scg_cols[0] == 0 && J.scg_cols[1] == 1 && J.scg_cols[2] == 2 && J.rhc_col == 3)
+        return dispatch_out<3, true, true>(ctx, P, items, st);
+    }
+    return dispatch_out<C, true, false>(ctx, P, items, st);
+  }
+  return dispatch_out<C, false, false>(ctx, P, items, st);
 }
 
 extern "C" int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, const scgrhc_outputs* out, void* stream) {
@@ -190,7 +197,7 @@ extern "C" int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, co
   const bool pred_only = J.flags & SCGRHC_PREDICATES_ONLY;
   if (J.C < 1 || J.C > SCGRHC_MAX_C) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "C=%d SCG channels (supported 1..%d)", J.C, SCGRHC_MAX_C);
   if (J.nsig < 1 || J.nsig > SCGRHC_MAX_NSIG) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "nsig=%d (supported 1..%d)", J.nsig, SCGRHC_MAX_NSIG);
-  if (J.W < 2 || J.W > 8 * NT) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "window of %d samples (supported 2..%d)", J.W, 8 * NT);
+  if (J.W < 2 || J.W > RMAX * NT) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "window of %d samples (supported 2..%d)", J.W, RMAX * NT);
   if (J.rhc_col < 0 || J.rhc_col >= J.nsig) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "RHC column %d outside 0..%d", J.rhc_col, J.nsig - 1);
   for (int c = 0; c < J.C; ++c)
     if (J.scg_cols[c] < 0 || J.scg_cols[c] >= J.nsig) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "SCG column %d outside 0..%d", J.scg_cols[c], J.nsig - 1);
@@ -216,7 +223,7 @@ extern "C" int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, co
   P.out = *out;
   P.err = ctx->err_dev;
   P.stages = ctx->stages > 0 ? ctx->stages : 2;
-  P.stage_elems = (int)(((long long)J.W * J.nsig + 2 + 1) & ~1LL);
+  P.stage_elems = (int)(((long long)J.W * J.nsig + J.nsig + 2 + 1) & ~1LL);  // + one padded row (next-row loads) + lead
   P.arena_elems_cap = J.arena_capacity_bytes / 8;
   switch (J.C) {
     case 1: return dispatch_nsig<1>(ctx, P, items, st);
@@ -310,6 +317,19 @@ extern "C" int scgrhc_rolling_range_lt(scgrhc_ctx* ctx, const double* y, int64_t
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   rolling_range_lt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y, n, m, threshold, flags);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_waveform_stats(scgrhc_ctx* ctx, const double* y, int64_t n_wave, int64_t L, double min_rhc,
+                                     double* stats, void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (n_wave < 0 || L < 1 || (n_wave && (!y || !stats))) return fail(ctx, SCGRHC_ERR_BAD_ARG, "waveform_stats: bad arguments");
+  if (n_wave == 0) return SCGRHC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const unsigned grid = (unsigned)std::min<long long>(n_wave, (long long)ctx->sm_count * 8);
+  waveform_stats_kernel<<<grid, 256, 0, st>>>(y, n_wave, L, min_rhc, stats);
   CUDA_TRY(ctx, cudaGetLastError());
   return SCGRHC_OK;
 }

@@ -187,6 +187,57 @@ __global__ void rolling_range_lt_kernel(const double* __restrict__ y, long long 
   flags[p] = f;
 }
 
+// ---- per-waveform statistics of arbitrary length (API parity of is_straight_line / in_rhc_range on
+//      waveforms that are not 2..1024 samples long; waveform_noise.py:29-41).  One block per waveform.
+//      stats[w] = {R^2, min, max, below_floor, nonfinite, sum}
+__global__ void __launch_bounds__(256) waveform_stats_kernel(const double* __restrict__ y, long long n_wave, long long L,
+                                                             double min_rhc, double* __restrict__ stats) {
+  __shared__ double red[8][4];
+  __shared__ int flags_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long w = blockIdx.x; w < n_wave; w += gridDim.x) {
+    const double* v = y + w * L;
+    double mn = CUDART_INF, mx = -CUDART_INF, sum = 0.0;
+    int f = 0;
+    if (threadIdx.x == 0) flags_s = 0;
+    __syncthreads();
+    for (long long i = threadIdx.x; i < L; i += blockDim.x) {
+      const double a = v[i];
+      mn = fmin(mn, a); mx = fmax(mx, a); sum = __dadd_rn(sum, a);
+      if (a < min_rhc) f |= 1;
+      if (!(fabs(a) <= 1.7976931348623157e308)) f |= 2;
+    }
+    mn = warp_min(mn); mx = warp_max(mx); sum = warp_sum(sum);
+    f = __reduce_or_sync(kFull, f);
+    if (lane == 0) { red[warp][0] = mn; red[warp][1] = mx; red[warp][2] = sum; if (f) atomicOr(&flags_s, f); }
+    __syncthreads();
+    mn = red[0][0]; mx = red[0][1]; sum = red[0][2];
+    for (int k = 1; k < 8; ++k) { mn = fmin(mn, red[k][0]); mx = fmax(mx, red[k][1]); sum = __dadd_rn(sum, red[k][2]); }
+    const int fl = flags_s;
+    __syncthreads();
+    const double ybar = __ddiv_rn(sum, (double)L), xbar = 0.5 * (double)(L - 1);
+    double sxy = 0.0, syy = 0.0;
+    for (long long i = threadIdx.x; i < L; i += blockDim.x) {
+      const double dy = __dsub_rn(v[i], ybar);
+      sxy = __fma_rn((double)i - xbar, dy, sxy);
+      syy = __fma_rn(dy, dy, syy);
+    }
+    sxy = warp_sum(sxy); syy = warp_sum(syy);
+    if (lane == 0) { red[warp][0] = sxy; red[warp][1] = syy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      sxy = red[0][0]; syy = red[0][1];
+      for (int k = 1; k < 8; ++k) { sxy = __dadd_rn(sxy, red[k][0]); syy = __dadd_rn(syy, red[k][1]); }
+      const double Ld = (double)L;
+      const double sxx = Ld * (Ld * Ld - 1.0) / 12.0;
+      double* o = stats + 6 * w;
+      o[0] = __ddiv_rn(__dmul_rn(sxy, sxy), __dmul_rn(sxx, syy));
+      o[1] = mn; o[2] = mx; o[3] = (fl & 1) ? 1.0 : 0.0; o[4] = (fl & 2) ? 1.0 : 0.0; o[5] = sum;
+    }
+    __syncthreads();
+  }
+}
+
 // ---- Markstein division self-test --------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
   x += 0x9E3779B97F4A7C15ull;

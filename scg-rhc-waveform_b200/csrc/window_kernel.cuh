@@ -12,7 +12,18 @@
 // chunk of W*nsig*8 bytes.  An elected thread streams it into shared memory with a 1-D bulk async
 // copy (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier; `stages` windows are in flight per
 // CTA, several CTAs per SM.  Each thread then owns rows t = tid + k*NT in registers, so the window is
-// read from shared memory once; reductions are warp shuffles + one small shared exchange.
+// read from shared memory once; reductions are warp shuffles + one small shared exchange and ONE
+// __syncthreads per window.
+//
+// Instruction economy (the kernel is issue-bound before it is HBM-bound; see profiles/):
+//   * no per-element division: one correctly rounded reciprocal per window + two FMA residual
+//     corrections (Markstein) give the correctly rounded quotient; windows whose scale could make the
+//     residuals underflow take a separate, non-unrolled IEEE-division loop (CTA-uniform branch);
+//   * below-floor is decided from the window minimum, non-finite RHC from the sum of squares, NaN in
+//     SCG from a 0*v accumulator — no per-element flag logic;
+//   * R^2 from one pass of sums shifted by K = y[0] (cancellation bounded by n because K is a sample);
+//   * the flat-line test first asks for >= 49 consecutive small steps |y[t+1]-y[t]| < thr (a necessary
+//     condition, one bit per sample, checked with shifts); only then the exact rolling range runs.
 #pragma once
 #include <float.h>
 #include <math_constants.h>
@@ -24,6 +35,7 @@ namespace scgrhc {
 constexpr int NT = 128;          // threads per CTA
 constexpr int NWARP = NT / kWarp;
 constexpr int kMaxStages = 8;
+constexpr int RMAX = 8;          // rows per thread, generic kernel: W <= RMAX * NT
 
 struct StageMeta {
   long long cand;   // candidate index
@@ -40,32 +52,31 @@ struct KParams {
   scgrhc_outputs out;
   unsigned long long* err;  // [0] error flags, [1] first offending candidate (atomicMin)
   int stages;
-  int stage_elems;          // doubles per stage buffer (even)
+  int stage_elems;          // doubles per stage buffer (even, >= W*nsig + nsig + 2)
   long long arena_elems_cap;
 };
 
-template <int R>
+constexpr int NRED = 8;  // smin, smax, ymin, ymax, s1, s2, sxy, nan-accumulator
+
 struct Scratch {
   uint64_t full[kMaxStages];
   StageMeta meta[kMaxStages];
-  double red1[NWARP][5];
-  double red2[NWARP][2];
-  uint32_t a49[R * NWARP];
-  uint32_t cmask[R * NWARP];
-  uint32_t wflags[NWARP];
-  int need_slow;
-  int slow_cnt[2];
+  double red[2][NWARP][NRED];        // double buffered by window parity: one __syncthreads per window
+  uint32_t cmask[2][RMAX * NWARP];
+  uint32_t a49[RMAX * NWARP];
+  int slow_cnt;
+  int slow_flag;
 };
 
-// Correctly rounded a/d from a correctly rounded reciprocal (Markstein): two FMA residual
-// corrections.  Validated against __ddiv_rn in tests (scgrhc_selftest_div).
+// Correctly rounded a/d from the correctly rounded reciprocal inv = RN(1/d) (Markstein): two FMA
+// residual corrections.  Valid when no intermediate underflows; the caller guarantees that per window
+// (see Normaliser::slow).  Validated against IEEE division in tests (scgrhc_selftest_div).
 __device__ __forceinline__ double div_by_recip(double a, double d, double inv) {
   double q = __dmul_rn(a, inv);
   double r = __fma_rn(-d, q, a);
   q = __fma_rn(r, inv, q);
   r = __fma_rn(-d, q, a);
   q = __fma_rn(r, inv, q);
-  if (fabs(q) < 0x1p-900 && a != 0.0) q = __ddiv_rn(a, d);  // residuals could underflow
   return q;
 }
 
@@ -76,12 +87,14 @@ struct Normaliser {
     mn = mn_;
     d = __dadd_rn(__dsub_rn(mx_, mn_), 0.0001);  // (max - min + 0.0001), recordutil.py:46
     inv = __drcp_rn(d);
-    slow = !(d < 0x1p1000 && d > 0x1p-1000);     // also catches NaN
+    // The fast path needs every non-zero numerator a = x - mn to satisfy |a| >= 2^-960 (then the
+    // residuals and the quotient stay normal): true when |mn| >= 2^-900 (a is then either >= |mn|/2
+    // or a multiple of ulp(mn)/2) and d is within [2^-14, 2^60].  Anything else (mn == 0, tiny, NaN,
+    // Inf, huge ranges) takes the IEEE-division loop.
+    slow = !(d >= 0x1p-14 && d <= 0x1p60 && fabs(mn_) >= 0x1p-900);
   }
-  __device__ __forceinline__ double operator()(double x) const {
-    double a = __dsub_rn(x, mn);
-    return slow ? __ddiv_rn(a, d) : div_by_recip(a, d, inv);
-  }
+  __device__ __forceinline__ double fast(double x) const { return div_by_recip(__dsub_rn(x, mn), d, inv); }
+  __device__ __forceinline__ double exact(double x) const { return __ddiv_rn(__dsub_rn(x, mn), d); }
 };
 
 __device__ __forceinline__ void cvt_out(float& o, double q) { o = __double2float_rn(q); }
@@ -93,7 +106,7 @@ __device__ __forceinline__ double sel4(int col, double v0, double v1, double v2,
   return (col & 2) ? hi : lo;
 }
 
-// ---- diagnostics: div_by_recip vs IEEE division on hashed operands --------------------------------
+// ---- diagnostics: the normaliser's fast path vs IEEE division on hashed operands -------------------
 __device__ __forceinline__ unsigned long long st_mix64(unsigned long long x) {
   x += 0x9E3779B97F4A7C15ull;
   unsigned long long z = x;
@@ -108,22 +121,28 @@ __global__ void __launch_bounds__(256) selftest_div_kernel(unsigned long long se
     const unsigned long long h1 = st_mix64(seed ^ (unsigned long long)(2 * i));
     const unsigned long long h2 = st_mix64(seed ^ (unsigned long long)(2 * i + 1));
     const double m1 = 1.0 + (double)(h1 >> 12) * 0x1p-52, m2 = (double)(h2 >> 11) * 0x1p-53;
-    double d, a;
-    if (mode == 0) {
-      d = ldexp(m1, (int)(h1 & 0xFFF) % 24 - 14);  // 2^-14 .. 2^10
-      a = d * m2;                                  // 0 <= a < d, rounded product: arbitrary mantissa
-    } else {
-      d = ldexp(m1, (int)(h1 & 0xFFF) % 801 - 400);
-      a = ldexp(1.0 + m2, (int)(h2 & 0xFFF) % 801 - 400);
-      if (h2 & 0x1000) a = -a;
+    double mn, mx, x;
+    if (mode == 0) {         // shaped like the normalisation: mn <= x <= mx, ranges 2^-14 .. 2^10
+      const double range = ldexp(m1, (int)(h1 & 0xFFF) % 24 - 14);
+      mn = ldexp((double)((h2 >> 3) & 0xFFFFF) - 524288.5, (int)(h1 >> 52) % 30 - 25);
+      mx = mn + range;
+      x = mn + range * m2;
+      if (x > mx) x = mx;
+    } else {                 // wide exponents, both signs, zeros: exercises the slow-path selection
+      mn = ldexp(m1, (int)(h1 & 0xFFF) % 2001 - 1000);
+      if (h1 & 0x1000) mn = -mn;
+      mx = mn + ldexp(1.0 + m2, (int)(h2 & 0xFFF) % 2001 - 1000);
+      x = mn + (mx - mn) * m2;
+      if (h2 & 0x2000) mn = 0.0;
     }
     Normaliser nz;
-    nz.mn = 0.0; nz.d = d; nz.inv = __drcp_rn(d); nz.slow = !(d < 0x1p1000 && d > 0x1p-1000);
-    const double q = nz.slow ? __ddiv_rn(a, d) : div_by_recip(a, d, nz.inv);
-    const double ref = __ddiv_rn(a, d);
-    bad64 += (__double_as_longlong(q) != __double_as_longlong(ref));
-    bad32 += (__float_as_int(__double2float_rn(q)) != __float_as_int(__double2float_rn(ref)));
-    ++cnt;
+    nz.init(mn, mx);
+    const double q = nz.slow ? nz.exact(x) : nz.fast(x);
+    const double ref = __ddiv_rn(__dsub_rn(x, mn), __dadd_rn(__dsub_rn(mx, mn), 0.0001));
+    const bool both_nan = (q != q) && (ref != ref);
+    bad64 += (__double_as_longlong(q) != __double_as_longlong(ref)) && !both_nan;
+    bad32 += (__float_as_int(__double2float_rn(q)) != __float_as_int(__double2float_rn(ref))) && !both_nan;
+    cnt += nz.slow ? 0 : 1;
   }
   for (int m = 16; m; m >>= 1) {
     bad64 += __shfl_xor_sync(kFull, bad64, m);
@@ -135,26 +154,32 @@ __global__ void __launch_bounds__(256) selftest_div_kernel(unsigned long long se
   }
 }
 
-template <int C, bool NSIG4, typename OutT, int R>
+// C      SCG channels;  NSIG4  rows are 4 doubles (16-byte shared loads);
+// IDENT  columns are (0..C-1 | C) in order (no selects);  WCT  compile-time window length (0: runtime)
+template <int C, bool NSIG4, bool IDENT, typename OutT, int WCT>
 __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ KParams P) {
   static_assert(SCGRHC_FLAT_WIN == 50, "run detection below is hard-wired to 49 = 32 + 16 + 1 pairs");
-  static_assert(R * NWARP <= 32, "one mask word per lane of warp 0");
+  constexpr int R = WCT ? (WCT + NT - 1) / NT : RMAX;
+  static_assert(R * NWARP <= 32 && R <= RMAX, "one mask word per lane");
+  static_assert(!IDENT || (NSIG4 && C == 3), "identity mapping is the 3 SCG + RHC record");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Scratch<R>& S = *reinterpret_cast<Scratch<R>*>(smem_raw);
-  double* stage_base = reinterpret_cast<double*>(smem_raw + ((sizeof(Scratch<R>) + 127) & ~size_t(127)));
+  Scratch& S = *reinterpret_cast<Scratch*>(smem_raw);
+  double* stage_base = reinterpret_cast<double*>(smem_raw + ((sizeof(Scratch) + 127) & ~size_t(127)));
 
   const scgrhc_job& J = P.job;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int W = J.W, nsig = J.nsig, nstage = P.stages;
+  const int W = WCT ? WCT : J.W;
+  const int nsig = NSIG4 ? 4 : J.nsig;
+  const int nstage = P.stages;
   const bool use_list = (J.flags & SCGRHC_USE_KEPT_LIST) != 0;
   const bool pred_only = (J.flags & SCGRHC_PREDICATES_ONLY) != 0;
   const bool norm_global = (J.flags & SCGRHC_NORM_GLOBAL) != 0;
   const bool keep_all = (J.flags & SCGRHC_KEEP_ALL) != 0;
   const double thr = J.flat_threshold, min_rhc = J.min_rhc;
-  const int rcol = J.rhc_col;
+  const int rcol = IDENT ? C : J.rhc_col;
   int col[C];
 #pragma unroll
-  for (int c = 0; c < C; ++c) col[c] = J.scg_cols[c];
+  for (int c = 0; c < C; ++c) col[c] = IDENT ? c : J.scg_cols[c];
 
   const long long items = use_list ? J.n_items : J.n_cand;
   const long long lo = items * (long long)blockIdx.x / gridDim.x;
@@ -163,7 +188,8 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
 
   if (tid == 0) {
     for (int s = 0; s < nstage; ++s) mbar_init(&S.full[s], 1);
-    S.slow_cnt[0] = S.slow_cnt[1] = 0;
+    S.slow_cnt = 0;
+    S.slow_flag = 0;
     fence_barrier_init();
   }
   __syncthreads();
@@ -209,11 +235,12 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
 
   const double xbar = 0.5 * (double)(W - 1);
   const double sxx = (double)W * ((double)W * (double)W - 1.0) / 12.0;  // sum (t - xbar)^2, exact here
-  const double inv_w = 1.0 / (double)W;
+  const double tx = (double)tid - xbar;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
+  int s = 0;
+  uint32_t parity = 0, par2 = 0;
   for (long long n = 0; n < hi - lo; ++n) {
-    const int s = (int)(n % nstage);
-    const uint32_t parity = (uint32_t)((n / nstage) & 1);
     mbar_wait(&S.full[s], parity);
     const StageMeta M = S.meta[s];
     double* sbuf = stage_base + (size_t)s * P.stage_elems;
@@ -224,26 +251,35 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
     }
     const double* win = sbuf + M.lead;
 
-    // ---- rows -> registers ----------------------------------------------------------------------
-    double x[R][C], y[R];
+    // ---- rows -> registers (+ the next row's RHC sample for the small-step bit) --------------------
+    double x[R][C], y[R], yn[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       const int t = tid + k * NT;
-      y[k] = 0.0;
+      const bool valid = WCT ? ((k + 1) * NT <= WCT || t < WCT) : (t < W);
+      y[k] = 0.0; yn[k] = 0.0;
 #pragma unroll
       for (int c = 0; c < C; ++c) x[k][c] = 0.0;
-      if (t < W) {
+      if (valid) {
         if constexpr (NSIG4) {
           const double2 a = *reinterpret_cast<const double2*>(win + 4 * t);
           const double2 b = *reinterpret_cast<const double2*>(win + 4 * t + 2);
+          const double2 nb = *reinterpret_cast<const double2*>(win + 4 * t + 6);  // row t+1, columns 2,3 (stage is padded)
+          if constexpr (IDENT) {
+            x[k][0] = a.x; x[k][1] = a.y; x[k][2] = b.x; y[k] = b.y; yn[k] = nb.y;
+          } else {
+            const double2 na = *reinterpret_cast<const double2*>(win + 4 * t + 4);
 #pragma unroll
-          for (int c = 0; c < C; ++c) x[k][c] = sel4(col[c], a.x, a.y, b.x, b.y);
-          y[k] = sel4(rcol, a.x, a.y, b.x, b.y);
+            for (int c = 0; c < C; ++c) x[k][c] = sel4(col[c], a.x, a.y, b.x, b.y);
+            y[k] = sel4(rcol, a.x, a.y, b.x, b.y);
+            yn[k] = sel4(rcol, na.x, na.y, nb.x, nb.y);
+          }
         } else {
           const double* row = win + (size_t)t * nsig;
 #pragma unroll
           for (int c = 0; c < C; ++c) x[k][c] = row[col[c]];
           y[k] = row[rcol];
+          yn[k] = row[nsig + rcol];
         }
       }
     }
@@ -253,75 +289,64 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
     bool keep = true;
 
     if (!use_list) {
-      // ---- pass 1: min/max, sum(y), floor / non-finite flags, small-step bits --------------------
-      double a_smin = CUDART_INF, a_smax = -CUDART_INF, a_ymin = CUDART_INF, a_ymax = -CUDART_INF, a_sum = 0.0;
-      uint32_t f = 0;
+      // ---- one pass of per-thread statistics --------------------------------------------------------
+      const double K = win[rcol];  // shift for the sums: a sample of the window, so cancellation is bounded by n
+      double a_smin = CUDART_INF, a_smax = -CUDART_INF, a_ymin = CUDART_INF, a_ymax = -CUDART_INF;
+      double s1 = 0.0, s2 = 0.0, sB = 0.0, nanacc = 0.0;
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         const int t = tid + k * NT;
-        if (t < W) {
+        const bool valid = WCT ? ((k + 1) * NT <= WCT || t < WCT) : (t < W);
+        const bool has_next = WCT ? ((k + 1) * NT < WCT || t + 1 < WCT) : (t + 1 < W);
+        bool cb = false;
+        if (valid) {
 #pragma unroll
           for (int c = 0; c < C; ++c) {
             const double v = x[k][c];
-            a_smin = fmin(a_smin, v);
-            a_smax = fmax(a_smax, v);
-            if (v != v) f |= 4u;
+            a_smin = v < a_smin ? v : a_smin;
+            a_smax = v > a_smax ? v : a_smax;
+            nanacc = __fma_rn(v, 0.0, nanacc);  // NaN iff some v is NaN or Inf
           }
           const double v = y[k];
-          a_ymin = fmin(a_ymin, v);
-          a_ymax = fmax(a_ymax, v);
-          a_sum = __dadd_rn(a_sum, v);
-          if (v < min_rhc) f |= 1u;
-          if (!(fabs(v) <= DBL_MAX)) f |= 2u;
+          a_ymin = v < a_ymin ? v : a_ymin;
+          a_ymax = v > a_ymax ? v : a_ymax;
+          const double dy = __dsub_rn(v, K);
+          s1 = __dadd_rn(s1, dy);
+          s2 = __fma_rn(dy, dy, s2);
+          sB = __fma_rn((double)k, dy, sB);
+          // c[t] = fl(|y[t+1] - y[t]|) < thr: necessary for any flat 50-window covering (t, t+1)
+          cb = has_next && (fabs(__dsub_rn(yn[k], v)) < thr);
         }
-        // c[t] = fl(|y[t+1] - y[t]|) < thr: necessary for any flat 50-window covering (t, t+1)
-        double yn = __shfl_down_sync(kFull, y[k], 1);
-        if (lane == 31 && t + 1 < W) yn = win[(size_t)(t + 1) * nsig + rcol];
-        const bool cb = (t + 1 < W) && (fabs(__dsub_rn(yn, y[k])) < thr);
         const uint32_t word = __ballot_sync(kFull, cb);
-        if (lane == 0) S.cmask[k * NWARP + warp] = word;
+        if (lane == 0) S.cmask[par2][k * NWARP + warp] = word;
       }
+      // sum_k (tid + NT k - xbar) dy_k = (tid - xbar) sum dy + NT sum k dy
+      double sxy = __fma_rn(tx, s1, __dmul_rn((double)NT, sB));
       a_smin = warp_min(a_smin); a_smax = warp_max(a_smax);
       a_ymin = warp_min(a_ymin); a_ymax = warp_max(a_ymax);
-      a_sum = warp_sum(a_sum);
-      f = __reduce_or_sync(kFull, f);
+      s1 = warp_sum(s1); s2 = warp_sum(s2); sxy = warp_sum(sxy); nanacc = warp_sum(nanacc);
       if (lane == 0) {
-        S.red1[warp][0] = a_smin; S.red1[warp][1] = a_smax; S.red1[warp][2] = a_ymin;
-        S.red1[warp][3] = a_ymax; S.red1[warp][4] = a_sum;
-        S.wflags[warp] = f;
+        double* r = S.red[par2][warp];
+        r[0] = a_smin; r[1] = a_smax; r[2] = a_ymin; r[3] = a_ymax; r[4] = s1; r[5] = s2; r[6] = sxy; r[7] = nanacc;
       }
-      __syncthreads();  // #1
-      if (tid == 0) S.slow_cnt[(n + 1) & 1] = 0;  // everyone is past iteration n-1, which used this slot
+      __syncthreads();  // the only block barrier of the common path; every thread is also done with the stage
 
-      smin = S.red1[0][0]; smax = S.red1[0][1]; ymin = S.red1[0][2]; ymax = S.red1[0][3];
-      double ysum = S.red1[0][4];
-      f = S.wflags[0];
+      {
+        const double* r = S.red[par2][0];
+        smin = r[0]; smax = r[1]; ymin = r[2]; ymax = r[3]; s1 = r[4]; s2 = r[5]; sxy = r[6]; nanacc = r[7];
 #pragma unroll
-      for (int w = 1; w < NWARP; ++w) {
-        smin = fmin(smin, S.red1[w][0]); smax = fmax(smax, S.red1[w][1]);
-        ymin = fmin(ymin, S.red1[w][2]); ymax = fmax(ymax, S.red1[w][3]);
-        ysum = __dadd_rn(ysum, S.red1[w][4]);
-        f |= S.wflags[w];
-      }
-      if (f & 4u) { smin = smax = __longlong_as_double(0x7ff8000000000000LL); }  // np.min/np.max propagate NaN
-
-      // ---- pass 2: centred sums for R^2; warp 0 also looks for >= 49 consecutive small steps -----
-      const double ybar = __dmul_rn(ysum, inv_w);
-      double sxy = 0.0, syy = 0.0;
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-        const int t = tid + k * NT;
-        if (t < W) {
-          const double dy = __dsub_rn(y[k], ybar);
-          sxy = __fma_rn((double)t - xbar, dy, sxy);
-          syy = __fma_rn(dy, dy, syy);
+        for (int w = 1; w < NWARP; ++w) {
+          r = S.red[par2][w];
+          smin = r[0] < smin ? r[0] : smin; smax = r[1] > smax ? r[1] : smax;
+          ymin = r[2] < ymin ? r[2] : ymin; ymax = r[3] > ymax ? r[3] : ymax;
+          s1 = __dadd_rn(s1, r[4]); s2 = __dadd_rn(s2, r[5]); sxy = __dadd_rn(sxy, r[6]); nanacc = __dadd_rn(nanacc, r[7]);
         }
       }
-      sxy = warp_sum(sxy); syy = warp_sum(syy);
-      if (lane == 0) { S.red2[warp][0] = sxy; S.red2[warp][1] = syy; }
-      if (warp == 0) {
-        constexpr int NWORDS = R * NWARP;
-        const uint32_t a1 = lane < NWORDS ? S.cmask[lane] : 0u;
+      // every warp scans the small-step mask for >= 49 consecutive ones (no second barrier)
+      constexpr int NWORDS = R * NWARP;
+      const uint32_t a1 = lane < NWORDS ? S.cmask[par2][lane] : 0u;
+      uint32_t a49;
+      {
         auto down = [&](uint32_t v, int d) {  // word (lane + d) of the mask, 0 past the end
           const uint32_t o = __shfl_down_sync(kFull, v, d);
           return (lane + d < 32) ? o : 0u;
@@ -333,41 +358,60 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
         const uint32_t a16 = a8 & shr(a8, 8);
         const uint32_t a32 = a16 & shr(a16, 16);
         const uint32_t a48 = a32 & down(a16, 1);
-        const uint32_t a49 = a48 & __funnelshift_r(down(a1, 1), down(a1, 2), 16);
-        if (lane < NWORDS) S.a49[lane] = a49;
-        const int any = __any_sync(kFull, a49 != 0u);
-        if (lane == 0) S.need_slow = any;
+        a49 = a48 & __funnelshift_r(down(a1, 1), down(a1, 2), 16);
       }
-      __syncthreads();  // #2
-
-      sxy = S.red2[0][0]; syy = S.red2[0][1];
-#pragma unroll
-      for (int w = 1; w < NWARP; ++w) { sxy = __dadd_rn(sxy, S.red2[w][0]); syy = __dadd_rn(syy, S.red2[w][1]); }
-      const double r2 = __ddiv_rn(__dmul_rn(sxy, sxy), __dmul_rn(sxx, syy));
+      const bool run49 = __any_sync(kFull, a49 != 0u);
+      // non-finite RHC <=> the shifted sum of squares is not finite (or it overflowed: recheck exactly)
+      const bool s2_bad = !(s2 <= DBL_MAX);
+      // NaN in SCG must poison the joint min/max as np.min/np.max do; Inf alone must not: recheck exactly
+      const bool scg_bad = nanacc != nanacc;
 
       int flat_cnt = 0;
-      if (S.need_slow) {  // exact rolling range, only where 49 consecutive small steps allow a flat window
-        int cnt = 0;
-        for (int k = 0; k < R; ++k) {
-          const int p = tid + k * NT;
-          if (p + SCGRHC_FLAT_WIN <= W && ((S.a49[p >> 5] >> (p & 31)) & 1u)) {
-            double mx = -CUDART_INF, mn = CUDART_INF;
-            for (int i = 0; i < SCGRHC_FLAT_WIN; ++i) {
-              const double v = win[(size_t)(p + i) * nsig + rcol];
-              mx = fmax(mx, v); mn = fmin(mn, v);
+      bool nonfinite = false;
+      if (run49 || s2_bad || scg_bad) {  // CTA-uniform and rare: exact work on the stage buffer / registers
+        if (warp == 0 && lane < NWORDS) S.a49[lane] = a49;
+        __syncthreads();
+        int cnt = 0, fl = 0;
+        if (run49) {
+          for (int k = 0; k < R; ++k) {
+            const int p = tid + k * NT;
+            if (p + SCGRHC_FLAT_WIN <= W && ((S.a49[p >> 5] >> (p & 31)) & 1u)) {
+              double mx = -CUDART_INF, mn = CUDART_INF;
+              for (int i = 0; i < SCGRHC_FLAT_WIN; ++i) {
+                const double v = win[(size_t)(p + i) * nsig + rcol];
+                mx = fmax(mx, v); mn = fmin(mn, v);
+              }
+              cnt += (__dsub_rn(mx, mn) < thr) ? 1 : 0;
             }
-            cnt += (__dsub_rn(mx, mn) < thr) ? 1 : 0;
           }
         }
-        if (cnt) atomicAdd(&S.slow_cnt[n & 1], cnt);
-        __syncthreads();  // #3 (rare)
-        flat_cnt = S.slow_cnt[n & 1];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const int t = tid + k * NT;
+          if (t < W) {
+            if (!(fabs(y[k]) <= DBL_MAX)) fl |= 1;
+#pragma unroll
+            for (int c = 0; c < C; ++c) if (x[k][c] != x[k][c]) fl |= 2;
+          }
+        }
+        if (cnt) atomicAdd(&S.slow_cnt, cnt);
+        if (fl) atomicOr(&S.slow_flag, fl);
+        __syncthreads();
+        flat_cnt = S.slow_cnt;
+        nonfinite = (S.slow_flag & 1) != 0;
+        if (S.slow_flag & 2) { smin = qnan; smax = qnan; }
+        __syncthreads();
+        if (tid == 0) { S.slow_cnt = 0; S.slow_flag = 0; }
       }
+
+      // Syy = sum (y-K)^2 - (sum (y-K))^2 / n ; Sxy is shift invariant because sum (t - xbar) = 0
+      const double syy = __dsub_rn(s2, __ddiv_rn(__dmul_rn(s1, s1), (double)W));
+      const double r2 = __ddiv_rn(__dmul_rn(sxy, sxy), __dmul_rn(sxx, syy));
       if (flat_cnt >= 2) reason |= SCGRHC_REASON_FLAT;
       if (r2 > 0.8) reason |= SCGRHC_REASON_STRAIGHT;
-      if (fabs(r2 - 0.8) < 1e-12) reason |= SCGRHC_REASON_AMBIGUOUS;
-      if (f & 1u) reason |= SCGRHC_REASON_FLOOR;
-      if (f & 2u) reason |= SCGRHC_REASON_NONFINITE;
+      if (fabs(r2 - 0.8) < 1e-9) reason |= SCGRHC_REASON_AMBIGUOUS;
+      if (ymin < min_rhc) reason |= SCGRHC_REASON_FLOOR;  // some sample < floor <=> the minimum is
+      if (nonfinite) reason |= SCGRHC_REASON_NONFINITE;
       keep = keep_all ||
              (reason & (SCGRHC_REASON_FLAT | SCGRHC_REASON_STRAIGHT | SCGRHC_REASON_FLOOR | SCGRHC_REASON_NONFINITE)) == 0;
 
@@ -384,6 +428,7 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
           atomicMin(P.err + 1, (unsigned long long)M.cand);
         }
       }
+      par2 ^= 1;
     } else {
       __syncthreads();  // all rows are in registers before the stage is refilled
       if (!norm_global) {  // dense re-materialisation with the per-window pairs of an earlier pass
@@ -395,6 +440,7 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
 
     // ---- the stage buffer is dead: refill it with window n + stages ---------------------------
     if (tid == 0 && lo + n + nstage < hi) issue(lo + n + nstage, s);
+    if (++s == nstage) { s = 0; parity ^= 1; }
 
     // ---- normalise from registers, transpose, cast, store ---------------------------------------
     if (keep && !pred_only) {
@@ -402,21 +448,44 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
       Normaliser ns, nr;
       ns.init(smin, smax);
       nr.init(ymin, ymax);
-      OutT* so = reinterpret_cast<OutT*>(P.out.scg_out) + (size_t)M.slot * C * W;
-      OutT* ro = reinterpret_cast<OutT*>(P.out.rhc_out) + (size_t)M.slot * W;
+      OutT* so = reinterpret_cast<OutT*>(P.out.scg_out) + (size_t)M.slot * C * W + tid;
+      OutT* ro = reinterpret_cast<OutT*>(P.out.rhc_out) + (size_t)M.slot * W + tid;
+      if (!(ns.slow || nr.slow)) {
 #pragma unroll
-      for (int k = 0; k < R; ++k) {
-        const int t = tid + k * NT;
-        if (t < W) {
+        for (int k = 0; k < R; ++k) {
+          const int t = tid + k * NT;
+          const bool valid = WCT ? ((k + 1) * NT <= WCT || t < WCT) : (t < W);
+          if (valid) {
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
+            for (int c = 0; c < C; ++c) {
+              OutT o;
+              cvt_out(o, ns.fast(x[k][c]));
+              st_cs(so + (size_t)c * W + k * NT, o);
+            }
             OutT o;
-            cvt_out(o, ns(x[k][c]));
-            st_cs(so + (size_t)c * W + t, o);
+            cvt_out(o, nr.fast(y[k]));
+            st_cs(ro + k * NT, o);
           }
-          OutT o;
-          cvt_out(o, nr(y[k]));
-          st_cs(ro + t, o);
+        }
+      } else {  // IEEE division; kept out of line (not unrolled) so the common path stays small
+#pragma unroll 1
+        for (int e = 0; e < R * (C + 1); ++e) {
+          const int k = e / (C + 1), c = e - k * (C + 1);
+          const int t = tid + k * NT;
+          if (t < W) {
+            double v = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < R; ++kk) {
+              if (kk == k) {
+                v = y[kk];
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) if (cc == c) v = x[kk][cc];
+              }
+            }
+            OutT o;
+            if (c < C) { cvt_out(o, ns.exact(v)); st_cs(so + (size_t)c * W + k * NT, o); }
+            else { cvt_out(o, nr.exact(v)); st_cs(ro + k * NT, o); }
+          }
         }
       }
     }

@@ -239,3 +239,80 @@ def shard_records(n_rec, rank, world):
   lo = n_rec * rank // world
   hi = n_rec * (rank + 1) // world
   return lo, hi
+
+
+class HostIngest:
+  """Host-resident cohort -> HBM -> hot path, chunked at record boundaries and double buffered:
+  the pinned-host -> device copy of chunk k+1 (copy stream) overlaps the window kernel of chunk k
+  (compute stream).  This is the end-to-end path a caller with records in host memory uses
+  (the reference reads each record from disk into host numpy arrays, recordutil.py:137)."""
+
+  def __init__(self, plan, record_rows, nsig, device, chunk_records=64):
+    self.plan, self.nsig, self.device = plan, nsig, torch.device(device)
+    rows = np.asarray(record_rows, dtype=np.int64)
+    base = np.concatenate([[0], np.cumsum(rows)])
+    self.total_rows = int(base[-1])
+    iv = plan.intervals
+    self.chunks = []
+    max_rows = 0
+    for r0 in range(0, len(rows), chunk_records):
+      r1 = min(len(rows), r0 + chunk_records)
+      lo, hi = int(base[r0]), int(base[r1])
+      a, b = np.searchsorted(iv['row0'], [lo, hi], side='left')
+      sub = iv[a:b].copy()
+      cand_lo = int(sub['cand0'][0]) if len(sub) else 0
+      n = int(sub['n_win'].sum())
+      sub['row0'] -= lo
+      sub['cand0'] -= cand_lo
+      t = torch.from_numpy(sub.view(np.int64).reshape(-1, 3).copy()).to(self.device) if len(sub) else None
+      self.chunks.append((lo, hi, cand_lo, n, t))
+      max_rows = max(max_rows, hi - lo)
+    self.bufs = [torch.empty((max_rows, nsig), dtype=torch.float64, device=self.device) for _ in range(2)]
+    self.copy_stream = torch.cuda.Stream(self.device)
+    self.h2d_bytes = self.total_rows * nsig * 8
+
+  def run(self, host_arena, scg_cols, rhc_col, min_rhc, out_dtype=torch.float32, flat_threshold=FLAT_THRESHOLD,
+          buffers=None):
+    """``host_arena``: (total_rows, nsig) fp64 CPU tensor (pinned for an asynchronous copy)."""
+    plan, dev = self.plan, self.device
+    n, W, Cn = plan.n_cand, plan.W, len(scg_cols)
+    b = buffers if buffers is not None else {}
+
+    def buf(name, shape, dtype):
+      t = b.get(name)
+      if t is None or t.shape != torch.Size(shape) or t.dtype != dtype:
+        t = b[name] = torch.empty(shape, dtype=dtype, device=dev)
+      return t
+
+    scg, rhc = buf('scg', (n, Cn, W), out_dtype), buf('rhc', (n, 1, W), out_dtype)
+    minmax, keep, reason = buf('minmax', (n, 4), torch.float64), buf('keep', (n,), torch.uint8), buf('reason', (n,), torch.uint8)
+    cand_win, cand_rec = buf('cand_win', (n,), torch.int32), buf('cand_rec', (n,), torch.int32)
+    kept_idx, start_idx, stop_idx = (buf(k, (n,), torch.int64) for k in ('kept_idx', 'start_idx', 'stop_idx'))
+    rec_id, n_kept_t = buf('rec_id', (n,), torch.int32), buf('n_kept', (1,), torch.int64)
+    flags = N.OUT_F64 if out_dtype == torch.float64 else 0
+    compute = torch.cuda.current_stream(dev)
+    done = [None, None]
+    self.copy_stream.wait_stream(compute)
+    bad = False
+    for k, (lo, hi, cand_lo, nc, iv) in enumerate(self.chunks):
+      dst = self.bufs[k & 1][:hi - lo]
+      with torch.cuda.stream(self.copy_stream):
+        if done[k & 1] is not None:
+          self.copy_stream.wait_event(done[k & 1])
+        dst.copy_(host_arena[lo:hi], non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(self.copy_stream)
+      compute.wait_event(ready)
+      if nc:
+        ops.process_windows(dst, iv, nc, W, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
+                            [0.0] * 4, None, 0, scg[cand_lo:], rhc[cand_lo:], minmax[cand_lo:], keep[cand_lo:],
+                            reason[cand_lo:], cand_win[cand_lo:], cand_rec[cand_lo:])
+      done[k & 1] = torch.cuda.Event()
+      done[k & 1].record(compute)
+    ops.compact_kept(keep, cand_win, cand_rec, n, W, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
+    n_kept = int(n_kept_t.item())      # device -> host read of the step's result
+    nonfinite = bool(((reason & N.REASON_NONFINITE) != 0).logical_and((reason & N.REASON_FLAT) == 0).any()) if n else False
+    if nonfinite:
+      raise ValueError('Input y contains NaN.')
+    return WindowStore(scg, rhc, minmax, keep, reason, kept_idx[:n_kept], start_idx[:n_kept], stop_idx[:n_kept],
+                       rec_id[:n_kept], n_kept, n, False, None)

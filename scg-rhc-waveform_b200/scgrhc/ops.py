@@ -156,6 +156,18 @@ def rolling_range_lt(y: Tensor, m: int, threshold: float, flags: Tensor) -> None
   N.check(c, N.lib().scgrhc_rolling_range_lt(c, _ptr(y), y.numel(), m, threshold, _ptr(flags), _stream(dev)))
 
 
+@torch.library.custom_op('scgrhc::waveform_stats', mutates_args=('stats',), device_types='cuda')
+def waveform_stats(y: Tensor, min_rhc: float, stats: Tensor) -> None:
+  """Per row of y (n_wave, L): R^2 of the OLS line, min, max, below-floor, non-finite, sum
+  (waveform_noise.py:29-41 for waveforms of any length)."""
+  dev = _dev(y)
+  _contig(y, torch.float64, 'y'); _contig(stats, torch.float64, 'stats')
+  if y.dim() != 2 or stats.numel() < 6 * y.shape[0]:
+    raise ValueError('y must be (n_wave, L) and stats (n_wave, 6)')
+  c = ctx(dev)
+  N.check(c, N.lib().scgrhc_waveform_stats(c, _ptr(y), y.shape[0], y.shape[1], min_rhc, _ptr(stats), _stream(dev)))
+
+
 @torch.library.custom_op('scgrhc::synth_records', mutates_args=('out',), device_types='cuda')
 def synth_records(out: Tensor, seed: int, rec0: int, n_rec: int, T: int, kinds: Sequence[int], defect_scale: int,
                   grid: int) -> None:
