@@ -51,16 +51,21 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 // ---- warp reductions over doubles ----------------------------------------------------------------
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(kFull, v, m); }
 
-__device__ __forceinline__ double warp_min(double v) {
-#pragma unroll
-  for (int m = 16; m; m >>= 1) v = fmin(v, shfl_xor_d(v, m));
-  return v;
-}
+// Exact fp64 max over a warp with two 32-bit REDUX ops instead of five 64-bit shuffle rounds: map the
+// double to an order-preserving unsigned 64-bit key, reduce the high words, then the low words among
+// the lanes that hold the winning high word.  Inputs must not be NaN (callers keep NaN out of their
+// running extrema); +-Inf and +-0 order correctly (-0 < +0 in key order, both compare equal as values).
 __device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-  for (int m = 16; m; m >>= 1) v = fmax(v, shfl_xor_d(v, m));
-  return v;
+  const uint32_t hi = (uint32_t)__double2hiint(v), lo = (uint32_t)__double2loint(v);
+  const uint32_t m = (uint32_t)((int32_t)hi >> 31);          // all ones for negative values
+  const uint32_t khi = hi ^ (m | 0x80000000u), klo = lo ^ m;
+  const uint32_t mh = __reduce_max_sync(kFull, khi);
+  const uint32_t ml = __reduce_max_sync(kFull, khi == mh ? klo : 0u);
+  const uint32_t im = (mh & 0x80000000u) ? 0u : 0xffffffffu;  // winner was negative: undo the complement
+  return __hiloint2double((int)(mh ^ (im | 0x80000000u)), (int)(ml ^ im));
 }
+__device__ __forceinline__ double warp_min(double v) { return -warp_max(-v); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int m = 16; m; m >>= 1) v = __dadd_rn(v, shfl_xor_d(v, m));

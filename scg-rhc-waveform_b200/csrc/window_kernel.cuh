@@ -56,7 +56,7 @@ struct KParams {
   long long arena_elems_cap;
 };
 
-constexpr int NRED = 8;  // smin, smax, ymin, ymax, s1, s2, sxy, nan-accumulator
+constexpr int NRED = 8;  // smin, smax, ymin, ymax, s1, s2 (+ 0*v NaN accumulator), sxy, run-candidate flag
 
 struct Scratch {
   uint64_t full[kMaxStages];
@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
   const double xbar = 0.5 * (double)(W - 1);
   const double sxx = (double)W * ((double)W * (double)W - 1.0) / 12.0;  // sum (t - xbar)^2, exact here
   const double tx = (double)tid - xbar;
+  const double inv_w = 1.0 / (double)W;
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
   int s = 0;
@@ -293,6 +294,7 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
       const double K = win[rcol];  // shift for the sums: a sample of the window, so cancellation is bounded by n
       double a_smin = CUDART_INF, a_smax = -CUDART_INF, a_ymin = CUDART_INF, a_ymax = -CUDART_INF;
       double s1 = 0.0, s2 = 0.0, sB = 0.0, nanacc = 0.0;
+      bool dense_word = false;
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         const int t = tid + k * NT;
@@ -319,34 +321,41 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
         }
         const uint32_t word = __ballot_sync(kFull, cb);
         if (lane == 0) S.cmask[par2][k * NWARP + warp] = word;
+        // 49 consecutive ones span at most 3 mask words, so one of them holds >= 17 of them
+        dense_word |= __popc(word) >= 17;
       }
       // sum_k (tid + NT k - xbar) dy_k = (tid - xbar) sum dy + NT sum k dy
       double sxy = __fma_rn(tx, s1, __dmul_rn((double)NT, sB));
       a_smin = warp_min(a_smin); a_smax = warp_max(a_smax);
       a_ymin = warp_min(a_ymin); a_ymax = warp_max(a_ymax);
-      s1 = warp_sum(s1); s2 = warp_sum(s2); sxy = warp_sum(sxy); nanacc = warp_sum(nanacc);
+      // 0*v is +-0 for finite v, so adding the accumulator leaves s2 unchanged unless some v is NaN/Inf
+      s1 = warp_sum(s1); s2 = warp_sum(__dadd_rn(s2, nanacc)); sxy = warp_sum(sxy);
       if (lane == 0) {
         double* r = S.red[par2][warp];
-        r[0] = a_smin; r[1] = a_smax; r[2] = a_ymin; r[3] = a_ymax; r[4] = s1; r[5] = s2; r[6] = sxy; r[7] = nanacc;
+        r[0] = a_smin; r[1] = a_smax; r[2] = a_ymin; r[3] = a_ymax; r[4] = s1; r[5] = s2; r[6] = sxy;
+        r[7] = dense_word ? 1.0 : 0.0;
       }
       __syncthreads();  // the only block barrier of the common path; every thread is also done with the stage
 
+      double dense;
       {
         const double* r = S.red[par2][0];
-        smin = r[0]; smax = r[1]; ymin = r[2]; ymax = r[3]; s1 = r[4]; s2 = r[5]; sxy = r[6]; nanacc = r[7];
+        smin = r[0]; smax = r[1]; ymin = r[2]; ymax = r[3]; s1 = r[4]; s2 = r[5]; sxy = r[6]; dense = r[7];
 #pragma unroll
         for (int w = 1; w < NWARP; ++w) {
           r = S.red[par2][w];
           smin = r[0] < smin ? r[0] : smin; smax = r[1] > smax ? r[1] : smax;
           ymin = r[2] < ymin ? r[2] : ymin; ymax = r[3] > ymax ? r[3] : ymax;
-          s1 = __dadd_rn(s1, r[4]); s2 = __dadd_rn(s2, r[5]); sxy = __dadd_rn(sxy, r[6]); nanacc = __dadd_rn(nanacc, r[7]);
+          s1 = __dadd_rn(s1, r[4]); s2 = __dadd_rn(s2, r[5]); sxy = __dadd_rn(sxy, r[6]); dense = __dadd_rn(dense, r[7]);
         }
       }
-      // every warp scans the small-step mask for >= 49 consecutive ones (no second barrier)
+      // `dense` counts the warps that saw a dense mask word; only then scan the small-step mask for
+      // >= 49 consecutive ones (every warp does, on the same shared words: no second barrier)
       constexpr int NWORDS = R * NWARP;
-      const uint32_t a1 = lane < NWORDS ? S.cmask[par2][lane] : 0u;
-      uint32_t a49;
-      {
+      uint32_t a49 = 0u;
+      bool run49 = false;
+      if (dense != 0.0) {
+        const uint32_t a1 = lane < NWORDS ? S.cmask[par2][lane] : 0u;
         auto down = [&](uint32_t v, int d) {  // word (lane + d) of the mask, 0 past the end
           const uint32_t o = __shfl_down_sync(kFull, v, d);
           return (lane + d < 32) ? o : 0u;
@@ -359,12 +368,12 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
         const uint32_t a32 = a16 & shr(a16, 16);
         const uint32_t a48 = a32 & down(a16, 1);
         a49 = a48 & __funnelshift_r(down(a1, 1), down(a1, 2), 16);
+        run49 = __any_sync(kFull, a49 != 0u);
       }
-      const bool run49 = __any_sync(kFull, a49 != 0u);
-      // non-finite RHC <=> the shifted sum of squares is not finite (or it overflowed: recheck exactly)
+      // non-finite RHC or NaN/Inf SCG <=> the shifted sum of squares (+ the 0*v accumulator) is not finite
+      // (or it overflowed): recheck exactly.  NaN in SCG must poison the joint min/max as np.min/np.max do.
       const bool s2_bad = !(s2 <= DBL_MAX);
-      // NaN in SCG must poison the joint min/max as np.min/np.max do; Inf alone must not: recheck exactly
-      const bool scg_bad = nanacc != nanacc;
+      const bool scg_bad = s2_bad;
 
       int flat_cnt = 0;
       bool nonfinite = false;
@@ -379,7 +388,7 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
               double mx = -CUDART_INF, mn = CUDART_INF;
               for (int i = 0; i < SCGRHC_FLAT_WIN; ++i) {
                 const double v = win[(size_t)(p + i) * nsig + rcol];
-                mx = fmax(mx, v); mn = fmin(mn, v);
+                mx = v > mx ? v : mx; mn = v < mn ? v : mn;
               }
               cnt += (__dsub_rn(mx, mn) < thr) ? 1 : 0;
             }
@@ -404,12 +413,14 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
         if (tid == 0) { S.slow_cnt = 0; S.slow_flag = 0; }
       }
 
-      // Syy = sum (y-K)^2 - (sum (y-K))^2 / n ; Sxy is shift invariant because sum (t - xbar) = 0
-      const double syy = __dsub_rn(s2, __ddiv_rn(__dmul_rn(s1, s1), (double)W));
-      const double r2 = __ddiv_rn(__dmul_rn(sxy, sxy), __dmul_rn(sxx, syy));
+      // Syy = sum (y-K)^2 - (sum (y-K))^2 / n ; Sxy is shift invariant because sum (t - xbar) = 0.
+      // R^2 > 0.8  <=>  Sxy^2 > 0.8 Sxx Syy (Syy > 0): no division; the two forms can only differ inside
+      // the ambiguity band that is flagged below.
+      const double syy = __dsub_rn(s2, __dmul_rn(__dmul_rn(s1, s1), inv_w));
+      const double lhs = __dmul_rn(sxy, sxy), den = __dmul_rn(sxx, syy);
       if (flat_cnt >= 2) reason |= SCGRHC_REASON_FLAT;
-      if (r2 > 0.8) reason |= SCGRHC_REASON_STRAIGHT;
-      if (fabs(r2 - 0.8) < 1e-9) reason |= SCGRHC_REASON_AMBIGUOUS;
+      if (syy > 0.0 && lhs > __dmul_rn(0.8, den)) reason |= SCGRHC_REASON_STRAIGHT;
+      if (syy > 0.0 && fabs(__fma_rn(-0.8, den, lhs)) < __dmul_rn(1e-9, den)) reason |= SCGRHC_REASON_AMBIGUOUS;
       if (ymin < min_rhc) reason |= SCGRHC_REASON_FLOOR;  // some sample < floor <=> the minimum is
       if (nonfinite) reason |= SCGRHC_REASON_NONFINITE;
       keep = keep_all ||

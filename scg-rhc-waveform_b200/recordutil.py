@@ -1,0 +1,459 @@
+"""Drop-in for the reference's ``recordutil`` (recordutil.py:1-236): same public names and signatures,
+window preparation on the GPU.
+
+  reference call                              here
+  ------------------------------------------  -----------------------------------------------------------
+  get_chamber_intervals(record, chamber)      C planner scgrhc_plan_record (fp64 int(t*500) truncation)
+  get_segments(params[, record_name])         keep/reject of every candidate window by the fused CUDA
+                                              kernel (predicates only); returns the reference's tuples
+  SCGDataset(segments, size, mm_scg, mm_rhc)  min/max + normalise + transpose + fp32 cast on the GPU
+  get_global_minmax_vals(segments)            device reduction of per-window pairs
+  save_dataloaders(params)                    THE HOT PATH: records -> HBM -> one fused kernel pass ->
+                                              device-resident train windows, CPU valid/test windows
+  load_dataloader(path)                       unpickle; train windows go back to the GPU
+
+What consumers receive is unchanged: ``waveform_train.run`` iterates the train loader and reads batch[0],
+batch[1] ((B,C,750) and (B,1,750) fp32, already CUDA so its ``.to(device)`` is a no-op);
+``waveform_test.run`` iterates ``loader.dataset`` and calls ``.numpy()`` on item[1], so valid/test items are
+CPU tensors.  Without a CUDA device or without libscgrhc.so every entry point that needs
+arithmetic raises — there is no CPU fallback.
+"""
+import json
+import os
+import pickle
+import sys
+from datetime import datetime
+from pathlib import Path
+from time import time
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+try:
+  import wfdb
+except ImportError:  # not in this image: own format-16 reader (scgrhc/wfdbio.py)
+  from scgrhc import wfdbio as wfdb
+
+from paramutil import Params
+from pathutil import PROCESSED_DATA_PATH
+from timelog import timelog
+from waveform_noise import has_noise  # noqa: F401  (re-exported like the reference, recordutil.py:17)
+
+from scgrhc import _native as N
+from scgrhc import engine, ops
+
+SAMPLE_FREQ = 500
+
+
+def _device():
+  if not torch.cuda.is_available():
+    raise RuntimeError('recordutil needs a CUDA device: window preparation runs in libscgrhc (no CPU fallback)')
+  return torch.device('cuda', torch.cuda.current_device())
+
+
+class SCGDataset(Dataset):
+  """
+  Container dataset class SCG and RHC segments (recordutil.py:22-79).
+
+  ``segments`` is the reference's list of ``(scg (L,C) f64, rhc (L,1) f64, record_name, start_idx,
+  stop_idx)`` tuples.  Items are ``(scg f32 (C,L), rhc f32 (1,L), record_name, start_idx, stop_idx,
+  (scg_min, scg_max), (rhc_min, rhc_max))`` as in the reference (:65).  Window tensors are stored batched
+  (``.scg`` (n,C,L), ``.rhc`` (n,1,L)); ``.segments`` materialises the per-item tuples on first use.
+  """
+
+  def __init__(self, segments, segment_size, minmax_scg, minmax_rhc, device='cpu'):
+    self.segment_size = int(segment_size * SAMPLE_FREQ)
+    self.device = torch.device(device)
+    self._segments = None
+    self.segments = self.init_segments(segments, minmax_scg, minmax_rhc)
+
+  # -- reference helpers (kept for API parity; the arithmetic they describe runs in the kernel) --------
+  def pad(self, tensor):
+    """Right-pad the last dim with zeros up to segment_size (recordutil.py:30-39).  The reference's
+    '>' branch indexes three dims of a 2-D tensor and raises IndexError; so does this."""
+    if tensor.shape[-1] < self.segment_size:
+      tensor = torch.nn.functional.pad(tensor, (0, self.segment_size - tensor.shape[-1]))
+    elif tensor.shape[-1] > self.segment_size:
+      tensor = tensor[:, :, :self.segment_size]
+    return tensor
+
+  def minmax_norm(self, tensor, minmax_vals):
+    """(x - min) / (max - min + 0.0001) on the GPU in fp64 (recordutil.py:41-47); returns a numpy array."""
+    x = np.ascontiguousarray(np.asarray(tensor, dtype=np.float64))
+    L = 512                                   # element-wise with a given pair: any window split will do
+    n = max(1, -(-x.size // L))
+    flat = np.zeros((n * L, 1), dtype=np.float64)
+    flat[:x.size, 0] = x.reshape(-1)
+    mm = (float(minmax_vals[0]), float(minmax_vals[1]))
+    out = _normalise_block(flat, n, mm, mm, torch.float64, L=L)[0]
+    return out.cpu().numpy().reshape(-1)[:x.size].reshape(x.shape)
+
+  def invert(self, tensor):
+    """Transpose + fp32 cast (recordutil.py:49-53)."""
+    return torch.tensor(np.asarray(tensor).T, dtype=torch.float32)
+
+  def init_segments(self, segments, minmax_scg, minmax_rhc):
+    """Normalise every segment (recordutil.py:55-66); mutates and returns the passed list like the
+    reference.  Segments are grouped by length so that each group is one kernel launch."""
+    n = len(segments)
+    self._names = [s[2] for s in segments]
+    self._start = np.array([int(s[3]) for s in segments], dtype=np.int64)
+    self._stop = np.array([int(s[4]) for s in segments], dtype=np.int64)
+    self._mm = np.zeros((n, 4), dtype=np.float64)
+    C = segments[0][0].shape[1] if n else 0
+    scg = torch.zeros((n, C, self.segment_size), dtype=torch.float32)
+    rhc = torch.zeros((n, 1, self.segment_size), dtype=torch.float32)
+    by_len = {}
+    for i, s in enumerate(segments):
+      by_len.setdefault(s[0].shape[0], []).append(i)
+    for L, idx in by_len.items():
+      if L > self.segment_size:
+        raise IndexError('too many indices for tensor of dimension 2')   # the reference's pad() on a long segment
+      block = np.concatenate([np.concatenate([segments[i][0], segments[i][1]], axis=1) for i in idx]).astype(np.float64)
+      s_t, r_t, mm = _normalise_block(block, len(idx), minmax_scg, minmax_rhc, torch.float32, L=L)
+      ii = torch.as_tensor(idx)
+      scg[ii, :, :L] = s_t.cpu()
+      rhc[ii, :, :L] = r_t.cpu()
+      self._mm[idx] = mm
+    self.scg, self.rhc = scg.to(self.device), rhc.to(self.device)
+    for i in range(n):
+      segments[i] = self._item(i)
+    self._segments = segments
+    return segments
+
+  @classmethod
+  def from_arrays(cls, scg, rhc, names, start, stop, minmax, segment_size):
+    """Hot-path constructor: batched tensors straight from the window kernel, no per-window Python."""
+    self = cls.__new__(cls)
+    self.segment_size = int(segment_size * SAMPLE_FREQ)
+    self.device = scg.device
+    self.scg, self.rhc = scg, rhc
+    self._names, self._start, self._stop, self._mm = list(names), np.asarray(start), np.asarray(stop), np.asarray(minmax)
+    self._segments = None
+    return self
+
+  def _item(self, i):
+    mm = self._mm[i]
+    return (self.scg[i], self.rhc[i], self._names[i], int(self._start[i]), int(self._stop[i]),
+            (np.float64(mm[0]), np.float64(mm[1])), (np.float64(mm[2]), np.float64(mm[3])))
+
+  @property
+  def segments(self):
+    if self._segments is None:
+      self._segments = [self._item(i) for i in range(len(self._names))]
+    return self._segments
+
+  @segments.setter
+  def segments(self, value):
+    self._segments = value
+
+  def to(self, device):
+    self.device = torch.device(device)
+    self.scg, self.rhc = self.scg.to(self.device), self.rhc.to(self.device)
+    self._segments = None
+    return self
+
+  def collate(self, idx):
+    """What default_collate makes of items ``idx`` (recordutil.py:198): [scg (B,C,L), rhc (B,1,L), names,
+    start (B,), stop (B,), [scg_min (B,), scg_max (B,)], [rhc_min (B,), rhc_max (B,)]]."""
+    if self.scg.is_cuda:
+      ii = idx.to(self.scg.device, torch.int64).contiguous()
+      scg = torch.empty((ii.numel(),) + tuple(self.scg.shape[1:]), dtype=self.scg.dtype, device=self.scg.device)
+      rhc = torch.empty((ii.numel(),) + tuple(self.rhc.shape[1:]), dtype=self.rhc.dtype, device=self.rhc.device)
+      ops.gather_windows(self.scg, ii, scg)
+      ops.gather_windows(self.rhc, ii, rhc)
+    else:
+      scg, rhc = self.scg[idx], self.rhc[idx]
+    h = idx.cpu().numpy()
+    mm = torch.from_numpy(self._mm[h])
+    return [scg, rhc, tuple(self._names[i] for i in h), torch.from_numpy(self._start[h]), torch.from_numpy(self._stop[h]),
+            [mm[:, 0], mm[:, 1]], [mm[:, 2], mm[:, 3]]]
+
+  def __getstate__(self):
+    st = dict(self.__dict__)
+    st['scg'], st['rhc'] = self.scg.cpu(), self.rhc.cpu()
+    st['_segments'] = None
+    st['device'] = str(self.device)
+    return st
+
+  def __setstate__(self, st):
+    self.__dict__.update(st)
+    want = torch.device(st['device'])
+    self.device = want if (want.type == 'cpu' or torch.cuda.is_available()) else torch.device('cpu')
+    if self.device.type == 'cuda':
+      self.device = torch.device('cuda', torch.cuda.current_device())
+    self.scg, self.rhc = self.scg.to(self.device), self.rhc.to(self.device)
+
+  def __len__(self):
+    """
+    Get number of segments.
+    """
+    return len(self._names)
+
+  def __getitem__(self, index):
+    """
+    Iterate through segments.
+    """
+    if self._segments is not None:
+      return self._segments[index]
+    if index < 0:
+      index += len(self)
+    if not 0 <= index < len(self):
+      raise IndexError(index)
+    return self._item(index)
+
+
+class WindowLoader:
+  """The slice of ``torch.utils.data.DataLoader`` the consumers use (``len``, iteration, ``.dataset``,
+  ``.batch_size``) with device-side batch assembly: a shuffled index permutation + one gather kernel per
+  batch instead of per-item collation (recordutil.py:198-200: shuffle=True, drop_last=False)."""
+
+  def __init__(self, dataset, batch_size=1, shuffle=False, generator=None):
+    self.dataset, self.batch_size, self.shuffle, self.generator = dataset, int(batch_size), shuffle, generator
+
+  def __len__(self):
+    return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+
+  def __iter__(self):
+    n = len(self.dataset)
+    order = torch.randperm(n, generator=self.generator) if self.shuffle else torch.arange(n)
+    for b in range(0, n, self.batch_size):
+      yield self.dataset.collate(order[b:b + self.batch_size])
+
+
+def _normalise_block(block, n, minmax_scg, minmax_rhc, out_dtype, L=None):
+  """``block``: (n*L, C+1) fp64, SCG columns then RHC.  Local pairs where a ``minmax_*`` is None, the
+  given pair otherwise (recordutil.py:58-59).  Returns (scg (n,C,L), rhc (n,1,L), minmax (n,4) numpy)."""
+  dev = _device()
+  Cn = block.shape[1] - 1
+  if Cn == 0:                         # minmax_norm() helper: a bare column, treated as its own "RHC"
+    block = np.concatenate([block, block], axis=1)
+    Cn = 1
+  L = L if L is not None else block.shape[0] // n
+  arena = torch.from_numpy(np.ascontiguousarray(block)).to(dev)
+  plan = engine.Plan(np.array([(0, 0, n, 0)], dtype=engine.INTERVAL_DTYPE), n, L)
+  st = engine.prepare_windows(arena, plan, list(range(Cn)), Cn, float('-inf'), predicates_only=True, keep_all=True,
+                              check=False)
+  mm = st.minmax.clone()
+  if minmax_scg is not None:
+    mm[:, 0], mm[:, 1] = float(minmax_scg[0]), float(minmax_scg[1])
+  if minmax_rhc is not None:
+    mm[:, 2], mm[:, 3] = float(minmax_rhc[0]), float(minmax_rhc[1])
+  scg = torch.empty((n, Cn, L), dtype=out_dtype, device=dev)
+  rhc = torch.empty((n, 1, L), dtype=out_dtype, device=dev)
+  flags = N.USE_KEPT_LIST | (N.OUT_F64 if out_dtype == torch.float64 else 0)
+  ops.process_windows(arena, plan.device_intervals(dev), n, L, list(range(Cn)), Cn, float('-inf'), 1e-3, flags,
+                      [0.0] * 4, torch.arange(n, device=dev), n, scg, rhc, mm, None, None, None, None)
+  return scg, rhc, mm.cpu().numpy()
+
+
+def get_record_names():
+  """
+  Get record names in a given directory (recordutil.py:82-90; order is arbitrary there, sorted here).
+  """
+  names = set()
+  for filename in os.listdir(PROCESSED_DATA_PATH):
+    if filename.endswith('.dat') or filename.endswith('.hea'):
+      names.add(Path(filename).stem)
+  return sorted(names)
+
+
+def _read_meta(record_name):
+  with open(os.path.join(PROCESSED_DATA_PATH, f'{record_name}.json'), 'r') as f:
+    return json.load(f)
+
+
+def get_chamber_intervals(record_name, chamber):
+  """
+  Get sample intervals for when cath was in a particular chamber (recordutil.py:93-110).
+  """
+  _, _, bounds = engine.plan_record(_read_meta(record_name), chamber, 0, 1)
+  return [(int(a), int(b)) for a, b in bounds]
+
+
+def get_channels(record, channel_names, start_idx, stop_idx):
+  """
+  Get specific channels from record by channel name (recordutil.py:113-119).  A host-side copy; raises
+  ValueError for a missing channel exactly like ``list.index``.
+  """
+  indexes = [record.sig_name.index(name) for name in channel_names]
+  return record.p_signal[start_idx:stop_idx, indexes]
+
+
+def _scan_record(params, record_name):
+  """Keep flags of every candidate window of one record, decided on the GPU."""
+  record = wfdb.rdrecord(os.path.join(PROCESSED_DATA_PATH, record_name))
+  W = int(params.segment_size * SAMPLE_FREQ)
+  cols, rcol = engine.resolve_columns(record.sig_name, params.in_channels)
+  p = np.ascontiguousarray(record.p_signal[:, cols + [rcol]], dtype=np.float64)
+  plan = engine.plan_cohort([_read_meta(record_name)], params.chamber, [p.shape[0]], W)
+  arena = torch.from_numpy(p).to(_device())
+  st = engine.prepare_windows(arena, plan, list(range(len(cols))), len(cols), params.min_RHC, predicates_only=True)
+  return record, plan, st.keep.cpu().numpy().astype(bool)
+
+
+def get_segments(params, record_name=None):
+  """
+  Get segments of a given size with the specified SCG channels (recordutil.py:122-149): the reference's
+  list of (scg (W,C) view, rhc (W,1) view, record_name, start_idx, stop_idx) for windows without noise.
+  """
+  if record_name is None:
+    segments = []
+    for record_name in get_record_names():
+      segments.extend(get_segments(params, record_name=record_name))
+    return segments
+  record, plan, keep = _scan_record(params, record_name)
+  W = plan.W
+  segments, cand = [], 0
+  for interval in get_chamber_intervals(record_name, params.chamber):
+    scg_signal = get_channels(record, params.in_channels, interval[0], interval[1])
+    rhc_signal = get_channels(record, ['RHC_pressure'], interval[0], interval[1])
+    for i in range(scg_signal.shape[0] // W):
+      if keep[cand]:
+        segments.append((scg_signal[i * W:(i + 1) * W], rhc_signal[i * W:(i + 1) * W], record_name, i * W, i * W + W))
+      cand += 1
+  return segments
+
+
+def get_global_minmax_vals(segments):
+  """
+  Get min and max values for normalization (recordutil.py:152-169): ((scg_min, scg_max), (rhc_min, rhc_max))
+  over all given segments, reduced on the GPU.
+  """
+  if len(segments) == 0:
+    return (None, None), (None, None)
+  dev = _device()
+  by_len = {}
+  for s in segments:
+    by_len.setdefault(s[0].shape[0], []).append(s)
+  parts = []
+  for L, group in by_len.items():
+    block = np.concatenate([np.concatenate([s[0], s[1]], axis=1) for s in group]).astype(np.float64)
+    Cn = block.shape[1] - 1
+    arena = torch.from_numpy(np.ascontiguousarray(block)).to(dev)
+    plan = engine.Plan(np.array([(0, 0, len(group), 0)], dtype=engine.INTERVAL_DTYPE), len(group), L)
+    st = engine.prepare_windows(arena, plan, list(range(Cn)), Cn, float('-inf'), predicates_only=True, keep_all=True,
+                                check=False, use_global_min_max=True)
+    parts.append(st.global_minmax.cpu().numpy())
+  g = np.stack(parts)
+  return ((np.float64(g[:, 0].min()), np.float64(g[:, 1].max())), (np.float64(g[:, 2].min()), np.float64(g[:, 3].max())))
+
+
+def train_valid_test_split(n, seed=None):
+  """Index split with sklearn's ``train_test_split(train_size=0.9)`` then ``(train_size=0.5)`` arithmetic
+  (recordutil.py:191-192): n_train = floor(0.9 n), the rest is split floor(0.5 m) / remainder; indices come
+  from one permutation per call, test part first, exactly as ShuffleSplit draws them.  ``seed=None`` uses
+  numpy's global RandomState like the reference (unseeded there)."""
+  rng = np.random.mtrand._rand if seed is None else np.random.RandomState(seed)
+
+  def split(idx, frac):
+    m = len(idx)
+    n_train = int(np.floor(frac * m))
+    n_test = m - n_train
+    if m and n_train == 0:
+      raise ValueError('With n_samples=%d, test_size=None and train_size=%s, the resulting train set will be empty. '
+                       'Adjust any of the aforementioned parameters.' % (m, frac))
+    perm = rng.permutation(m)
+    return idx[perm[n_test:n_test + n_train]], idx[perm[:n_test]]
+
+  train, rest = split(np.arange(n), 0.9)
+  valid, test = split(rest, 0.5)
+  return train, valid, test
+
+
+def prepare_cohort(params, record_names=None):
+  """Records -> HBM -> fused window kernel.  Returns (WindowStore, record_names): every kept window of the
+  cohort, device resident, in the reference's order (records in ``record_names`` order)."""
+  names = list(record_names) if record_names is not None else get_record_names()
+  W = int(params.segment_size * SAMPLE_FREQ)
+  C = len(params.in_channels)
+  blocks, metas, rows = [], [], []
+  for name in names:
+    record = wfdb.rdrecord(os.path.join(PROCESSED_DATA_PATH, name))
+    cols, rcol = engine.resolve_columns(record.sig_name, params.in_channels)
+    blocks.append(np.ascontiguousarray(record.p_signal[:, cols + [rcol]], dtype=np.float64))
+    metas.append(_read_meta(name))
+    rows.append(blocks[-1].shape[0])
+  plan = engine.plan_cohort(metas, params.chamber, rows, W, names)
+  dev = _device()
+  total = int(sum(rows))
+  host = torch.empty((total, C + 1), dtype=torch.float64, pin_memory=True)
+  at = 0
+  for b in blocks:
+    host[at:at + b.shape[0]] = torch.from_numpy(b)
+    at += b.shape[0]
+  arena = host.to(dev, non_blocking=True)
+  store = engine.prepare_windows(arena, plan, list(range(C)), C, params.min_RHC,
+                                 use_global_min_max=bool(params.use_global_min_max))
+  return store, names
+
+
+def save_dataloaders(params):
+  """
+  Get training and test segments, then save as loader objects (recordutil.py:172-216).
+  """
+  if os.path.exists(params.train_path):
+    raise Exception('Train file already exists!')
+  elif os.path.exists(params.valid_path):
+    raise Exception('Valid file already exists!')
+  elif os.path.exists(params.test_path):
+    raise Exception('Test file already exists!')
+
+  store, names = prepare_cohort(params)
+  n_all = store.n_kept
+  train_idx, valid_idx, test_idx = train_valid_test_split(n_all, getattr(params, 'split_seed', None))
+
+  rec_id = store.rec_id.cpu().numpy()
+  start, stop = store.start_idx.cpu().numpy(), store.stop_idx.cpu().numpy()
+  mm = store.kept_minmax().cpu().numpy()
+
+  def make(idx, device):
+    pos = torch.as_tensor(idx, dtype=torch.int64, device=store.kept_idx.device)
+    scg, rhc = store.gather(pos)
+    return SCGDataset.from_arrays(scg.to(device), rhc.to(device), [names[r] for r in rec_id[idx]], start[idx], stop[idx],
+                                  mm[idx], params.segment_size)
+
+  train_set = make(train_idx, store.kept_idx.device)     # stays in HBM for waveform_train
+  valid_set = make(valid_idx, 'cpu')                     # waveform_test calls .numpy() on items
+  test_set = make(test_idx, 'cpu')
+
+  train_loader = WindowLoader(train_set, batch_size=params.batch_size, shuffle=True)
+  valid_loader = WindowLoader(valid_set, batch_size=1, shuffle=True)
+  test_loader = WindowLoader(test_set, batch_size=1, shuffle=True)
+
+  with open(params.train_path, 'wb') as f:
+    pickle.dump(train_loader, f)
+
+  with open(params.valid_path, 'wb') as f:
+    pickle.dump(valid_loader, f)
+
+  with open(params.test_path, 'wb') as f:
+    pickle.dump(test_loader, f)
+
+  with open(os.path.join(params.dir_path, 'record_log.txt'), 'w') as f:
+    f.write(f'Dataset created: {datetime.now()}\n')
+    f.write(f'All segments: {n_all}\n')
+    f.write(f'Valid segments: {len(valid_idx)}\n')
+    f.write(f'Train segments: {len(train_idx)}\n')
+    f.write(f'Test segments: {len(test_idx)}\n')
+
+
+def load_dataloader(path):
+  """
+  Load prior loader object (recordutil.py:219-224).
+  """
+  with open(path, 'rb') as f:
+    return pickle.load(f)
+
+
+def run(params):
+  start_time = time()
+  print(timelog(f'Run recordutil for {params.dir_path}', start_time))
+  save_dataloaders(params)
+
+
+if __name__ == '__main__':
+  dir_path = sys.argv[1]
+  params = Params(os.path.join(dir_path, 'params.json'))
+  run(params)

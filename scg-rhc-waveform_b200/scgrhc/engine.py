@@ -36,7 +36,8 @@ def event_table(meta, chamber):
   events['END'] = (t1 - t0).total_seconds()
   keys = list(events.keys())
   times = np.array([float(events[k]) for k in keys], dtype=np.float64)
-  match = np.array([k.split('_')[0] == chamber for k in keys], dtype=np.uint8)
+  # '*' (extension, waveform_01 legacy default): every chamber event, i.e. no chamber segmentation
+  match = np.array([(k != 'END') if chamber == '*' else (k.split('_')[0] == chamber) for k in keys], dtype=np.uint8)
   return times, match
 
 

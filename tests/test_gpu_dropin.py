@@ -1,0 +1,174 @@
+"""GPU: the drop-in modules (waveform_noise, recordutil) behind the reference's own signatures, checked
+against fixtures produced by the unmodified reference and against the oracle."""
+import json
+import os
+import pickle
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import scgrhc_oracle as orc
+from oracle import synth_ref
+from oracle.ref_harness import FakeRecord
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+import recordutil  # noqa: E402
+import waveform_noise  # noqa: E402
+from scgrhc import wfdbio  # noqa: E402
+
+P50 = types.SimpleNamespace(min_RHC=-50)
+
+
+def test_waveform_noise_api_matches_reference():
+  g = np.load(os.path.join(H.GOLDEN, 'predicates.npz'))
+  names, ys = H.predicate_inputs()
+  n_adv = int(g['n_adv'])
+  segs = json.loads(str(g['adv_segments']))
+  for i in range(n_adv):
+    y = ys[i]
+    assert waveform_noise.get_flat_lines(y) == [tuple(s) for s in segs[i]], names[i]
+    assert waveform_noise.is_straight_line(y) == bool(g['straight'][i]), names[i]
+    assert waveform_noise.in_rhc_range(P50, y) == bool(g['in_range'][i]), names[i]
+    assert waveform_noise.has_noise(P50, y) == bool(g['has_noise'][i]), names[i]
+  assert (waveform_noise.has_noise_batch(P50, ys) == g['has_noise']).all()
+  # non-default arguments and other lengths go through the standalone kernels
+  y = ys[0][:300]
+  assert waveform_noise.get_flat_lines(y, threshold=0.5, min_duration=0.02, sampling_rate=250) == \
+      orc.flat_segments(y, threshold=0.5, min_duration=0.02, sampling_rate=250)
+  long = np.concatenate([ys[0], ys[1], ys[2]])
+  assert waveform_noise.has_noise(P50, long) == orc.has_noise(long, -50)
+  assert waveform_noise.is_straight_line(0.5 * np.arange(2000) + 3) is True
+  with pytest.raises(ValueError):
+    bad = ys[0].copy(); bad[5] = np.nan
+    waveform_noise.has_noise(P50, bad)
+
+
+@pytest.fixture
+def data_root(tmp_path, monkeypatch):
+  records = {}
+  monkeypatch.setattr(recordutil, 'PROCESSED_DATA_PATH', str(tmp_path))
+  monkeypatch.setattr(recordutil.wfdb, 'rdrecord', lambda path: records[os.path.basename(path)])
+
+  def add(name, sig, p, meta):
+    records[name] = FakeRecord(sig, p)
+    (tmp_path / (name + '.json')).write_text(json.dumps(meta))
+    (tmp_path / (name + '.hea')).write_text('')
+  return add
+
+
+def cfg_params(cfg, **over):
+  c = H.effective_config(cfg)
+  c.update(over)
+  return types.SimpleNamespace(**c)
+
+
+def test_recordutil_api_matches_reference(data_root):
+  g = np.load(os.path.join(H.GOLDEN, 'record_small.npz'))
+  sig, p, meta = H.small_record()
+  data_root('small', sig, p, meta)
+  assert recordutil.get_record_names() == ['small']
+  for name, case in H.load_json('intervals.json').items():
+    data_root(name, ['RHC_pressure'], np.zeros((1, 1)), case['meta'])
+    for chamber, want in case['intervals'].items():
+      assert [list(x) for x in recordutil.get_chamber_intervals(name, chamber)] == want
+  for cfg in ('waveform_06', 'waveform_10', 'waveform_19'):
+    params = cfg_params(cfg)
+    segs = recordutil.get_segments(params, record_name='small')
+    assert [s[3] for s in segs] == g[cfg + '.start'].tolist() and [s[4] for s in segs] == g[cfg + '.stop'].tolist()
+    assert all(s[0].shape == (750, len(params.in_channels)) and s[1].shape == (750, 1) and s[2] == 'small' for s in segs)
+    gm = recordutil.get_global_minmax_vals(segs)
+    want = orc.global_minmax(g[cfg + '.minmax'])
+    assert [gm[0][0], gm[0][1], gm[1][0], gm[1][1]] == want.tolist()
+    raw = list(segs)
+    ds = recordutil.SCGDataset(segs, params.segment_size, None, None)
+    assert ds.segments is segs and len(ds) == len(raw) and ds.segment_size == 750
+    for i in (0, len(ds) - 1):
+      item = ds[i]
+      assert item is segs[i] and len(item) == 7
+      assert item[0].dtype == torch.float32 and not item[0].is_cuda and tuple(item[0].shape) == (len(params.in_channels), 750)
+      assert item[0].numpy().tobytes() == g[cfg + '.scg'][i].tobytes()
+      assert item[1].numpy().tobytes() == g[cfg + '.rhc'][i].tobytes()
+      assert (item[2], item[3], item[4]) == ('small', raw[i][3], raw[i][4])
+      assert [item[5][0], item[5][1], item[6][0], item[6][1]] == g[cfg + '.minmax'][i].tolist()
+      assert isinstance(item[5][0], np.float64)
+    # dataset-global pairs (use_global_min_max): same arithmetic with the given pairs
+    ds2 = recordutil.SCGDataset(list(raw), params.segment_size, gm[0], gm[1])
+    s0 = ((raw[0][0] - gm[0][0]) / (gm[0][1] - gm[0][0] + 0.0001)).T.astype(np.float32)
+    assert ds2[0][0].numpy().tobytes() == s0.tobytes() and ds2[0][5] == gm[0]
+    # helper methods kept from the reference
+    mn = ds.minmax_norm(raw[0][0], (raw[0][0].min(), raw[0][0].max()))
+    assert mn.tobytes() == orc.minmax_norm(raw[0][0], raw[0][0].min(), raw[0][0].max()).tobytes()
+    assert ds.pad(torch.zeros(2, 700)).shape[-1] == 750
+    with pytest.raises(IndexError):
+      ds.pad(torch.zeros(2, 800))
+  with pytest.raises(ValueError):
+    recordutil.get_segments(cfg_params('waveform_06', in_channels=['nope']), record_name='small')
+
+
+def test_save_dataloaders_end_to_end(tmp_path, monkeypatch):
+  """Records on disk (WFDB format 16) -> save_dataloaders -> pickles -> what the consumers read."""
+  root = tmp_path / 'data'; root.mkdir()
+  exp = tmp_path / 'waveform_06'; exp.mkdir()
+  monkeypatch.setattr(recordutil, 'PROCESSED_DATA_PATH', str(root))
+  monkeypatch.setattr(recordutil, 'wfdb', wfdbio)
+  sig = synth_ref.SIG_NAMES_5
+  meta = synth_ref.record_meta(120, events={'RA_1': 0, 'PA_1': 20, 'RV_1': 100})
+  want = {}
+  for r in range(3):
+    p = synth_ref.gen_record(H.SEED, 40 + r, 60000, kinds=synth_ref.kinds_for(sig))
+    wfdbio.wrsamp('rec%d' % r, 500, ['g', 'g', 'g', 'mmHg', 'mV'], sig, p, write_dir=str(root))
+    (root / ('rec%d.json' % r)).write_text(json.dumps(meta))
+    q = wfdbio.rdrecord(str(root / ('rec%d' % r))).p_signal          # what the pipeline sees after quantisation
+    rw = orc.scan_record(q, sig, meta, sig[:3], 'PA', 1.5, -50)
+    s, rr, mm = orc.normalise_record(q, sig, sig[:3], rw)
+    for k, st in enumerate(rw.rel_start[rw.keep]):
+      want[('rec%d' % r, int(st))] = (s[k], rr[k], mm[k])
+  c = H.effective_config('waveform_06')
+  params = types.SimpleNamespace(dir_path=str(exp), train_path=str(exp / 'loader_train.pickle'),
+                                 valid_path=str(exp / 'loader_valid.pickle'), test_path=str(exp / 'loader_test.pickle'),
+                                 batch_size=16, split_seed=3, **{k: c[k] for k in ('in_channels', 'chamber', 'segment_size', 'min_RHC', 'use_global_min_max')})
+  recordutil.run(params)
+  with pytest.raises(Exception, match='Train file already exists!'):
+    recordutil.save_dataloaders(params)
+  log = (exp / 'record_log.txt').read_text().splitlines()
+  counts = {ln.split(':')[0]: int(ln.split(':')[1]) for ln in log[1:]}
+  n = len(want)
+  assert counts['All segments'] == n and counts['Train segments'] == int(np.floor(0.9 * n))
+  assert counts['Valid segments'] + counts['Test segments'] + counts['Train segments'] == n
+  train = recordutil.load_dataloader(params.train_path)
+  valid = recordutil.load_dataloader(params.valid_path)
+  with open(params.test_path, 'rb') as f:
+    test = pickle.load(f)                                   # waveform_test.py:115-116
+  seen = set()
+  # waveform_train.py:357-362: iterate batches, take [0] and [1], .to(device)
+  assert len(train) == -(-counts['Train segments'] // 16)
+  nb = 0
+  for i, segment in enumerate(train):
+    scg, rhc = segment[0], segment[1]
+    assert scg.is_cuda and rhc.is_cuda and scg.dtype == torch.float32
+    assert scg.to('cuda') is scg
+    assert scg.shape[1:] == (3, 750) and rhc.shape[1:] == (1, 750) and len(segment) == 7
+    for b in range(scg.shape[0]):
+      key = (segment[2][b], int(segment[3][b]))
+      s, r, mm = want[key]
+      assert scg[b].cpu().numpy().tobytes() == s.tobytes() and rhc[b].cpu().numpy().tobytes() == r.tobytes()
+      assert int(segment[4][b]) == key[1] + 750 and float(segment[5][0][b]) == mm[0] and float(segment[6][1][b]) == mm[3]
+      seen.add(key)
+    nb += 1
+  assert nb == len(train)
+  # waveform_test.py:58-67: iterate loader.dataset, .unsqueeze(0), .detach().numpy(), unpack item[6]
+  for loader in (valid, test):
+    for segment in loader.dataset:
+      scg = segment[0].unsqueeze(0)
+      real = segment[1].detach().numpy()[0, :]
+      min_rhc, max_rhc = segment[6]
+      key = (segment[2], int(segment[3]))
+      s, r, mm = want[key]
+      assert scg.shape == (1, 3, 750) and real.tobytes() == r[0].tobytes() and (min_rhc, max_rhc) == (mm[2], mm[3])
+      assert int(segment[4]) == key[1] + 750
+      seen.add(key)
+  assert seen == set(want)                                  # every kept window lands in exactly one split

@@ -1,0 +1,120 @@
+"""CPU tests: C-ABI exports, host planner, params loader, WFDB I/O, split arithmetic, gloo all-reduce."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import scgrhc_oracle as orc
+from oracle import synth_ref
+from tests import helpers as H
+
+import scgrhc  # noqa: E402
+from scgrhc import _native as N  # noqa: E402
+from scgrhc import wfdbio  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+  with open(os.path.join(ROOT, 'include', 'scgrhc.h')) as f:
+    declared = set(re.findall(r'^(?:int|void|const char\*)\s+(scgrhc_[a-z0-9_]+)\s*\(', f.read(), flags=re.M))
+  assert declared == set(N.SYMBOLS), declared ^ set(N.SYMBOLS)
+  lib = ctypes.CDLL(scgrhc._native._build.LIB)
+  for name in declared:
+    assert hasattr(lib, name), name
+  assert lib.scgrhc_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_a_device():
+  if torch.cuda.is_available():
+    pytest.skip('a CUDA device is present')
+  lib = N.lib()
+  h = ctypes.c_void_p()
+  assert lib.scgrhc_ctx_create(0, ctypes.byref(h)) == N.ERR_NO_DEVICE
+  assert b'no CPU fallback' in lib.scgrhc_last_error(None)
+  with pytest.raises(NotImplementedError):
+    torch.ops.scgrhc.rolling_range_lt(torch.zeros(8, dtype=torch.float64), 4, 1e-3, torch.zeros(8, dtype=torch.uint8))
+  import waveform_noise
+  with pytest.raises(RuntimeError):
+    waveform_noise.get_flat_lines(np.zeros(100))
+
+
+def test_planner_matches_reference_intervals_and_slicing():
+  cases = H.load_json('intervals.json')
+  for name, case in cases.items():
+    for chamber, want in case['intervals'].items():
+      iv, n, bounds = scgrhc.plan_record(case['meta'], chamber, 0, 750)
+      assert [list(b) for b in bounds] == want, (name, chamber)
+      for T in (0, 1, 749, 750, 100000, 299999, 600500):
+        iv, n, _ = scgrhc.plan_record(case['meta'], chamber, T, 750, rec_base_row=123, rec_id=4, cand_base=9)
+        a, r, w = orc.candidate_windows([tuple(b) for b in want], T, 750)
+        mine = np.concatenate([i['row0'] - 123 + np.arange(i['n_win']) * 750 for i in iv]) if len(iv) else np.zeros(0)
+        assert n == len(a) and (mine == a).all(), (name, chamber, T)
+        if len(iv):
+          assert iv['cand0'][0] == 9 and (np.diff(iv['cand0']) == iv['n_win'][:-1]).all() and (iv['rec_id'] == 4).all()
+
+
+def test_plan_uniform_equals_plan_cohort():
+  meta = synth_ref.record_meta(600)
+  a = scgrhc.plan_uniform(meta, 'PA', 300000, 750, 5, rec0=3)
+  b = scgrhc.plan_cohort([meta] * 5, 'PA', [300000] * 5, 750)
+  assert a.n_cand == b.n_cand == 1000
+  assert (a.intervals['row0'] == b.intervals['row0']).all() and (a.intervals['cand0'] == b.intervals['cand0']).all()
+  assert (a.intervals['rec_id'] == b.intervals['rec_id'] + 3).all()
+
+
+def test_params_loads_all_37_configs(tmp_path):
+  from paramutil import Params
+  table = H.configs()
+  for cfg, c in table.items():
+    data = {k: c[k] for k in ('in_channels', 'chamber', 'segment_size', 'batch_size', 'min_RHC', 'use_global_min_max') if k in c}
+    for k in c['all_keys']:
+      data.setdefault(k, 1 if k not in ('dir_path', 'train_path', 'valid_path', 'test_path', 'checkpoint_dir_path',
+                                         'comparison_dir_path', 'pred_top_dir_path', 'pred_rand_dir_path') else k)
+    data['dir_path'] = cfg
+    p = tmp_path / (cfg + '.json')
+    p.write_text(json.dumps(data))
+    params = Params(str(p))
+    assert params.in_channels == c['in_channels'] and params.segment_size == 1.5
+    assert params.train_path == os.path.join(cfg, 'train_path')
+    if c['reference_params_error'] is None:
+      assert params.chamber == c['chamber'] and params.min_RHC == -50 and params.use_global_min_max is False
+      Params(str(p), strict=True)
+    else:
+      with pytest.raises(KeyError):                 # the reference's own loader rejects these five
+        Params(str(p), strict=True)
+      assert params.min_RHC == float('-inf') and params.use_global_min_max is False
+      assert params.chamber == c.get('chamber', '*')
+
+
+def test_wfdbio_roundtrip(tmp_path):
+  sig = synth_ref.SIG_NAMES_5
+  p = synth_ref.gen_record(H.SEED, 9, 5000, kinds=synth_ref.kinds_for(sig))
+  d, gain, base = wfdbio.wrsamp('r9', 500, ['g'] * 3 + ['mmHg', 'mV'], sig, p, write_dir=str(tmp_path))
+  rec = wfdbio.rdrecord(str(tmp_path / 'r9'))
+  assert rec.sig_name == sig and rec.fs == 500 and rec.p_signal.shape == p.shape
+  assert (rec.d_signal == d).all()
+  want = (d.astype(np.float64) - np.array(base, dtype=np.float64)) / np.array(gain)
+  assert rec.p_signal.tobytes() == want.tobytes()
+  assert np.abs(rec.p_signal - p).max() <= 0.5 / min(gain) * 1.0001
+
+
+def test_split_arithmetic_matches_sklearn():
+  import runpy
+  runpy.run_path(os.path.join(ROOT, 'tests', 'recordutil_split_probe.py'))
+
+
+def test_gloo_minmax_allreduce_and_sharding():
+  script = os.path.join(ROOT, 'tests', 'dist_worker.py')
+  env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29533')
+  out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29533', script],
+                       capture_output=True, text=True, env=env, timeout=300)
+  assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+  assert 'DIST_OK' in out.stdout
