@@ -169,7 +169,9 @@ int scgrhc_synth_records(scgrhc_ctx* ctx, uint64_t seed, int64_t rec0, int64_t n
 /* ---- diagnostics: compares the kernel's reciprocal-based division (Markstein correction) with
  *      IEEE division on n hashed operand pairs; counts (device, 3 x uint64): fp64 mismatches,
  *      mismatches after the fp32 cast, pairs evaluated.  mode 0: operands shaped like the
- *      normalisation (0 <= a < d, d in [1e-4, 1e3]); mode 1: |exponents| up to 400. */
+ *      normalisation (min <= x <= max, ranges 2^-14..2^10); mode 1: exponents up to +-1000, zeros (selects the
+ *      IEEE loop); mode 2: the integer-checked fp32 tier, half of the quotients planted within 8 ulp64 of float
+ *      rounding boundaries — counts = {operands not eligible, fp32 mismatches among unflagged, flagged}. */
 int scgrhc_selftest_div(scgrhc_ctx* ctx, uint64_t seed, int64_t n, int32_t mode, uint64_t* counts, void* stream);
 
 #ifdef __cplusplus

@@ -50,6 +50,11 @@ def test_division_by_reciprocal_is_correctly_rounded():
     assert bad64 == 0 and bad32 == 0, (mode, bad64, bad32)
     # mode 0 is shaped like real windows and must stay on the reciprocal path; mode 1 mixes in the IEEE loop
     assert n_fast > (0.99 if mode == 0 else 0.01) * (1 << 28), (mode, n_fast)
+  # fp32 tier: every element the integer check lets through must round to the reference's float;
+  # elements planted on float rounding boundaries must be flagged (and only about that many)
+  ineligible, bad32, flagged = ops.selftest_div(0, 77, 1 << 28, 2)
+  assert bad32 == 0 and ineligible < 1e-4 * (1 << 28), (bad32, ineligible)   # |min| < 2^-10 falls to the next tier
+  assert 1e-3 * (1 << 28) < flagged < 0.55 * (1 << 28), flagged   # planted boundaries survive rounding of x only in part
 
 
 def test_predicates_match_reference_golden():
