@@ -316,7 +316,7 @@ def run_b200(args):
   except Exception:
     pass
   roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-              'traffic': traffic, 'kernel': 'scgrhc::window_kernel<C=3,NSIG4,float,R=6>', 'kernel_ms': ms_kernel,
+              'traffic': traffic, 'kernel': 'scgrhc::window_kernel<C=3,NSIG4,IDENT,%s,W=750>' % ('double' if args.out_f64 else 'float'), 'kernel_ms': ms_kernel,
               'algorithmic_bytes_per_launch': alg, 'peak_source': peak_src,
               'bytes_per_kept_window': W * C * 8 + W * 8 + W * (C + 1) * out_bytes + 53}
 
@@ -363,7 +363,8 @@ def run_b200(args):
 
   if rank == 0:
     sampler.stop()
-  clocks = sampler.summary(windows) if rank == 0 else None
+  clocks = sampler.summary(windows[:1]) if rank == 0 else None          # the device-resident timed region
+  clocks_e2e = sampler.summary(windows[1:]) if rank == 0 and len(windows) > 1 else None
 
   cpu = cpu_fast_d = None
   if rank == 0 and world == 1 and not args.no_cpu:
@@ -393,7 +394,7 @@ def run_b200(args):
             'roofline': roofline, 'cpu_baseline': cpu, 'cpu_baseline_fast': cpu_fast_d, 'e2e': e2e,
             'gpu_launches': args.steps * (4 + (2 if args.global_minmax else 0)),
             'launches_per_step': 'window_kernel + count_kept + scan_blocks + scatter_kept',
-            'clocks': clocks}
+            'clocks': clocks, 'clocks_e2e': clocks_e2e}
     print(json.dumps(line), flush=True)
   if world > 1:
     dist.destroy_process_group()
