@@ -155,6 +155,12 @@ int scgrhc_gather_windows(scgrhc_ctx* ctx, const void* store, const int64_t* slo
 int scgrhc_rolling_range_lt(scgrhc_ctx* ctx, const double* y, int64_t n, int32_t m, double threshold,
                             uint8_t* flags, void* stream);
 
+/* ---- record ingest (what wfdb.rdrecord does on the host at recordutil.py:137): WFDB format-16 digital frames
+ *      d (T, nsig_in) int16, device -> physical fp64 samples out (T, ncols), device, for the selected columns:
+ *      (d - baseline) / gain, the invalid code -32768 -> NaN.  gain/baseline/cols are host arrays of ncols entries. */
+int scgrhc_decode_fmt16(scgrhc_ctx* ctx, const int16_t* d, int64_t T, int32_t nsig_in, const int32_t* cols,
+                        int32_t ncols, const double* gain, const double* baseline, double* out, void* stream);
+
 /* ---- is_straight_line / in_rhc_range on waveforms of any length (waveform_noise.py:29-41), one
  *      waveform per row of y (n_wave, L); stats (n_wave, 6) = {R^2, min, max, below_floor, nonfinite, sum} */
 int scgrhc_waveform_stats(scgrhc_ctx* ctx, const double* y, int64_t n_wave, int64_t L, double min_rhc,

@@ -321,6 +321,28 @@ extern "C" int scgrhc_rolling_range_lt(scgrhc_ctx* ctx, const double* y, int64_t
   return SCGRHC_OK;
 }
 
+extern "C" int scgrhc_decode_fmt16(scgrhc_ctx* ctx, const int16_t* d, int64_t T, int32_t nsig_in, const int32_t* cols,
+                                   int32_t ncols, const double* gain, const double* baseline, double* out, void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (T < 0 || nsig_in < 1 || ncols < 1 || ncols > SCGRHC_MAX_C + 1 || !cols || !gain || !baseline || (T && (!d || !out)))
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "decode_fmt16: bad arguments (1..%d output columns)", SCGRHC_MAX_C + 1);
+  DecodeParams P;
+  P.d = d; P.out = out; P.T = T; P.nsig_in = nsig_in; P.ncols = ncols;
+  for (int j = 0; j < ncols; ++j) {
+    if (cols[j] < 0 || cols[j] >= nsig_in) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "decode_fmt16: column %d outside 0..%d", cols[j], nsig_in - 1);
+    if (gain[j] == 0.0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "decode_fmt16: zero gain");
+    P.cols[j] = cols[j]; P.gain[j] = gain[j]; P.baseline[j] = baseline[j];
+  }
+  if (T == 0) return SCGRHC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const long long total = T * ncols;
+  const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16);
+  decode_fmt16_kernel<<<grid, 256, 0, st>>>(P);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
 extern "C" int scgrhc_waveform_stats(scgrhc_ctx* ctx, const double* y, int64_t n_wave, int64_t L, double min_rhc,
                                      double* stats, void* stream) {
   if (!ctx) return SCGRHC_ERR_BAD_ARG;

@@ -168,6 +168,28 @@ __global__ void __launch_bounds__(256) gather_windows_kernel(const unsigned char
   }
 }
 
+// ---- record ingest: WFDB format-16 digital frames -> physical fp64 samples on the device ------------------
+// wfdb's dac(): p = (d - baseline) / gain in fp64, the invalid-sample code -32768 -> NaN.  Only the selected
+// columns are produced, so the arena the window kernel reads is (rows, ncols) with the identity column map.
+struct DecodeParams {
+  const short* d;          // (T, nsig_in) interleaved frames
+  double* out;             // (T, ncols)
+  long long T;
+  int nsig_in, ncols;
+  int cols[SCGRHC_MAX_C + 1];
+  double gain[SCGRHC_MAX_C + 1], baseline[SCGRHC_MAX_C + 1];
+};
+__global__ void __launch_bounds__(256) decode_fmt16_kernel(const __grid_constant__ DecodeParams P) {
+  const long long total = P.T * P.ncols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long t = e / P.ncols;
+    const int j = (int)(e - t * P.ncols);
+    const short d = P.d[t * P.nsig_in + P.cols[j]];
+    const double v = __ddiv_rn(__dsub_rn((double)d, P.baseline[j]), P.gain[j]);
+    P.out[e] = d == -32768 ? __longlong_as_double(0x7ff8000000000000LL) : v;
+  }
+}
+
 // ---- standalone rolling range (API parity of get_flat_lines with non-default arguments) ------------
 __global__ void rolling_range_lt_kernel(const double* __restrict__ y, long long n, int m, double thr,
                                         uint8_t* __restrict__ flags) {

@@ -362,30 +362,57 @@ def train_valid_test_split(n, seed=None):
   return train, valid, test
 
 
-def prepare_cohort(params, record_names=None):
+def prepare_cohort(params, record_names=None, chunk_records=32):
   """Records -> HBM -> fused window kernel.  Returns (WindowStore, record_names): every kept window of the
-  cohort, device resident, in the reference's order (records in ``record_names`` order)."""
+  cohort, device resident, in the reference's order (records in ``record_names`` order).
+
+  Ingest: when the reader exposes the digital frames (``d_signal``/``adc_gain``/``baseline``, as scgrhc.wfdbio
+  does for format-16 records) the selected columns travel to the GPU as int16 and are converted there
+  ((d - baseline) / gain in fp64, what wfdb.rdrecord does on the host at recordutil.py:137); otherwise the fp64
+  ``p_signal`` columns are uploaded.  Only the C SCG columns + RHC are uploaded, so the arena always has the
+  identity column layout."""
   names = list(record_names) if record_names is not None else get_record_names()
   W = int(params.segment_size * SAMPLE_FREQ)
   C = len(params.in_channels)
-  blocks, metas, rows = [], [], []
+  blocks, metas, rows, gains, bases = [], [], [], [], []
+  digital = True
   for name in names:
     record = wfdb.rdrecord(os.path.join(PROCESSED_DATA_PATH, name))
     cols, rcol = engine.resolve_columns(record.sig_name, params.in_channels)
-    blocks.append(np.ascontiguousarray(record.p_signal[:, cols + [rcol]], dtype=np.float64))
+    sel = cols + [rcol]
+    digital = digital and getattr(record, 'd_signal', None) is not None and getattr(record, 'adc_gain', None) is not None \
+        and getattr(record, 'baseline', None) is not None and record.d_signal.dtype == np.int16
+    blocks.append((record, sel))
     metas.append(_read_meta(name))
-    rows.append(blocks[-1].shape[0])
+    rows.append(record.d_signal.shape[0] if digital else record.p_signal.shape[0])
   plan = engine.plan_cohort(metas, params.chamber, rows, W, names)
   dev = _device()
   total = int(sum(rows))
-  host = torch.empty((total, C + 1), dtype=torch.float64, pin_memory=True)
+  host = torch.empty((total, C + 1), dtype=torch.int16 if digital else torch.float64, pin_memory=True)
   at = 0
-  for b in blocks:
-    host[at:at + b.shape[0]] = torch.from_numpy(b)
-    at += b.shape[0]
-  arena = host.to(dev, non_blocking=True)
-  store = engine.prepare_windows(arena, plan, list(range(C)), C, params.min_RHC,
-                                 use_global_min_max=bool(params.use_global_min_max))
+  for (record, sel), n in zip(blocks, rows):
+    if digital:
+      host[at:at + n] = torch.from_numpy(np.ascontiguousarray(record.d_signal[:, sel]))
+      gains.append([float(record.adc_gain[j]) for j in sel])
+      bases.append([float(record.baseline[j]) for j in sel])
+    else:
+      host[at:at + n] = torch.from_numpy(np.ascontiguousarray(record.p_signal[:, sel], dtype=np.float64))
+    at += n
+  if not params.use_global_min_max:
+    ing = engine.HostIngest(plan, rows, C + 1, dev, chunk_records=chunk_records, digital_nsig=(C + 1) if digital else None)
+    store = ing.run(host, list(range(C)), C, params.min_RHC, decode=(list(range(C + 1)), gains, bases) if digital else None)
+    return store, names
+  # dataset-global pairs need the whole cohort resident for the second pass
+  if digital:
+    d_dev = host.to(dev, non_blocking=True)
+    arena = torch.empty((total, C + 1), dtype=torch.float64, device=dev)
+    at = 0
+    for r, n in enumerate(rows):
+      ops.decode_fmt16(d_dev[at:at + n], list(range(C + 1)), gains[r], bases[r], arena[at:at + n])
+      at += n
+  else:
+    arena = host.to(dev, non_blocking=True)
+  store = engine.prepare_windows(arena, plan, list(range(C)), C, params.min_RHC, use_global_min_max=True)
   return store, names
 
 

@@ -248,10 +248,14 @@ class HostIngest:
   (compute stream).  This is the end-to-end path a caller with records in host memory uses
   (the reference reads each record from disk into host numpy arrays, recordutil.py:137)."""
 
-  def __init__(self, plan, record_rows, nsig, device, chunk_records=64):
+  def __init__(self, plan, record_rows, nsig, device, chunk_records=64, digital_nsig=None):
+    """``nsig``: columns of the fp64 arena the window kernel reads.  ``digital_nsig``: the host cohort is WFDB
+    format-16 int16 frames with that many signals per frame; they are copied as int16 (4x fewer PCIe bytes than
+    fp64 physical samples) and converted on the device (scgrhc_decode_fmt16)."""
     self.plan, self.nsig, self.device = plan, nsig, torch.device(device)
     rows = np.asarray(record_rows, dtype=np.int64)
     base = np.concatenate([[0], np.cumsum(rows)])
+    self.record_base = base
     self.total_rows = int(base[-1])
     iv = plan.intervals
     self.chunks = []
@@ -266,15 +270,20 @@ class HostIngest:
       sub['row0'] -= lo
       sub['cand0'] -= cand_lo
       t = torch.from_numpy(sub.view(np.int64).reshape(-1, 3).copy()).to(self.device) if len(sub) else None
-      self.chunks.append((lo, hi, cand_lo, n, t))
+      self.chunks.append((lo, hi, cand_lo, n, t, r0, r1))
       max_rows = max(max_rows, hi - lo)
     self.bufs = [torch.empty((max_rows, nsig), dtype=torch.float64, device=self.device) for _ in range(2)]
+    self.digital_nsig = digital_nsig
+    self.dbufs = [torch.empty((max_rows, digital_nsig), dtype=torch.int16, device=self.device) for _ in range(2)] \
+        if digital_nsig else None
     self.copy_stream = torch.cuda.Stream(self.device)
-    self.h2d_bytes = self.total_rows * nsig * 8
+    self.h2d_bytes = self.total_rows * (digital_nsig * 2 if digital_nsig else nsig * 8)
 
   def run(self, host_arena, scg_cols, rhc_col, min_rhc, out_dtype=torch.float32, flat_threshold=FLAT_THRESHOLD,
-          buffers=None):
-    """``host_arena``: (total_rows, nsig) fp64 CPU tensor (pinned for an asynchronous copy)."""
+          buffers=None, decode=None):
+    """``host_arena``: (total_rows, nsig) fp64 CPU tensor (pinned for an asynchronous copy), or — with
+    ``digital_nsig`` — (total_rows, digital_nsig) int16 frames plus ``decode = (cols, gain, baseline)`` where
+    gain/baseline are one list per selected column (all records) or one such list per record."""
     plan, dev = self.plan, self.device
     n, W, Cn = plan.n_cand, plan.W, len(scg_cols)
     b = buffers if buffers is not None else {}
@@ -295,15 +304,27 @@ class HostIngest:
     done = [None, None]
     self.copy_stream.wait_stream(compute)
     bad = False
-    for k, (lo, hi, cand_lo, nc, iv) in enumerate(self.chunks):
+    digital = self.digital_nsig is not None
+    if digital and decode is None:
+      raise ValueError('digital cohort: decode=(cols, gain, baseline) is required')
+    for k, (lo, hi, cand_lo, nc, iv, r0, r1) in enumerate(self.chunks):
       dst = self.bufs[k & 1][:hi - lo]
+      stage = self.dbufs[k & 1][:hi - lo] if digital else dst
       with torch.cuda.stream(self.copy_stream):
         if done[k & 1] is not None:
           self.copy_stream.wait_event(done[k & 1])
-        dst.copy_(host_arena[lo:hi], non_blocking=True)
+        stage.copy_(host_arena[lo:hi], non_blocking=True)
         ready = torch.cuda.Event()
         ready.record(self.copy_stream)
       compute.wait_event(ready)
+      if digital:
+        cols, gain, baseline = decode
+        if isinstance(gain[0], (list, tuple, np.ndarray)):      # per-record calibration
+          for r in range(r0, r1):
+            a, b2 = int(self.record_base[r]) - lo, int(self.record_base[r + 1]) - lo
+            ops.decode_fmt16(stage[a:b2], list(cols), [float(v) for v in gain[r]], [float(v) for v in baseline[r]], dst[a:b2])
+        else:
+          ops.decode_fmt16(stage, list(cols), [float(v) for v in gain], [float(v) for v in baseline], dst)
       if nc:
         ops.process_windows(dst, iv, nc, W, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
                             [0.0] * 4, None, 0, scg[cand_lo:], rhc[cand_lo:], minmax[cand_lo:], keep[cand_lo:],

@@ -156,6 +156,20 @@ def rolling_range_lt(y: Tensor, m: int, threshold: float, flags: Tensor) -> None
   N.check(c, N.lib().scgrhc_rolling_range_lt(c, _ptr(y), y.numel(), m, threshold, _ptr(flags), _stream(dev)))
 
 
+@torch.library.custom_op('scgrhc::decode_fmt16', mutates_args=('out',), device_types='cuda')
+def decode_fmt16(d: Tensor, cols: Sequence[int], gain: Sequence[float], baseline: Sequence[float], out: Tensor) -> None:
+  """WFDB format-16 frames (T, nsig) int16 -> physical fp64 (T, len(cols)): (d - baseline) / gain, -32768 -> NaN
+  (the host-side dac of wfdb.rdrecord, recordutil.py:137, moved onto the device)."""
+  dev = _dev(d)
+  _contig(d, torch.int16, 'd'); _contig(out, torch.float64, 'out')
+  n = len(cols)
+  if d.dim() != 2 or out.numel() < d.shape[0] * n or len(gain) != n or len(baseline) != n:
+    raise ValueError('decode_fmt16: d must be (T, nsig), out (T, len(cols)); one gain and baseline per column')
+  c = ctx(dev)
+  N.check(c, N.lib().scgrhc_decode_fmt16(c, _ptr(d), d.shape[0], d.shape[1], (C.c_int32 * n)(*cols), n,
+                                         (C.c_double * n)(*gain), (C.c_double * n)(*baseline), _ptr(out), _stream(dev)))
+
+
 @torch.library.custom_op('scgrhc::waveform_stats', mutates_args=('stats',), device_types='cuda')
 def waveform_stats(y: Tensor, min_rhc: float, stats: Tensor) -> None:
   """Per row of y (n_wave, L): R^2 of the OLS line, min, max, below-floor, non-finite, sum

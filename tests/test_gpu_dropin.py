@@ -172,3 +172,46 @@ def test_save_dataloaders_end_to_end(tmp_path, monkeypatch):
       assert int(segment[4]) == key[1] + 750
       seen.add(key)
   assert seen == set(want)                                  # every kept window lands in exactly one split
+
+
+def test_device_decode_matches_host_dac_and_digital_ingest(tmp_path, monkeypatch):
+  """Format-16 frames decoded on the device == wfdb's host-side (d - baseline) / gain, bit for bit; the digital
+  ingest path (int16 over PCIe) gives the same windows as the physical one, also with dataset-global pairs."""
+  from scgrhc import ops
+  root = tmp_path / 'data'; root.mkdir()
+  monkeypatch.setattr(recordutil, 'PROCESSED_DATA_PATH', str(root))
+  monkeypatch.setattr(recordutil, 'wfdb', wfdbio)
+  sig = synth_ref.SIG_NAMES_5
+  meta = synth_ref.record_meta(80, events={'PA_1': 1.0, 'RV_1': 70})
+  for r in range(3):
+    p = synth_ref.gen_record(H.SEED, 80 + r, 40000 + 37 * r, kinds=synth_ref.kinds_for(sig))
+    if r == 1:
+      p[1234, 3] = np.nan                                  # stored as the invalid code -32768 -> NaN -> flat-free window raises
+    wfdbio.wrsamp('rec%d' % r, 500, ['g', 'g', 'g', 'mmHg', 'mV'], sig, p, write_dir=str(root))
+    (root / ('rec%d.json' % r)).write_text(json.dumps(meta))
+  rec = wfdbio.rdrecord(str(root / 'rec1'))
+  d = torch.from_numpy(rec.d_signal.copy()).cuda()
+  out = torch.empty((d.shape[0], 3), dtype=torch.float64, device='cuda')
+  sel = [4, 0, 3]
+  ops.decode_fmt16(d, sel, [rec.adc_gain[j] for j in sel], [float(rec.baseline[j]) for j in sel], out)
+  want = rec.p_signal[:, sel]
+  got = out.cpu().numpy()
+  assert np.isnan(got[1234, 2]) and np.array_equal(np.isnan(got), np.isnan(want))
+  assert got[~np.isnan(got)].tobytes() == want[~np.isnan(want)].tobytes()
+  c = H.effective_config('waveform_08')                     # lat + dv: a non-trivial column selection
+  params = types.SimpleNamespace(in_channels=c['in_channels'], chamber='PA', segment_size=1.5, min_RHC=-50, use_global_min_max=False)
+  with pytest.raises(ValueError):                           # the NaN reaches the regression, as in the reference
+    recordutil.prepare_cohort(params, ['rec0', 'rec1', 'rec2'])
+  for use_global in (False, True):
+    params.use_global_min_max = use_global
+    dig, _ = recordutil.prepare_cohort(params, ['rec0', 'rec2'], chunk_records=1)
+    # same cohort through the physical (fp64 p_signal) path: hide the digital frames from the reader
+    monkeypatch.setattr(recordutil, 'wfdb', types.SimpleNamespace(
+      rdrecord=lambda path: FakeRecord(wfdbio.rdrecord(path).sig_name, wfdbio.rdrecord(path).p_signal)))
+    phy, _ = recordutil.prepare_cohort(params, ['rec0', 'rec2'], chunk_records=1)
+    monkeypatch.setattr(recordutil, 'wfdb', wfdbio)
+    assert dig.n_kept == phy.n_kept > 0
+    assert torch.equal(dig.start_idx, phy.start_idx) and torch.equal(dig.rec_id, phy.rec_id)
+    assert torch.equal(dig.kept_minmax(), phy.kept_minmax())
+    a, b = dig.materialise(), phy.materialise()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
