@@ -257,3 +257,56 @@ def test_full_size_properties_1000_records():
   m = st.rec_id >= n_rec // 2
   assert torch.equal(sth.start_idx, st.start_idx[m]) and torch.equal(sth.rec_id, st.rec_id[m])
   assert torch.equal(sth.kept_minmax(), st.kept_minmax()[m])
+
+
+@pytest.mark.parametrize('segment_size,nsig', [(1.0, 4), (2.0, 4), (0.128, 5), (0.1, 4), (0.004, 4), (1.7, 12), (2.048, 3)])
+def test_other_window_lengths_and_wide_records(segment_size, nsig):
+  """The runtime-W kernel (every length 2..1024 the library accepts) and records with many signals."""
+  names = (synth_ref.SIG_NAMES_5 + ['s%d' % i for i in range(5, 12)])[:nsig] if nsig != 3 else ['patch_ACC_hf', 'RHC_pressure', 'patch_ACC_dv']
+  if nsig == 4:
+    names = synth_ref.DEFAULT_SIG_NAMES
+  kinds = synth_ref.kinds_for(names)
+  W = int(segment_size * 500)
+  T = 20011
+  chans = [n for n in names if n.startswith('patch_ACC')][::-1]
+  meta = synth_ref.record_meta(40, events={'PA_1': 0.302, 'RA_1': 25.4, 'PA_2': 31.001})
+  arena = torch.empty((2 * T, nsig), dtype=torch.float64, device=DEV)
+  ops.synth_records(arena, 5, 0, 2, T, list(kinds), 16, 750)
+  cols, rcol = scgrhc.resolve_columns(names, chans)
+  plan = scgrhc.plan_uniform(meta, 'PA', T, W, 2)
+  st = scgrhc.prepare_windows(arena, plan, cols, rcol, -50.0, out_dtype=torch.float64)
+  scg, rhc = st.materialise()
+  scg, rhc, rec_id = scg.cpu().numpy(), rhc.cpu().numpy(), st.rec_id.cpu().numpy()
+  for r in range(2):
+    p = synth_ref.gen_record(5, r, T, kinds=kinds)
+    rw = orc.scan_record(p, names, meta, chans, 'PA', segment_size, -50.0)
+    # exactly-constant windows shorter than 51 samples are excluded: the reference's R^2 on them is rounding
+    # noise of np.average (1.0 or 0.0, DESIGN.md §2); longer ones are flat-line rejects on both sides
+    const = (rw.minmax[:, 2] == rw.minmax[:, 3]) & (W < 51)
+    m = rec_id == r
+    mine = st.start_idx.cpu().numpy()[m]
+    cand_of = {int(a): i for i, a in enumerate(rw.abs_start)}
+    abs_mine = st.kept_idx.cpu().numpy()[m] - (plan.n_cand // 2) * r
+    ok_mine = ~const[abs_mine]
+    k = np.nonzero(rw.keep & ~const)[0]
+    assert abs_mine[ok_mine].tolist() == k.tolist(), (segment_size, r)
+    assert mine[ok_mine].tolist() == rw.rel_start[k].tolist()
+    rw.keep = rw.keep & ~const
+    s_o, r_o, mm_o = orc.normalise_record(p, names, chans, rw, out_dtype=np.float64)
+    assert scg[m][ok_mine].tobytes() == s_o.tobytes() and rhc[m][ok_mine].tobytes() == r_o.tobytes()
+  assert plan.n_cand > 0
+
+
+def test_unsupported_shapes_fail_loudly():
+  arena = torch.zeros((5000, 4), dtype=torch.float64, device=DEV)
+  meta = synth_ref.record_meta(10, events={'PA_1': 0})
+  plan = scgrhc.plan_uniform(meta, 'PA', 5000, 1025, 1)
+  with pytest.raises(N.ScgrhcError, match='window of 1025 samples'):
+    scgrhc.prepare_windows(arena, plan, [0, 1, 2], 3, -50.0)
+  plan = scgrhc.plan_uniform(meta, 'PA', 5000, 750, 1)
+  with pytest.raises(N.ScgrhcError):
+    scgrhc.prepare_windows(arena, plan, [0, 1, 2, 3, 0], 3, -50.0)
+  with pytest.raises(N.ScgrhcError):
+    scgrhc.prepare_windows(arena, plan, [0, 1, 7], 3, -50.0)
+  with pytest.raises(RuntimeError):
+    scgrhc.prepare_windows(arena.cpu(), plan, [0, 1, 2], 3, -50.0)
