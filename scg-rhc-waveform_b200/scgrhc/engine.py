@@ -172,7 +172,7 @@ def prepare_windows(arena, plan, scg_cols, rhc_col, min_rhc, use_global_min_max=
   iv = plan.device_intervals(dev)
   f64 = out_dtype == torch.float64
   base_flags = (N.OUT_F64 if f64 else 0) | (N.KEEP_ALL if keep_all else 0)
-  b = buffers or {}
+  b = buffers if buffers is not None else {}
 
   def buf(name, shape, dtype):
     t = b.get(name)

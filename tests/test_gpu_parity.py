@@ -93,19 +93,21 @@ def test_record_small_golden_bit_exact(cfg):
 
 
 def test_records_full_golden_all_configs():
+  """All 36 runnable configs as ONE sweep job over a device-resident cohort (BASELINE configs[4])."""
+  import types
+  from scgrhc import sweep
   full = H.load_json('records_full.json')
   table = H.configs()
   recs = {('rec%d' % r): H.full_record(r) for r in (0, 1)}
   sig = recs['rec0'][0]
   metas = [recs['rec0'][2], recs['rec1'][2]]
   arena = torch.from_numpy(np.concatenate([recs['rec0'][1], recs['rec1'][1]])).to(DEV)
-  for cfg, entry in full['configs'].items():
-    c = H.effective_config(cfg, table)
-    W = int(c['segment_size'] * 500)
-    cols, rcol = scgrhc.resolve_columns(sig, c['in_channels'])
-    plan = scgrhc.plan_cohort(metas, c['chamber'], [300000, 300000], W)
-    st = scgrhc.prepare_windows(arena, plan, cols, rcol, c['min_RHC'], use_global_min_max=c['use_global_min_max'])
-    if c['use_global_min_max']:
+  configs = {cfg: types.SimpleNamespace(**H.effective_config(cfg, table)) for cfg in full['configs']}
+  assert len(configs) == 36
+  seen = 0
+  for cfg, st in sweep.iter_sweep(arena, sig, metas, [300000, 300000], configs, buffers={}):
+    entry, c = full['configs'][cfg], configs[cfg]
+    if c.use_global_min_max:
       assert [float(v).hex() for v in st.global_minmax.cpu().tolist()] == entry['global_minmax_hex']
     scg, rhc = st.materialise()
     scg, rhc = scg.cpu().numpy(), rhc.cpu().numpy()
@@ -120,6 +122,8 @@ def test_records_full_golden_all_configs():
       assert H.sha(mm[m]) == want['minmax_sha'], (cfg, name)
       assert H.sha(scg[m]) == want['scg_sha'], (cfg, name)
       assert H.sha(rhc[m]) == want['rhc_sha'], (cfg, name)
+    seen += 1
+  assert seen == 36
 
 
 @pytest.mark.parametrize('nsig,out_dtype', [(4, torch.float32), (4, torch.float64), (5, torch.float32), (7, torch.float64)])
