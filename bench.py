@@ -320,10 +320,33 @@ def run_b200(args):
               'algorithmic_bytes_per_launch': alg, 'peak_source': peak_src,
               'bytes_per_kept_window': W * C * 8 + W * 8 + W * (C + 1) * out_bytes + 53}
 
+  # ---- BASELINE configs[2]: batches of 256 kept windows gathered on the device for the trainer ----
+  kept_pos = kept_idx[:n_kept]
+  perm = kept_pos[torch.randperm(n_kept, device=dev)[:256 * 64]].contiguous()
+  b_scg = torch.empty((256, C, W), dtype=out_dtype, device=dev)
+  b_rhc = torch.empty((256, 1, W), dtype=out_dtype, device=dev)
+  nb = perm.numel() // 256
+  def collate(i):
+    ops.gather_windows(scg, perm[i * 256:(i + 1) * 256], b_scg)
+    ops.gather_windows(rhc, perm[i * 256:(i + 1) * 256], b_rhc)
+  for i in range(min(4, nb)):
+    collate(i)
+  ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ca.record()
+  for i in range(nb):
+    collate(i)
+  cb.record()
+  torch.cuda.synchronize()
+  ms_b = ca.elapsed_time(cb) / max(nb, 1)
+  batch256 = {'us_per_batch': ms_b * 1e3, 'windows_per_s': 256 / (ms_b * 1e-3) if nb else None,
+              'gbs': 2 * 256 * (C + 1) * W * out_bytes / (ms_b * 1e-3) / 1e9 if nb else None,
+              'what': 'shuffled batch of 256 kept windows -> (256,%d,750)+(256,1,750) device tensors, 2 gather launches' % C}
+
   # ---- end to end through the host API: pinned host records -> H2D -> hot path -> D2H result ----
   e2e = None
   windows = [(t_host0, t_host1)]
-  if not args.no_e2e:
+  def run_e2e():
+    nonlocal e2e
     host = torch.empty(arena.shape, dtype=torch.float64, pin_memory=True)
     host.copy_(arena)
     torch.cuda.synchronize()
@@ -395,6 +418,13 @@ def run_b200(args):
                               '(d - baseline) / gain runs on the device (scgrhc_decode_fmt16); cohort quantised with gains %s' % gains}
       del hostd
 
+
+  if not args.no_e2e:
+    try:
+      run_e2e()
+    except (RuntimeError, MemoryError) as exc:      # e.g. pinned host memory exhausted with 8 ranks on one host
+      e2e = dict(e2e or {}, error=str(exc)[:300])
+
   if rank == 0:
     sampler.stop()
   clocks = sampler.summary(windows[:1]) if rank == 0 else None          # the device-resident timed region
@@ -428,7 +458,7 @@ def run_b200(args):
             'roofline': roofline, 'cpu_baseline': cpu, 'cpu_baseline_fast': cpu_fast_d, 'e2e': e2e,
             'gpu_launches': args.steps * (4 + (2 if args.global_minmax else 0)),
             'launches_per_step': 'window_kernel + count_kept + scan_blocks + scatter_kept',
-            'clocks': clocks, 'clocks_e2e': clocks_e2e}
+            'batch256': batch256, 'clocks': clocks, 'clocks_e2e': clocks_e2e}
     print(json.dumps(line), flush=True)
   if world > 1:
     dist.destroy_process_group()
