@@ -102,6 +102,25 @@ class ClockSampler:
             'samples': len(sel), 'power_w_max': max(pw) if pw else None}
 
 
+def bind_to_gpu_numa(local):
+  """Pin this rank to the CPUs the driver reports as local to its GPU, so that the pinned host staging buffers are
+  first-touched on the GPU's NUMA node (matters for the end-to-end leg when 8 ranks share one host)."""
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(local)
+    ncpu = os.cpu_count() or 1
+    words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+    want = {i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1}
+    cpus = sorted(want & os.sched_getaffinity(0))
+    if cpus:
+      os.sched_setaffinity(0, cpus)
+      return len(cpus)
+  except Exception:
+    pass
+  return None
+
+
 def measured_peak():
   try:
     with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -229,6 +248,7 @@ def run_b200(args):
     raise RuntimeError('bench.py needs a CUDA device: the hot path has no CPU fallback')
   torch.cuda.set_device(local)
   dev = torch.device('cuda', local)
+  numa_cpus = bind_to_gpu_numa(local) if world > 1 else None
   if world > 1:
     dist.init_process_group('nccl', device_id=dev)
   if args.ctas_per_sm or args.stages:
@@ -458,7 +478,7 @@ def run_b200(args):
             'roofline': roofline, 'cpu_baseline': cpu, 'cpu_baseline_fast': cpu_fast_d, 'e2e': e2e,
             'gpu_launches': args.steps * (4 + (2 if args.global_minmax else 0)),
             'launches_per_step': 'window_kernel + count_kept + scan_blocks + scatter_kept',
-            'batch256': batch256, 'clocks': clocks, 'clocks_e2e': clocks_e2e}
+            'batch256': batch256, 'numa_bound_cpus': numa_cpus, 'clocks': clocks, 'clocks_e2e': clocks_e2e}
     print(json.dumps(line), flush=True)
   if world > 1:
     dist.destroy_process_group()

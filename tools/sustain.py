@@ -6,7 +6,9 @@ import torch, bench, scgrhc
 from scgrhc import ops
 
 n_rec, iters = int(sys.argv[1]), int(sys.argv[2])
+ctas, stages = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (0, 0)
 dev = torch.device('cuda', 0)
+ops.set_tuning(0, ctas, stages)
 arena = torch.empty((n_rec * bench.T_ROWS, 4), dtype=torch.float64, device=dev)
 ops.synth_records(arena, bench.SEED, 0, n_rec, bench.T_ROWS, bench.KINDS, 16, bench.W)
 plan = scgrhc.plan_uniform(bench.meta(), 'PA', bench.T_ROWS, bench.W, n_rec)
@@ -33,7 +35,5 @@ torch.cuda.synchronize()
 t1 = time.time()
 p.terminate()
 ms = [a.elapsed_time(b) for a, b in evs]
-for i in range(0, iters, max(1, iters // 20)):
-  print('iter %4d: %.3f ms' % (i, ms[i]))
-print('under load:', [s for t, s in samples if t0 <= t <= t1][::5])
-print('idle before:', [s for t, s in samples if t < t0][-3:])
+print('ctas %d stages %d: first10 %.3f ms  last50%% mean %.3f ms' % (ctas, stages, sum(ms[:10]) / 10, sum(ms[iters // 2:]) / (iters - iters // 2)))
+print('under load (last):', [s for t, s in samples if t0 <= t <= t1][-2:])
