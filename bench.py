@@ -279,11 +279,11 @@ def run_b200(args):
   gmm = torch.empty(4, dtype=torch.float64, device=dev)
 
   def kernel_step():
-    ops.process_windows(arena, iv, n, W, cols, rcol, MIN_RHC, 1e-3, flags, [0.0] * 4, None, 0,
+    ops.process_windows(arena, iv, n, W, 0, cols, rcol, MIN_RHC, 1e-3, flags, [0.0] * 4, None, 0,
                         scg, rhc, minmax, keep, reason, cand_win, cand_rec)
 
   def tail_step():
-    ops.compact_kept(keep, cand_win, cand_rec, n, W, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
+    ops.compact_kept(keep, cand_win, cand_rec, n, W, 0, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
     if args.global_minmax:   # BASELINE configs[3]: dataset-level min/max statistics + all-reduce
       ops.global_minmax(minmax, keep, n, gmm)
       scgrhc.allreduce_minmax(gmm)

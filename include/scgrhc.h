@@ -62,7 +62,7 @@ typedef enum {
 typedef struct {
   int64_t row0;   /* first arena row of the (clamped) interval: record base row + slice start */
   int64_t cand0;  /* index of its first candidate window = exclusive prefix sum of n_win */
-  int32_t n_win;  /* L // W, recordutil.py:141 */
+  int32_t n_win;  /* L // W, recordutil.py:141 (stride extension: (L - W) // stride + 1) */
   int32_t rec_id; /* caller's record number, reported back per kept window */
 } scgrhc_interval;
 
@@ -79,7 +79,8 @@ typedef struct {
   uint32_t flags;
   const scgrhc_interval* intervals; /* device, sorted by cand0 */
   int32_t n_intervals;
-  int32_t reserved0;
+  int32_t stride;               /* rows between consecutive windows of an interval; 0 = W (the reference: non-overlapping,
+                                   recordutil.py:143).  Extension: overlapping windows, start_idx = i*stride */
   int64_t n_cand;               /* total candidate windows = sum n_win */
   double min_rhc;               /* params.min_RHC, waveform_noise.py:39 */
   double flat_threshold;        /* 1e-3, waveform_noise.py:6 */
@@ -104,6 +105,8 @@ typedef struct {
   int64_t* stop_idx;  /* device (n_cand): start_idx + W (recordutil.py:144) */
   int32_t* rec_id;    /* device (n_cand) */
   int64_t* n_kept;    /* device (1) */
+  int32_t stride;     /* 0 = W; start_idx = i*stride */
+  int32_t reserved;
 } scgrhc_compact;
 
 typedef struct scgrhc_ctx scgrhc_ctx;
@@ -125,7 +128,7 @@ int scgrhc_ctx_sm_count(const scgrhc_ctx* ctx);
  * Writes up to out_cap intervals (also the empty ones are skipped) and the raw (a,b) sample
  * bounds of every matching event to bounds[2*k] (may be NULL).  cand_base seeds cand0. */
 int scgrhc_plan_record(const double* event_time, const uint8_t* event_match, int n_events,
-                       int64_t T, int32_t W, int64_t rec_base_row, int32_t rec_id, int64_t cand_base,
+                       int64_t T, int32_t W, int32_t stride /* 0 = W */, int64_t rec_base_row, int32_t rec_id, int64_t cand_base,
                        scgrhc_interval* out, int out_cap, int* n_out, int64_t* n_cand,
                        int64_t* bounds, int bounds_cap, int* n_bounds);
 
@@ -149,6 +152,15 @@ int scgrhc_check_errors(scgrhc_ctx* ctx, void* stream, int64_t* first_bad_cand);
 /* ---- batch collate (default_collate of recordutil.py:198): out[b] = store[slot[b]] ---------- */
 int scgrhc_gather_windows(scgrhc_ctx* ctx, const void* store, const int64_t* slots, int64_t n,
                           int64_t window_bytes, void* out, void* stream);
+
+/* ---- extension (named by the project brief, ABSENT from the reference; default off): train-time noise injection
+ *      fused into the batch gather of fp32 windows: out[b][e] = store[slots[b]][e] + sigma * N(0,1).  Normals come from
+ *      the counter-based Philox4x32-10 generator (key = seed, counter = (quad index, offset)) through Box-Muller;
+ *      `offset` selects an independent stream per batch.  scgrhc_philox_words exposes the raw 4x32-bit blocks
+ *      (nquads * 4 words, device, 16-byte aligned) for seed-exact checks against a host implementation. */
+int scgrhc_gather_windows_noise(scgrhc_ctx* ctx, const float* store, const int64_t* slots, int64_t n,
+                                int64_t window_elems, float* out, float sigma, uint64_t seed, uint64_t offset, void* stream);
+int scgrhc_philox_words(scgrhc_ctx* ctx, uint64_t seed, uint64_t offset, int64_t nquads, uint32_t* out, void* stream);
 
 /* ---- standalone predicate helpers for API parity of waveform_noise.get_flat_lines with
  *      non-default arguments: flags[p] = (rolling range over m samples ending at p) < threshold */

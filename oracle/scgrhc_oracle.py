@@ -53,20 +53,22 @@ def chamber_intervals(meta, chamber):
 # ----------------------------------------------------------------------------------------
 # a5/a6  get_channels + window enumeration  (recordutil.py:113-119, 136-146)
 # ----------------------------------------------------------------------------------------
-def candidate_windows(intervals, T, W):
+def candidate_windows(intervals, T, W, stride=None):
   """Candidate windows of one record, in the reference's order (interval order, then i).
 
   ``p_signal[a:b]`` (recordutil.py:118) follows Python slice semantics, so the bounds are
   clamped (and negative values wrap) exactly as ``slice(a, b).indices(T)`` does; the number
   of windows is ``L // W`` (:141) and ``start_idx = i*W`` is relative to the interval (:143).
+  ``stride`` (extension, not in the reference): rows between window starts; None = W.
   Returns int64 arrays (abs_start, rel_start, interval_index)."""
   abs_start, rel_start, which = [], [], []
   for k, (a, b) in enumerate(intervals):
     lo, hi, _ = slice(a, b).indices(T)
-    n = max(0, hi - lo) // W
+    L, st = max(0, hi - lo), (W if stride is None else stride)
+    n = L // W if st == W else ((L - W) // st + 1 if L >= W else 0)
     for i in range(n):
-      abs_start.append(lo + i * W)
-      rel_start.append(i * W)
+      abs_start.append(lo + i * st)
+      rel_start.append(i * st)
       which.append(k)
   return (np.asarray(abs_start, dtype=np.int64), np.asarray(rel_start, dtype=np.int64),
           np.asarray(which, dtype=np.int32))
@@ -189,7 +191,7 @@ class RecordWindows:
                'nonfinite', 'minmax', 'W', 'C')
 
 
-def scan_record(p_signal, sig_name, meta, in_channels, chamber, segment_size, min_rhc):
+def scan_record(p_signal, sig_name, meta, in_channels, chamber, segment_size, min_rhc, stride=None):
   """get_segments for one record (recordutil.py:133-149) without materialising windows.
   ``list.index`` raises ValueError for a missing channel (:117), as here."""
   W = int(segment_size * SAMPLE_FREQ)
@@ -199,7 +201,7 @@ def scan_record(p_signal, sig_name, meta, in_channels, chamber, segment_size, mi
   intervals = chamber_intervals(meta, chamber)
   out = RecordWindows()
   out.W, out.C = W, len(cols)
-  out.abs_start, out.rel_start, out.interval = candidate_windows(intervals, T, W)
+  out.abs_start, out.rel_start, out.interval = candidate_windows(intervals, T, W, stride)
   n = len(out.abs_start)
   idx = out.abs_start[:, None] + np.arange(W)[None, :]
   rhc = p_signal[:, rcol][idx] if n else np.empty((0, W))

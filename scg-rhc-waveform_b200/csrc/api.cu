@@ -111,10 +111,11 @@ static void slice_indices(int64_t a, int64_t b, int64_t T, int64_t* lo, int64_t*
 }
 
 extern "C" int scgrhc_plan_record(const double* event_time, const uint8_t* event_match, int n_events, int64_t T,
-                                  int32_t W, int64_t rec_base_row, int32_t rec_id, int64_t cand_base,
+                                  int32_t W, int32_t stride, int64_t rec_base_row, int32_t rec_id, int64_t cand_base,
                                   scgrhc_interval* out, int out_cap, int* n_out, int64_t* n_cand, int64_t* bounds,
                                   int bounds_cap, int* n_bounds) {
-  if (!n_out || !n_cand || W <= 0 || T < 0 || n_events < 0 || (n_events && (!event_time || !event_match)))
+  if (stride == 0) stride = W;
+  if (!n_out || !n_cand || W <= 0 || stride < 0 || T < 0 || n_events < 0 || (n_events && (!event_time || !event_match)))
     return SCGRHC_ERR_BAD_ARG;
   std::vector<int> order(n_events);
   for (int i = 0; i < n_events; ++i) order[i] = i;
@@ -131,7 +132,7 @@ extern "C" int scgrhc_plan_record(const double* event_time, const uint8_t* event
     int64_t lo, hi;
     slice_indices(a, b, T, &lo, &hi);
     const int64_t L = hi > lo ? hi - lo : 0;
-    const int64_t nw = L / W;
+    const int64_t nw = stride == W ? L / W : (L >= W ? (L - W) / stride + 1 : 0);
     if (nw <= 0) continue;
     if (nw > INT32_MAX) return SCGRHC_ERR_BAD_ARG;
     if (out && k < out_cap) {
@@ -201,7 +202,7 @@ extern "C" int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, co
   if (J.rhc_col < 0 || J.rhc_col >= J.nsig) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "RHC column %d outside 0..%d", J.rhc_col, J.nsig - 1);
   for (int c = 0; c < J.C; ++c)
     if (J.scg_cols[c] < 0 || J.scg_cols[c] >= J.nsig) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "SCG column %d outside 0..%d", J.scg_cols[c], J.nsig - 1);
-  if (J.n_cand < 0 || J.n_intervals < 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "negative counts");
+  if (J.n_cand < 0 || J.n_intervals < 0 || J.stride < 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "negative counts");
   if (J.arena_capacity_bytes < J.arena_rows * (int64_t)J.nsig * 8) return fail(ctx, SCGRHC_ERR_BAD_ARG, "arena_capacity_bytes smaller than the arena");
   if ((reinterpret_cast<uintptr_t>(J.arena) & 15) != 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "arena must be 16-byte aligned");
   const long long items = use_list ? J.n_items : J.n_cand;
@@ -275,7 +276,8 @@ extern "C" int scgrhc_compact_kept(scgrhc_ctx* ctx, const uint8_t* keep, const i
   count_kept_kernel<<<(unsigned)nblocks, CB, 0, st>>>(keep, n_cand, ctx->block_counts);
   scan_blocks_kernel<<<1, 1024, 0, st>>>(ctx->block_counts, (int)nblocks, ctx->block_offsets,
                                          reinterpret_cast<long long*>(out->n_kept));
-  scatter_kept_kernel<<<(unsigned)nblocks, CB, 0, st>>>(keep, cand_win, cand_rec, n_cand, W, ctx->block_offsets, *out);
+  scatter_kept_kernel<<<(unsigned)nblocks, CB, 0, st>>>(keep, cand_win, cand_rec, n_cand, W, out->stride > 0 ? out->stride : W,
+                                                        ctx->block_offsets, *out);
   CUDA_TRY(ctx, cudaGetLastError());
   return SCGRHC_OK;
 }
@@ -305,6 +307,33 @@ extern "C" int scgrhc_gather_windows(scgrhc_ctx* ctx, const void* store, const i
   gather_windows_kernel<<<grid, 256, 0, st>>>(static_cast<const unsigned char*>(store),
                                               reinterpret_cast<const long long*>(slots), n, window_bytes,
                                               static_cast<unsigned char*>(out));
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_gather_windows_noise(scgrhc_ctx* ctx, const float* store, const int64_t* slots, int64_t n,
+                                           int64_t window_elems, float* out, float sigma, uint64_t seed, uint64_t offset,
+                                           void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (n < 0 || window_elems <= 0 || (n && (!store || !slots || !out)))
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "gather_windows_noise: bad arguments");
+  if (n == 0) return SCGRHC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const long long quads = (n * window_elems + 3) / 4;
+  const unsigned grid = (unsigned)std::min<long long>((quads + 255) / 256, (long long)ctx->sm_count * 16);
+  gather_noise_kernel<<<grid, 256, 0, st>>>(store, reinterpret_cast<const long long*>(slots), n, window_elems, out, sigma, seed, offset);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_philox_words(scgrhc_ctx* ctx, uint64_t seed, uint64_t offset, int64_t nquads, uint32_t* out, void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (nquads < 0 || (nquads && !out)) return fail(ctx, SCGRHC_ERR_BAD_ARG, "philox_words: bad arguments");
+  if (nquads == 0) return SCGRHC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  philox_words_kernel<<<(unsigned)((nquads + 255) / 256), 256, 0, st>>>(seed, offset, nquads, reinterpret_cast<uint4*>(out));
   CUDA_TRY(ctx, cudaGetLastError());
   return SCGRHC_OK;
 }

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(const int* __restrict
 
 __global__ void __launch_bounds__(CB) scatter_kept_kernel(const uint8_t* __restrict__ keep,
                                                           const int32_t* __restrict__ cand_win,
-                                                          const int32_t* __restrict__ cand_rec, long long n, int W,
+                                                          const int32_t* __restrict__ cand_rec, long long n, int W, int stride,
                                                           const long long* __restrict__ block_offsets,
                                                           scgrhc_compact out) {
   // thread t owns CITEMS consecutive flags so that ranks follow candidate order
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(CB) scatter_kept_kernel(const uint8_t* __restr
       const long long j = base + i;
       out.kept_idx[r] = j;
       if (out.start_idx) {
-        const long long st = (long long)cand_win[j] * W;
+        const long long st = (long long)cand_win[j] * stride;
         out.start_idx[r] = st;
         out.stop_idx[r] = st + W;
       }
@@ -188,6 +188,57 @@ __global__ void __launch_bounds__(256) decode_fmt16_kernel(const __grid_constant
     const double v = __ddiv_rn(__dsub_rn((double)d, P.baseline[j]), P.gain[j]);
     P.out[e] = d == -32768 ? __longlong_as_double(0x7ff8000000000000LL) : v;
   }
+}
+
+// ---- extension (north star, absent from the reference): train-time noise injection fused into the batch gather.
+// Counter-based Philox4x32-10 (Salmon et al., Random123; the cuRAND-style 4x32 variant, NOT numpy's 4x64):
+// key = seed, counter = (block index of the element quad, stream offset).  Element j of the batch takes word j&3
+// of block j>>2; words (0,1) and (2,3) feed one Box-Muller pair each.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long offset, unsigned long long q) {
+  const uint4 u = philox4x32_10(make_uint4((unsigned)q, (unsigned)(q >> 32), (unsigned)offset, (unsigned)(offset >> 32)),
+                                make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = ((float)u.x + 0.5f) * k, u1 = ((float)u.y + 0.5f) * k, u2 = ((float)u.z + 0.5f) * k, u3 = ((float)u.w + 0.5f) * k;
+  const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+  float s0, c0, s1, c1;
+  sincosf(6.2831853071795865f * u1, &s0, &c0);
+  sincosf(6.2831853071795865f * u3, &s1, &c1);
+  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+__global__ void __launch_bounds__(256) gather_noise_kernel(const float* __restrict__ store, const long long* __restrict__ slots,
+                                                           long long n, long long E, float* __restrict__ out, float sigma,
+                                                           unsigned long long seed, unsigned long long offset) {
+  // E (elements per window) is a multiple of 2, so a quad never straddles more than two windows; handle per element
+  const long long quads = (n * E + 3) >> 2;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
+    const float4 z = philox_normal4(seed, offset, (unsigned long long)q);
+    const float zs[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const long long j = 4 * q + r;
+      if (j < n * E) {
+        const long long b = j / E, e = j - b * E;
+        out[j] = __fmaf_rn(sigma, zs[r], __ldcs(store + slots[b] * E + e));
+      }
+    }
+  }
+}
+__global__ void philox_words_kernel(unsigned long long seed, unsigned long long offset, long long nquads, uint4* out) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nquads)
+    out[q] = philox4x32_10(make_uint4((unsigned)q, (unsigned)(q >> 32), (unsigned)offset, (unsigned)(offset >> 32)),
+                           make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
 }
 
 // ---- standalone rolling range (API parity of get_flat_lines with non-default arguments) ------------

@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
   const int W = WCT ? WCT : J.W;
   const int nsig = NSIG4 ? 4 : J.nsig;
   const int nstage = P.stages;
+  const int wstride = J.stride > 0 ? J.stride : W;
   const bool use_list = (J.flags & SCGRHC_USE_KEPT_LIST) != 0;
   const bool pred_only = (J.flags & SCGRHC_PREDICATES_ONLY) != 0;
   const bool norm_global = (J.flags & SCGRHC_NORM_GLOBAL) != 0;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
     const long long cand = use_list ? J.kept_list[item] : item;
     while (cand >= p_cand0 + p_nwin) load_iv(++p_iv);
     const int i = (int)(cand - p_cand0);
-    const long long elem0 = (p_row0 + (long long)i * W) * nsig;
+    const long long elem0 = (p_row0 + (long long)i * wstride) * nsig;
     const int lead = (int)(elem0 & 1);
     const long long n_even = ((long long)W * nsig + lead + 1) & ~1LL;
     StageMeta m;

@@ -5,7 +5,9 @@ Same class, same attribute names, same ``Params(path)`` call.  Differences, all 
     SURVEY.md §0) load with documented defaults (``LEGACY_DEFAULTS``); ``Params(path, strict=True)``
     restores the reference's hard ``KeyError``;
   * optional keys read with ``.data.get`` only (absent from all 37 shipped params.json, so shipped
-    behaviour is unchanged): ``split_seed`` (reproducible train/valid/test split).
+    behaviour is unchanged): ``split_seed`` (reproducible train/valid/test split), ``segment_stride``
+    (seconds between window starts; default = ``segment_size``, i.e. the reference's non-overlapping windows), ``noise_std`` / ``noise_seed`` (train-time
+    noise injection on SCG batches).
 """
 import json
 import os
@@ -50,6 +52,9 @@ class Params:
     self.use_global_min_max = g('use_global_min_max')
     # additive, optional
     self.split_seed = self.data.get('split_seed')
+    self.segment_stride = self.data.get('segment_stride')
+    self.noise_std = self.data.get('noise_std')      # train-time Gaussian noise on SCG batches (extension, default off)
+    self.noise_seed = self.data.get('noise_seed')
 
   def _get(self, key):
     if key in self.data or self.strict or key not in LEGACY_DEFAULTS:

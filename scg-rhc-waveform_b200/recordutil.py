@@ -154,14 +154,17 @@ class SCGDataset(Dataset):
     self._segments = None
     return self
 
-  def collate(self, idx):
+  def collate(self, idx, noise=None):
     """What default_collate makes of items ``idx`` (recordutil.py:198): [scg (B,C,L), rhc (B,1,L), names,
     start (B,), stop (B,), [scg_min (B,), scg_max (B,)], [rhc_min (B,), rhc_max (B,)]]."""
     if self.scg.is_cuda:
       ii = idx.to(self.scg.device, torch.int64).contiguous()
       scg = torch.empty((ii.numel(),) + tuple(self.scg.shape[1:]), dtype=self.scg.dtype, device=self.scg.device)
       rhc = torch.empty((ii.numel(),) + tuple(self.rhc.shape[1:]), dtype=self.rhc.dtype, device=self.rhc.device)
-      ops.gather_windows(self.scg, ii, scg)
+      if noise is not None and noise[0] > 0 and self.scg.dtype == torch.float32:
+        ops.gather_windows_noise(self.scg, ii, scg, float(noise[0]), int(noise[1]), int(noise[2]))   # extension: SCG inputs only
+      else:
+        ops.gather_windows(self.scg, ii, scg)
       ops.gather_windows(self.rhc, ii, rhc)
     else:
       scg, rhc = self.scg[idx], self.rhc[idx]
@@ -209,8 +212,11 @@ class WindowLoader:
   ``.batch_size``) with device-side batch assembly: a shuffled index permutation + one gather kernel per
   batch instead of per-item collation (recordutil.py:198-200: shuffle=True, drop_last=False)."""
 
-  def __init__(self, dataset, batch_size=1, shuffle=False, generator=None):
+  def __init__(self, dataset, batch_size=1, shuffle=False, generator=None, noise_std=0.0, noise_seed=0):
     self.dataset, self.batch_size, self.shuffle, self.generator = dataset, int(batch_size), shuffle, generator
+    # extension (absent from the reference, default off): Gaussian noise on the SCG inputs of every batch, drawn from a
+    # counter-based Philox stream (seed, batch counter) inside the gather kernel
+    self.noise_std, self.noise_seed, self._batches_served = float(noise_std), int(noise_seed), 0
 
   def __len__(self):
     return (len(self.dataset) + self.batch_size - 1) // self.batch_size
@@ -219,7 +225,9 @@ class WindowLoader:
     n = len(self.dataset)
     order = torch.randperm(n, generator=self.generator) if self.shuffle else torch.arange(n)
     for b in range(0, n, self.batch_size):
-      yield self.dataset.collate(order[b:b + self.batch_size])
+      noise = (self.noise_std, self.noise_seed, self._batches_served) if self.noise_std > 0 else None
+      self._batches_served += 1
+      yield self.dataset.collate(order[b:b + self.batch_size], noise)
 
 
 def _normalise_block(block, n, minmax_scg, minmax_rhc, out_dtype, L=None):
@@ -243,7 +251,7 @@ def _normalise_block(block, n, minmax_scg, minmax_rhc, out_dtype, L=None):
   scg = torch.empty((n, Cn, L), dtype=out_dtype, device=dev)
   rhc = torch.empty((n, 1, L), dtype=out_dtype, device=dev)
   flags = N.USE_KEPT_LIST | (N.OUT_F64 if out_dtype == torch.float64 else 0)
-  ops.process_windows(arena, plan.device_intervals(dev), n, L, list(range(Cn)), Cn, float('-inf'), 1e-3, flags,
+  ops.process_windows(arena, plan.device_intervals(dev), n, L, 0, list(range(Cn)), Cn, float('-inf'), 1e-3, flags,
                       [0.0] * 4, torch.arange(n, device=dev), n, scg, rhc, mm, None, None, None, None)
   return scg, rhc, mm.cpu().numpy()
 
@@ -385,7 +393,8 @@ def prepare_cohort(params, record_names=None, chunk_records=32):
     blocks.append((record, sel))
     metas.append(_read_meta(name))
     rows.append(record.d_signal.shape[0] if digital else record.p_signal.shape[0])
-  plan = engine.plan_cohort(metas, params.chamber, rows, W, names)
+  stride_s = getattr(params, 'segment_stride', None)
+  plan = engine.plan_cohort(metas, params.chamber, rows, W, names, stride=int(stride_s * SAMPLE_FREQ) if stride_s else 0)
   dev = _device()
   total = int(sum(rows))
   host = torch.empty((total, C + 1), dtype=torch.int16 if digital else torch.float64, pin_memory=True)
@@ -445,7 +454,8 @@ def save_dataloaders(params):
   valid_set = make(valid_idx, 'cpu')                     # waveform_test calls .numpy() on items
   test_set = make(test_idx, 'cpu')
 
-  train_loader = WindowLoader(train_set, batch_size=params.batch_size, shuffle=True)
+  train_loader = WindowLoader(train_set, batch_size=params.batch_size, shuffle=True,
+                              noise_std=getattr(params, 'noise_std', None) or 0.0, noise_seed=getattr(params, 'noise_seed', None) or 0)
   valid_loader = WindowLoader(valid_set, batch_size=1, shuffle=True)
   test_loader = WindowLoader(test_set, batch_size=1, shuffle=True)
 

@@ -23,7 +23,7 @@ class Job(C.Structure):
   _fields_ = [('arena', C.c_void_p), ('arena_rows', C.c_int64), ('arena_capacity_bytes', C.c_int64),
               ('nsig', C.c_int32), ('W', C.c_int32), ('C', C.c_int32), ('scg_cols', C.c_int32 * MAX_C),
               ('rhc_col', C.c_int32), ('flags', C.c_uint32), ('intervals', C.c_void_p),
-              ('n_intervals', C.c_int32), ('reserved0', C.c_int32), ('n_cand', C.c_int64),
+              ('n_intervals', C.c_int32), ('stride', C.c_int32), ('n_cand', C.c_int64),
               ('min_rhc', C.c_double), ('flat_threshold', C.c_double), ('global_minmax', C.c_double * 4),
               ('kept_list', C.c_void_p), ('n_items', C.c_int64)]
 
@@ -35,7 +35,7 @@ class Outputs(C.Structure):
 
 class Compact(C.Structure):
   _fields_ = [('kept_idx', C.c_void_p), ('start_idx', C.c_void_p), ('stop_idx', C.c_void_p),
-              ('rec_id', C.c_void_p), ('n_kept', C.c_void_p)]
+              ('rec_id', C.c_void_p), ('n_kept', C.c_void_p), ('stride', C.c_int32), ('reserved', C.c_int32)]
 
 
 class ScgrhcError(RuntimeError):
@@ -51,7 +51,7 @@ _lib = None
 SYMBOLS = ['scgrhc_abi_version', 'scgrhc_ctx_create', 'scgrhc_ctx_destroy', 'scgrhc_last_error',
            'scgrhc_ctx_set_tuning', 'scgrhc_ctx_sm_count', 'scgrhc_plan_record', 'scgrhc_process_windows',
            'scgrhc_compact_kept', 'scgrhc_global_minmax', 'scgrhc_check_errors', 'scgrhc_gather_windows',
-           'scgrhc_rolling_range_lt', 'scgrhc_decode_fmt16', 'scgrhc_waveform_stats', 'scgrhc_synth_records', 'scgrhc_selftest_div']
+           'scgrhc_gather_windows_noise', 'scgrhc_philox_words', 'scgrhc_rolling_range_lt', 'scgrhc_decode_fmt16', 'scgrhc_waveform_stats', 'scgrhc_synth_records', 'scgrhc_selftest_div']
 
 
 def lib():
@@ -73,7 +73,7 @@ def lib():
   L.scgrhc_last_error.restype = C.c_char_p
   L.scgrhc_ctx_set_tuning.argtypes = [vp, C.c_int, C.c_int]
   L.scgrhc_ctx_sm_count.argtypes = [vp]
-  L.scgrhc_plan_record.argtypes = [C.POINTER(dbl), C.POINTER(C.c_uint8), C.c_int, i64, i32, i64, i32, i64,
+  L.scgrhc_plan_record.argtypes = [C.POINTER(dbl), C.POINTER(C.c_uint8), C.c_int, i64, i32, i32, i64, i32, i64,
                                    C.POINTER(Interval), C.c_int, C.POINTER(C.c_int), C.POINTER(i64),
                                    C.POINTER(i64), C.c_int, C.POINTER(C.c_int)]
   L.scgrhc_process_windows.argtypes = [vp, C.POINTER(Job), C.POINTER(Outputs), vp]
@@ -81,6 +81,8 @@ def lib():
   L.scgrhc_global_minmax.argtypes = [vp, vp, vp, i64, vp, vp]
   L.scgrhc_check_errors.argtypes = [vp, vp, C.POINTER(i64)]
   L.scgrhc_gather_windows.argtypes = [vp, vp, vp, i64, i64, vp, vp]
+  L.scgrhc_gather_windows_noise.argtypes = [vp, vp, vp, i64, i64, vp, C.c_float, u64, u64, vp]
+  L.scgrhc_philox_words.argtypes = [vp, u64, u64, i64, vp, vp]
   L.scgrhc_rolling_range_lt.argtypes = [vp, vp, i64, i32, dbl, vp, vp]
   L.scgrhc_decode_fmt16.argtypes = [vp, vp, i64, i32, C.POINTER(i32), i32, C.POINTER(dbl), C.POINTER(dbl), vp, vp]
   L.scgrhc_waveform_stats.argtypes = [vp, vp, i64, i64, dbl, vp, vp]

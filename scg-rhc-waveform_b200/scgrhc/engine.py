@@ -41,7 +41,7 @@ def event_table(meta, chamber):
   return times, match
 
 
-def plan_record(meta, chamber, T, W, rec_base_row=0, rec_id=0, cand_base=0):
+def plan_record(meta, chamber, T, W, rec_base_row=0, rec_id=0, cand_base=0, stride=0):
   """(intervals structured array, n_cand, bounds) for one record via the C planner."""
   tab = event_table(meta, chamber)
   if tab is None or len(tab[0]) < 2:
@@ -52,7 +52,7 @@ def plan_record(meta, chamber, T, W, rec_base_row=0, rec_id=0, cand_base=0):
   bounds = (C.c_int64 * (2 * n))()
   n_out, n_b, n_cand = C.c_int(0), C.c_int(0), C.c_int64(0)
   rc = N.lib().scgrhc_plan_record(times.ctypes.data_as(C.POINTER(C.c_double)),
-                                  match.ctypes.data_as(C.POINTER(C.c_uint8)), n, int(T), int(W),
+                                  match.ctypes.data_as(C.POINTER(C.c_uint8)), n, int(T), int(W), int(stride),
                                   int(rec_base_row), int(rec_id), int(cand_base), out, n,
                                   C.byref(n_out), C.byref(n_cand), bounds, n, C.byref(n_b))
   if rc != N.OK:
@@ -69,6 +69,7 @@ class Plan:
   n_cand: int
   W: int
   record_names: List[str] = field(default_factory=list)
+  stride: int = 0                  # 0 = W (non-overlapping, the reference); extension: rows between window starts
   _dev: Optional[torch.Tensor] = None
 
   def device_intervals(self, device):
@@ -79,28 +80,28 @@ class Plan:
     return self._dev
 
 
-def plan_cohort(metas, chamber, T_rows, W, record_names=None):
+def plan_cohort(metas, chamber, T_rows, W, record_names=None, stride=0):
   """Plan for records stored back to back in the arena; ``T_rows[r]`` rows each."""
   ivs, base, cand = [], 0, 0
   for r, meta in enumerate(metas):
-    iv, n, _ = plan_record(meta, chamber, T_rows[r], W, base, r, cand)
+    iv, n, _ = plan_record(meta, chamber, T_rows[r], W, base, r, cand, stride)
     ivs.append(iv)
     base += int(T_rows[r])
     cand += n
   iv = np.concatenate(ivs) if ivs else np.zeros(0, dtype=INTERVAL_DTYPE)
-  return Plan(iv, cand, W, list(record_names) if record_names is not None else [])
+  return Plan(iv, cand, W, list(record_names) if record_names is not None else [], stride)
 
 
-def plan_uniform(meta, chamber, T, W, n_rec, rec0=0):
+def plan_uniform(meta, chamber, T, W, n_rec, rec0=0, stride=0):
   """Every record shares one side-car (synthetic cohorts): plan record 0 in C, replicate with offsets."""
-  iv0, n0, _ = plan_record(meta, chamber, T, W, 0, 0, 0)
+  iv0, n0, _ = plan_record(meta, chamber, T, W, 0, 0, 0, stride)
   k = len(iv0)
   iv = np.tile(iv0, n_rec)
   r = np.repeat(np.arange(n_rec, dtype=np.int64), k)
   iv['row0'] += r * T
   iv['cand0'] += r * n0
   iv['rec_id'] = (r + rec0).astype(np.int32)
-  return Plan(iv, n0 * n_rec, W)
+  return Plan(iv, n0 * n_rec, W, [], stride)
 
 
 @dataclass
@@ -198,9 +199,9 @@ def prepare_windows(arena, plan, scg_cols, rhc_col, min_rhc, use_global_min_max=
     scg = buf('scg', (n, Cn, W), out_dtype)
     rhc = buf('rhc', (n, 1, W), out_dtype)
   flags = base_flags | (N.PREDICATES_ONLY if (predicates_only or two_pass) else 0)
-  ops.process_windows(arena, iv, n, W, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
+  ops.process_windows(arena, iv, n, W, plan.stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
                       [0.0] * 4, None, 0, scg, rhc, minmax, keep, reason, cand_win, cand_rec)
-  ops.compact_kept(keep, cand_win, cand_rec, n, W, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
+  ops.compact_kept(keep, cand_win, cand_rec, n, W, plan.stride, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
   gmm = None
   if use_global_min_max:
     gmm = buf('gmm', (4,), torch.float64)
@@ -214,7 +215,7 @@ def prepare_windows(arena, plan, scg_cols, rhc_col, min_rhc, use_global_min_max=
     scg = buf('scg', (n_kept, Cn, W), out_dtype)
     rhc = buf('rhc', (n_kept, 1, W), out_dtype)
     if n_kept:
-      ops.process_windows(arena, iv, n, W, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold),
+      ops.process_windows(arena, iv, n, W, plan.stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold),
                           base_flags | N.USE_KEPT_LIST | N.NORM_GLOBAL, gmm.cpu().tolist(), kept_idx, n_kept,
                           scg, rhc, minmax, None, None, None, None)
     dense = True
@@ -326,12 +327,12 @@ class HostIngest:
         else:
           ops.decode_fmt16(stage, list(cols), [float(v) for v in gain], [float(v) for v in baseline], dst)
       if nc:
-        ops.process_windows(dst, iv, nc, W, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
+        ops.process_windows(dst, iv, nc, W, plan.stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
                             [0.0] * 4, None, 0, scg[cand_lo:], rhc[cand_lo:], minmax[cand_lo:], keep[cand_lo:],
                             reason[cand_lo:], cand_win[cand_lo:], cand_rec[cand_lo:])
       done[k & 1] = torch.cuda.Event()
       done[k & 1].record(compute)
-    ops.compact_kept(keep, cand_win, cand_rec, n, W, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
+    ops.compact_kept(keep, cand_win, cand_rec, n, W, plan.stride, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
     n_kept = int(n_kept_t.item())      # device -> host read of the step's result
     nonfinite = bool(((reason & N.REASON_NONFINITE) != 0).logical_and((reason & N.REASON_FLAT) == 0).any()) if n else False
     if nonfinite:

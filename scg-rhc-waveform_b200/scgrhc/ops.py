@@ -59,7 +59,7 @@ def _contig(t, dtype, name):
 @torch.library.custom_op('scgrhc::process_windows',
                          mutates_args=('scg_out', 'rhc_out', 'minmax', 'keep', 'reason', 'cand_win', 'cand_rec'),
                          device_types='cuda')
-def process_windows(arena: Tensor, intervals: Tensor, n_cand: int, W: int, scg_cols: Sequence[int], rhc_col: int,
+def process_windows(arena: Tensor, intervals: Tensor, n_cand: int, W: int, stride: int, scg_cols: Sequence[int], rhc_col: int,
                     min_rhc: float, flat_threshold: float, flags: int, global_minmax: Sequence[float],
                     kept_list: Optional[Tensor], n_items: int, scg_out: Optional[Tensor], rhc_out: Optional[Tensor],
                     minmax: Optional[Tensor], keep: Optional[Tensor], reason: Optional[Tensor],
@@ -83,6 +83,7 @@ def process_windows(arena: Tensor, intervals: Tensor, n_cand: int, W: int, scg_c
   j.arena_capacity_bytes = arena.numel() * 8
   j.nsig = arena.shape[1]
   j.W = W
+  j.stride = stride
   j.C = len(scg_cols)
   for i, c in enumerate(scg_cols):
     j.scg_cols[i] = c
@@ -111,7 +112,7 @@ def process_windows(arena: Tensor, intervals: Tensor, n_cand: int, W: int, scg_c
 
 @torch.library.custom_op('scgrhc::compact_kept', mutates_args=('kept_idx', 'start_idx', 'stop_idx', 'rec_id', 'n_kept'),
                          device_types='cuda')
-def compact_kept(keep: Tensor, cand_win: Tensor, cand_rec: Tensor, n_cand: int, W: int, kept_idx: Tensor,
+def compact_kept(keep: Tensor, cand_win: Tensor, cand_rec: Tensor, n_cand: int, W: int, stride: int, kept_idx: Tensor,
                  start_idx: Tensor, stop_idx: Tensor, rec_id: Tensor, n_kept: Tensor) -> None:
   """Ordered list of kept windows = the order of the list get_segments returns (recordutil.py:148)."""
   dev = _dev(keep)
@@ -119,7 +120,7 @@ def compact_kept(keep: Tensor, cand_win: Tensor, cand_rec: Tensor, n_cand: int, 
   for t, nm in ((kept_idx, 'kept_idx'), (start_idx, 'start_idx'), (stop_idx, 'stop_idx'), (n_kept, 'n_kept')):
     _contig(t, torch.int64, nm)
   _contig(rec_id, torch.int32, 'rec_id')
-  co = N.Compact(_ptr(kept_idx), _ptr(start_idx), _ptr(stop_idx), _ptr(rec_id), _ptr(n_kept))
+  co = N.Compact(_ptr(kept_idx), _ptr(start_idx), _ptr(stop_idx), _ptr(rec_id), _ptr(n_kept), stride, 0)
   c = ctx(dev)
   N.check(c, N.lib().scgrhc_compact_kept(c, _ptr(keep), _ptr(cand_win), _ptr(cand_rec), n_cand, W, C.byref(co), _stream(dev)))
 
@@ -145,6 +146,27 @@ def gather_windows(store: Tensor, slots: Tensor, out: Tensor) -> None:
     raise ValueError('out too small')
   c = ctx(dev)
   N.check(c, N.lib().scgrhc_gather_windows(c, _ptr(store), _ptr(slots), slots.numel(), wb, _ptr(out), _stream(dev)))
+
+
+@torch.library.custom_op('scgrhc::gather_windows_noise', mutates_args=('out',), device_types='cuda')
+def gather_windows_noise(store: Tensor, slots: Tensor, out: Tensor, sigma: float, seed: int, offset: int) -> None:
+  """Extension (absent from the reference): batch gather + sigma * N(0,1) from Philox4x32-10 / Box-Muller."""
+  dev = _dev(store)
+  _contig(slots, torch.int64, 'slots'); _contig(store, torch.float32, 'store'); _contig(out, torch.float32, 'out')
+  E = store[0].numel()
+  if out.numel() < E * slots.numel():
+    raise ValueError('out too small')
+  c = ctx(dev)
+  N.check(c, N.lib().scgrhc_gather_windows_noise(c, _ptr(store), _ptr(slots), slots.numel(), E, _ptr(out), C.c_float(sigma),
+                                                 C.c_uint64(seed & (2 ** 64 - 1)), C.c_uint64(offset & (2 ** 64 - 1)), _stream(dev)))
+
+
+def philox_words(device_index, seed, offset, nquads):
+  """Raw Philox4x32-10 blocks (nquads, 4) uint32 as int64 numpy array, for seed-exact checks."""
+  out = torch.empty((nquads, 4), dtype=torch.int32, device='cuda:%d' % device_index)
+  c = ctx(device_index)
+  N.check(c, N.lib().scgrhc_philox_words(c, C.c_uint64(seed), C.c_uint64(offset), nquads, _ptr(out), _stream(device_index)))
+  return out.cpu().numpy().astype('int64') & 0xFFFFFFFF
 
 
 @torch.library.custom_op('scgrhc::rolling_range_lt', mutates_args=('flags',), device_types='cuda')

@@ -215,3 +215,37 @@ def test_device_decode_matches_host_dac_and_digital_ingest(tmp_path, monkeypatch
     assert torch.equal(dig.kept_minmax(), phy.kept_minmax())
     a, b = dig.materialise(), phy.materialise()
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_noise_injection_extension_philox():
+  """Extension (absent from the reference): seed-exact Philox4x32-10 stream, Box-Muller within fp32 tolerance,
+  distribution checks, and the loader wiring (SCG inputs only, a fresh stream per batch, off by default)."""
+  from oracle import philox_ref
+  from scgrhc import ops
+  for seed, offset in ((0, 0), (0x5C6, 7), (0xDEADBEEFCAFEF00D, 0x1_0000_0003)):
+    got = ops.philox_words(0, seed, offset, 4096)
+    assert (got == philox_ref.words(seed, offset, 4096).astype(np.int64)).all()
+  n, C, W = 300, 3, 750
+  g = torch.Generator().manual_seed(1)
+  store = torch.rand((n, C, W), generator=g).cuda()
+  slots = torch.randperm(n, generator=g)[:256].cuda()
+  out = torch.empty((256, C, W), dtype=torch.float32, device='cuda')
+  sigma = 0.05
+  ops.gather_windows_noise(store, slots, out, sigma, 99, 5)
+  z = philox_ref.normals(99, 5, 256 * C * W).reshape(256, C, W)
+  want = store[slots].cpu().numpy() + np.float32(sigma) * z
+  assert np.abs(out.cpu().numpy() - want).max() < 2e-6
+  resid = ((out - store[slots]) / sigma).double().flatten().cpu().numpy()
+  assert abs(resid.mean()) < 5e-3 and abs(resid.std() - 1) < 5e-3
+  from scipy import stats
+  assert stats.kstest(resid[::7], 'norm').pvalue > 1e-3
+  assert abs(stats.skew(resid)) < 0.02 and abs(stats.kurtosis(resid)) < 0.05
+  # loader wiring
+  ds = recordutil.SCGDataset.from_arrays(store, torch.rand((n, 1, W)).cuda(), ['r'] * n, np.arange(n) * W, np.arange(n) * W + W,
+                                         np.zeros((n, 4)), 1.5)
+  plain = list(recordutil.WindowLoader(ds, batch_size=128))
+  noisy = recordutil.WindowLoader(ds, batch_size=128, noise_std=0.1, noise_seed=4)
+  a, b = list(noisy), list(noisy)
+  assert torch.equal(plain[0][0], store[:128]) and torch.equal(a[0][1], plain[0][1])          # targets untouched
+  d0 = (a[0][0] - plain[0][0]).std().item()
+  assert 0.09 < d0 < 0.11 and not torch.equal(a[0][0], b[0][0]) and not torch.equal(a[0][0][:44], a[1][0][:44])

@@ -314,3 +314,22 @@ def test_unsupported_shapes_fail_loudly():
     scgrhc.prepare_windows(arena, plan, [0, 1, 7], 3, -50.0)
   with pytest.raises(RuntimeError):
     scgrhc.prepare_windows(arena.cpu(), plan, [0, 1, 2], 3, -50.0)
+
+
+@pytest.mark.parametrize('stride', [750, 250, 1, 1000])
+def test_strided_windows_extension(stride):
+  """Overlapping / gapped windows (extension; stride == W is the reference): same per-window arithmetic."""
+  sig = synth_ref.DEFAULT_SIG_NAMES
+  T = 9000
+  p = synth_ref.gen_record(H.SEED, 31, T, kinds=synth_ref.kinds_for(sig))
+  meta = synth_ref.record_meta(18, events={'PA_1': 0.5, 'RV_1': 9.3, 'PA_2': 11})
+  plan = scgrhc.plan_cohort([meta], 'PA', [T], 750, stride=stride)
+  arena = torch.from_numpy(p).to(DEV)
+  st = scgrhc.prepare_windows(arena, plan, [0, 1, 2], 3, -50.0)
+  rw = orc.scan_record(p, sig, meta, sig[:3], 'PA', 1.5, -50.0, stride=stride)
+  assert plan.n_cand == len(rw.abs_start) > 0
+  k = np.nonzero(rw.keep)[0]
+  assert st.start_idx.cpu().tolist() == rw.rel_start[k].tolist() and st.stop_idx.cpu().tolist() == (rw.rel_start[k] + 750).tolist()
+  s_o, r_o, mm_o = orc.normalise_record(p, sig, sig[:3], rw)
+  scg, rhc = st.materialise()
+  assert scg.cpu().numpy().tobytes() == s_o.tobytes() and rhc.cpu().numpy().tobytes() == r_o.tobytes()

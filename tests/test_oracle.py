@@ -90,3 +90,16 @@ def test_records_full_all_configs():
       assert H.sha(mm) == want['minmax_sha'], (cfg, n)
       assert H.sha(scg) == want['scg_sha'], (cfg, n)
       assert H.sha(rhc) == want['rhc_sha'], (cfg, n)
+
+
+def test_philox_known_answer_vectors():
+  """Random123 kat_vectors for philox4x32_10 pin the host generator the device stream is compared with."""
+  from oracle import philox_ref
+  kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+         ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+         ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+  for ctr, key, want in kat:
+    got = philox_ref.philox4x32_10(np.array([ctr], dtype=np.uint64), key)[0]
+    assert tuple(int(v) for v in got) == want
+  z = philox_ref.normals(7, 3, 200000)
+  assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01

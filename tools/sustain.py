@@ -23,7 +23,7 @@ def rd():
   for line in p.stdout: samples.append((time.time(), line.strip()))
 threading.Thread(target=rd, daemon=True).start()
 def step():
-  ops.process_windows(arena, iv, n, W, [0, 1, 2], 3, -50.0, 1e-3, 0, [0.0] * 4, None, 0, scg, rhc, minmax, keep, reason, cw, cr)
+  ops.process_windows(arena, iv, n, W, 0, [0, 1, 2], 3, -50.0, 1e-3, 0, [0.0] * 4, None, 0, scg, rhc, minmax, keep, reason, cw, cr)
 for _ in range(3): step()
 torch.cuda.synchronize()
 time.sleep(0.5)

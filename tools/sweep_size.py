@@ -28,7 +28,7 @@ def run(n_rec, iters=10, flags=0):
   cr = torch.empty(n, dtype=torch.int32, device=dev)
 
   def step():
-    ops.process_windows(arena, iv, n, W, [0, 1, 2], 3, -50.0, 1e-3, flags, [0.0] * 4, None, 0, scg, rhc, minmax, keep, reason, cw, cr)
+    ops.process_windows(arena, iv, n, W, 0, [0, 1, 2], 3, -50.0, 1e-3, flags, [0.0] * 4, None, 0, scg, rhc, minmax, keep, reason, cw, cr)
   for _ in range(3):
     step()
   torch.cuda.synchronize()

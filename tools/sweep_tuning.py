@@ -35,7 +35,7 @@ def main():
         try:
           ops.set_tuning(0, ctas, stages)
           def step():
-            ops.process_windows(arena, iv, n, W, [0, 1, 2], 3, -50.0, 1e-3, flags, [0.0] * 4, None, 0,
+            ops.process_windows(arena, iv, n, W, 0, [0, 1, 2], 3, -50.0, 1e-3, flags, [0.0] * 4, None, 0,
                                 scg, rhc, minmax, keep, reason, cw, cr)
           for _ in range(3):
             step()
