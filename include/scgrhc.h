@@ -162,6 +162,22 @@ int scgrhc_gather_windows_noise(scgrhc_ctx* ctx, const float* store, const int64
                                 int64_t window_elems, float* out, float sigma, uint64_t seed, uint64_t offset, void* stream);
 int scgrhc_philox_words(scgrhc_ctx* ctx, uint64_t seed, uint64_t offset, int64_t nquads, uint32_t* out, void* stream);
 
+/* ---- evaluation metrics of the consumer (waveform_test.py:21-50,66-70), per window: both fp32 waveforms (n, W) are
+ *      de-normalised with the window's RHC pair minmax (n, 2) = {rhc_min, rhc_max} as reverse_minmax does
+ *      (v * (max - min) + min in fp64, no epsilon); out (n, 2) = {Pearson r, RMSE}.  Confidence intervals stay on the host. */
+int scgrhc_window_metrics(scgrhc_ctx* ctx, const float* real, const float* pred, const double* minmax, int64_t n,
+                          int32_t W, double* out, void* stream);
+
+/* ---- extension (named by the project brief, ABSENT from the reference; default off): zero-phase IIR filtering of
+ *      the columns fcols[0..ncf) of every record of the arena, scipy.signal.sosfiltfilt semantics (odd extension by
+ *      `edge` samples, lfilter_zi initial state scaled by the first sample, forward pass, reversed second pass, trim).
+ *      x, y: (rows, ncols) device (y may alias nothing of x; unfiltered columns of y are not written); tmp: device,
+ *      (rows + 2*edge*n_rec) * ncf doubles; row0: n_rec+1 record boundaries, on the device AND on the host; sos
+ *      (nsec, 6) with a0 == 1, zi (nsec, 2) = scipy.signal.sosfilt_zi(sos), both host.  Bit-identical to scipy. */
+int scgrhc_sosfiltfilt(scgrhc_ctx* ctx, const double* x, double* y, double* tmp, const int64_t* row0_dev,
+                       const int64_t* row0_host, int32_t n_rec, int32_t ncols, const int32_t* fcols, int32_t ncf,
+                       const double* sos, const double* zi, int32_t nsec, int32_t edge, void* stream);
+
 /* ---- standalone predicate helpers for API parity of waveform_noise.get_flat_lines with
  *      non-default arguments: flags[p] = (rolling range over m samples ending at p) < threshold */
 int scgrhc_rolling_range_lt(scgrhc_ctx* ctx, const double* y, int64_t n, int32_t m, double threshold,

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "aux_kernels.cuh"
+#include "filter_kernels.cuh"
 #include "window_kernel.cuh"
 
 using namespace scgrhc;
@@ -334,6 +335,53 @@ extern "C" int scgrhc_philox_words(scgrhc_ctx* ctx, uint64_t seed, uint64_t offs
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   philox_words_kernel<<<(unsigned)((nquads + 255) / 256), 256, 0, st>>>(seed, offset, nquads, reinterpret_cast<uint4*>(out));
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_window_metrics(scgrhc_ctx* ctx, const float* real, const float* pred, const double* minmax, int64_t n,
+                                     int32_t W, double* out, void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (n < 0 || W < 2 || (n && (!real || !pred || !minmax || !out))) return fail(ctx, SCGRHC_ERR_BAD_ARG, "window_metrics: bad arguments");
+  if (n == 0) return SCGRHC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const unsigned grid = (unsigned)std::min<long long>((n + 7) / 8, (long long)ctx->sm_count * 8);
+  window_metrics_kernel<<<grid, 256, 0, st>>>(real, pred, minmax, n, W, out);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_sosfiltfilt(scgrhc_ctx* ctx, const double* x, double* y, double* tmp, const int64_t* row0_dev,
+                                  const int64_t* row0_host, int32_t n_rec, int32_t ncols, const int32_t* fcols, int32_t ncf,
+                                  const double* sos, const double* zi, int32_t nsec, int32_t edge, void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (n_rec < 0 || ncols < 1 || ncf < 1 || ncf > kMaxFilterCols || nsec < 1 || nsec > kMaxSections || edge < 0 || !sos || !zi || !fcols ||
+      (n_rec && (!x || !y || !tmp || !row0_dev || !row0_host)))
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "sosfiltfilt: bad arguments (1..%d sections, 1..%d filtered columns)", kMaxSections, kMaxFilterCols);
+  if (n_rec == 0) return SCGRHC_OK;
+  SosParams P;
+  P.x = x; P.y = y; P.tmp = tmp; P.row0 = reinterpret_cast<const long long*>(row0_dev);
+  P.n_rec = n_rec; P.ncols = ncols; P.nsec = nsec; P.edge = edge; P.ncf = ncf;
+  for (int r = 0; r < n_rec; ++r)
+    if (row0_host[r + 1] - row0_host[r] <= edge)   // scipy: "The length of the input vector x must be greater than padlen"
+      return fail(ctx, SCGRHC_ERR_BAD_ARG, "The length of the input vector x must be greater than padlen, which is %d.", edge);
+  for (int j = 0; j < ncf; ++j) {
+    if (fcols[j] < 0 || fcols[j] >= ncols) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "sosfiltfilt: column %d outside 0..%d", fcols[j], ncols - 1);
+    P.fcols[j] = fcols[j];
+  }
+  for (int s = 0; s < nsec; ++s) {
+    if (sos[6 * s + 3] != 1.0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "sos[:, 3] should be all ones");
+    for (int k = 0; k < 6; ++k) P.sos[s][k] = sos[6 * s + k];
+    P.zi[s][0] = zi[2 * s]; P.zi[s][1] = zi[2 * s + 1];
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int cpw = 32 / nsec, groups = (ncf + cpw - 1) / cpw;
+  const long long warps = (long long)n_rec * groups;
+  const unsigned grid = (unsigned)((warps + 3) / 4);
+  sosfilt_pass_kernel<0><<<grid, 128, 0, st>>>(P);
+  sosfilt_pass_kernel<1><<<grid, 128, 0, st>>>(P);
   CUDA_TRY(ctx, cudaGetLastError());
   return SCGRHC_OK;
 }

@@ -241,6 +241,43 @@ __global__ void philox_words_kernel(unsigned long long seed, unsigned long long 
                            make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
 }
 
+// ---- evaluation metrics of waveform_test.py:21-50,66-70 on the device: de-normalise both waveforms with the window's
+//      RHC pair (reverse_minmax: v*(max-min)+min, no epsilon), Pearson r (centred, as scipy.stats.pearsonr) and RMSE.
+//      One warp per window; out[w] = {pcc_r, rmse}.
+__global__ void __launch_bounds__(256) window_metrics_kernel(const float* __restrict__ real, const float* __restrict__ pred,
+                                                             const double* __restrict__ minmax, long long n, int W,
+                                                             double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long w = warp0; w < n; w += nwarps) {
+    const double mn = minmax[2 * w], range = __dsub_rn(minmax[2 * w + 1], mn);
+    const float* a = real + w * W;
+    const float* b = pred + w * W;
+    double sx = 0, sy = 0, sd = 0;
+    for (int i = lane; i < W; i += 32) {
+      const double x = __dadd_rn(__dmul_rn((double)a[i], range), mn), y = __dadd_rn(__dmul_rn((double)b[i], range), mn);
+      sx = __dadd_rn(sx, x); sy = __dadd_rn(sy, y);
+      const double d = __dsub_rn(x, y);
+      sd = __fma_rn(d, d, sd);
+    }
+    sx = warp_sum(sx); sy = warp_sum(sy); sd = warp_sum(sd);
+    const double mx = sx / W, my = sy / W;
+    double sxx = 0, syy = 0, sxy = 0;
+    for (int i = lane; i < W; i += 32) {
+      const double x = __dsub_rn(__dadd_rn(__dmul_rn((double)a[i], range), mn), mx);
+      const double y = __dsub_rn(__dadd_rn(__dmul_rn((double)b[i], range), mn), my);
+      sxx = __fma_rn(x, x, sxx); syy = __fma_rn(y, y, syy); sxy = __fma_rn(x, y, sxy);
+    }
+    sxx = warp_sum(sxx); syy = warp_sum(syy); sxy = warp_sum(sxy);
+    if (lane == 0) {
+      double r = sxy / (sqrt(sxx) * sqrt(syy));
+      r = r > 1.0 ? 1.0 : (r < -1.0 ? -1.0 : r);
+      out[2 * w] = r;
+      out[2 * w + 1] = sqrt(sd / W);
+    }
+  }
+}
+
 // ---- standalone rolling range (API parity of get_flat_lines with non-default arguments) ------------
 __global__ void rolling_range_lt_kernel(const double* __restrict__ y, long long n, int m, double thr,
                                         uint8_t* __restrict__ flags) {

@@ -169,6 +169,20 @@ def philox_words(device_index, seed, offset, nquads):
   return out.cpu().numpy().astype('int64') & 0xFFFFFFFF
 
 
+@torch.library.custom_op('scgrhc::window_metrics', mutates_args=('out',), device_types='cuda')
+def window_metrics(real: Tensor, pred: Tensor, minmax: Tensor, out: Tensor) -> None:
+  """Per window: de-normalise real/pred (n, W) fp32 with (rhc_min, rhc_max) and return Pearson r and RMSE
+  (waveform_test.py:21-50,66-70: reverse_minmax, pearsonr, sqrt(mean_squared_error))."""
+  dev = _dev(real)
+  _contig(real, torch.float32, 'real'); _contig(pred, torch.float32, 'pred')
+  _contig(minmax, torch.float64, 'minmax'); _contig(out, torch.float64, 'out')
+  n, W = real.shape[0], real[0].numel()
+  if pred.numel() != real.numel() or minmax.numel() < 2 * n or out.numel() < 2 * n:
+    raise ValueError('window_metrics: shape mismatch')
+  c = ctx(dev)
+  N.check(c, N.lib().scgrhc_window_metrics(c, _ptr(real), _ptr(pred), _ptr(minmax), n, W, _ptr(out), _stream(dev)))
+
+
 @torch.library.custom_op('scgrhc::rolling_range_lt', mutates_args=('flags',), device_types='cuda')
 def rolling_range_lt(y: Tensor, m: int, threshold: float, flags: Tensor) -> None:
   """flags[p] = rolling(m).max - rolling(m).min < threshold (waveform_noise.py:10-13)."""

@@ -249,3 +249,24 @@ def test_noise_injection_extension_philox():
   assert torch.equal(plain[0][0], store[:128]) and torch.equal(a[0][1], plain[0][1])          # targets untouched
   d0 = (a[0][0] - plain[0][0]).std().item()
   assert 0.09 < d0 < 0.11 and not torch.equal(a[0][0], b[0][0]) and not torch.equal(a[0][0][:44], a[1][0][:44])
+
+
+def test_evaluation_metrics_on_device_match_consumer_formulas():
+  """waveform_test.py:21-50 (reverse_minmax, scipy pearsonr, sqrt(sklearn MSE)) per window, on the device."""
+  from scipy.stats import pearsonr
+  from sklearn.metrics import mean_squared_error
+  from scgrhc import ops
+  g = torch.Generator().manual_seed(3)
+  n, W = 64, 750
+  real = torch.rand((n, 1, W), generator=g)
+  pred = (real + 0.1 * torch.randn((n, 1, W), generator=g)).clamp(0, 1)
+  pred[5] = real[5]                                    # r == 1 exactly
+  mm = np.stack([np.linspace(-5, 20, n), np.linspace(30, 90, n)], axis=1)
+  out = torch.empty((n, 2), dtype=torch.float64, device='cuda')
+  ops.window_metrics(real.cuda(), pred.cuda(), torch.from_numpy(mm).cuda(), out)
+  got = out.cpu().numpy()
+  for i in range(n):
+    x = real[i].numpy()[0, :] * (np.float64(mm[i, 1]) - np.float64(mm[i, 0])) + np.float64(mm[i, 0])   # reverse_minmax
+    y = pred[i].numpy()[0, :] * (np.float64(mm[i, 1]) - np.float64(mm[i, 0])) + np.float64(mm[i, 0])
+    assert abs(got[i, 0] - pearsonr(x, y).statistic) < 1e-12
+    assert abs(got[i, 1] - np.sqrt(mean_squared_error(x, y))) < 1e-12 * max(1.0, got[i, 1])
