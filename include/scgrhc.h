@@ -128,7 +128,8 @@ int scgrhc_ctx_sm_count(const scgrhc_ctx* ctx);
  * Writes up to out_cap intervals (also the empty ones are skipped) and the raw (a,b) sample
  * bounds of every matching event to bounds[2*k] (may be NULL).  cand_base seeds cand0. */
 int scgrhc_plan_record(const double* event_time, const uint8_t* event_match, int n_events,
-                       int64_t T, int32_t W, int32_t stride /* 0 = W */, int64_t rec_base_row, int32_t rec_id, int64_t cand_base,
+                       int64_t T, int32_t W, int32_t stride /* 0 = W */, double fs /* <= 0: 500 Hz, recordutil.py:19 */,
+                       int64_t rec_base_row, int32_t rec_id, int64_t cand_base,
                        scgrhc_interval* out, int out_cap, int* n_out, int64_t* n_cand,
                        int64_t* bounds, int bounds_cap, int* n_bounds);
 
@@ -177,6 +178,15 @@ int scgrhc_window_metrics(scgrhc_ctx* ctx, const float* real, const float* pred,
 int scgrhc_sosfiltfilt(scgrhc_ctx* ctx, const double* x, double* y, double* tmp, const int64_t* row0_dev,
                        const int64_t* row0_host, int32_t n_rec, int32_t ncols, const int32_t* fcols, int32_t ncf,
                        const double* sos, const double* zi, int32_t nsec, int32_t edge, void* stream);
+
+/* ---- extension (named by the project brief, ABSENT from the reference; default off): rational resampling of every
+ *      record of the arena, scipy.signal.resample_poly semantics (polyphase upfirdn, zero padding).  taps: device,
+ *      scipy's transposed-flipped table (up x per_phase, scipy/signal/_upfirdn.py:_pad_h) of the up-scaled, pre-padded
+ *      FIR; in0/out0: device record boundaries (n_rec+1) of x (rows_in, ncols) and y (rows_out, ncols);
+ *      out rows per record = ceil(n_in*up/down); n_pre_remove as in resample_poly.  Bit-identical to scipy. */
+int scgrhc_resample_poly(scgrhc_ctx* ctx, const double* x, double* y, const double* taps_dev, const int64_t* in0_dev,
+                         const int64_t* out0_dev, int32_t n_rec, int64_t max_out_rows, int32_t ncols, int32_t up, int32_t down,
+                         int32_t per_phase, int32_t n_pre_remove, void* stream);
 
 /* ---- standalone predicate helpers for API parity of waveform_noise.get_flat_lines with
  *      non-default arguments: flags[p] = (rolling range over m samples ending at p) < threshold */

@@ -112,10 +112,11 @@ static void slice_indices(int64_t a, int64_t b, int64_t T, int64_t* lo, int64_t*
 }
 
 extern "C" int scgrhc_plan_record(const double* event_time, const uint8_t* event_match, int n_events, int64_t T,
-                                  int32_t W, int32_t stride, int64_t rec_base_row, int32_t rec_id, int64_t cand_base,
+                                  int32_t W, int32_t stride, double fs, int64_t rec_base_row, int32_t rec_id, int64_t cand_base,
                                   scgrhc_interval* out, int out_cap, int* n_out, int64_t* n_cand, int64_t* bounds,
                                   int bounds_cap, int* n_bounds) {
   if (stride == 0) stride = W;
+  if (!(fs > 0.0)) fs = (double)SCGRHC_SAMPLE_FREQ;
   if (!n_out || !n_cand || W <= 0 || stride < 0 || T < 0 || n_events < 0 || (n_events && (!event_time || !event_match)))
     return SCGRHC_ERR_BAD_ARG;
   std::vector<int> order(n_events);
@@ -126,8 +127,8 @@ extern "C" int scgrhc_plan_record(const double* event_time, const uint8_t* event
   for (int i = 0; i + 1 < n_events; ++i) {
     const int e = order[i];
     if (!event_match[e]) continue;
-    const int64_t a = py_trunc(event_time[e] * (double)SCGRHC_SAMPLE_FREQ);
-    const int64_t b = py_trunc(event_time[order[i + 1]] * (double)SCGRHC_SAMPLE_FREQ);
+    const int64_t a = py_trunc(event_time[e] * fs);
+    const int64_t b = py_trunc(event_time[order[i + 1]] * fs);
     if (bounds && nb < bounds_cap) { bounds[2 * nb] = a; bounds[2 * nb + 1] = b; }
     ++nb;
     int64_t lo, hi;
@@ -299,15 +300,19 @@ extern "C" int scgrhc_global_minmax(scgrhc_ctx* ctx, const double* minmax, const
 extern "C" int scgrhc_gather_windows(scgrhc_ctx* ctx, const void* store, const int64_t* slots, int64_t n,
                                      int64_t window_bytes, void* out, void* stream) {
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
-  if (n < 0 || window_bytes <= 0 || (window_bytes & 7) || (n && (!store || !slots || !out)))
-    return fail(ctx, SCGRHC_ERR_BAD_ARG, "gather: bad arguments (window_bytes must be a positive multiple of 8)");
+  if (n < 0 || window_bytes <= 0 || (window_bytes & 3) || (n && (!store || !slots || !out)))
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "gather: bad arguments (window_bytes must be a positive multiple of 4)");
   if (n == 0) return SCGRHC_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const unsigned grid = (unsigned)std::min<long long>(n, (long long)ctx->sm_count * 8);
-  gather_windows_kernel<<<grid, 256, 0, st>>>(static_cast<const unsigned char*>(store),
-                                              reinterpret_cast<const long long*>(slots), n, window_bytes,
-                                              static_cast<unsigned char*>(out));
+  const bool w8 = (window_bytes & 7) == 0 && (reinterpret_cast<uintptr_t>(store) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+  if (w8)
+    gather_windows_kernel<uint2><<<grid, 256, 0, st>>>(static_cast<const unsigned char*>(store), reinterpret_cast<const long long*>(slots),
+                                                       n, window_bytes, static_cast<unsigned char*>(out));
+  else
+    gather_windows_kernel<unsigned int><<<grid, 256, 0, st>>>(static_cast<const unsigned char*>(store), reinterpret_cast<const long long*>(slots),
+                                                              n, window_bytes, static_cast<unsigned char*>(out));
   CUDA_TRY(ctx, cudaGetLastError());
   return SCGRHC_OK;
 }
@@ -382,6 +387,30 @@ extern "C" int scgrhc_sosfiltfilt(scgrhc_ctx* ctx, const double* x, double* y, d
   const unsigned grid = (unsigned)((warps + 3) / 4);
   sosfilt_pass_kernel<0><<<grid, 128, 0, st>>>(P);
   sosfilt_pass_kernel<1><<<grid, 128, 0, st>>>(P);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_resample_poly(scgrhc_ctx* ctx, const double* x, double* y, const double* taps_dev, const int64_t* in0_dev,
+                                    const int64_t* out0_dev, int32_t n_rec, int64_t max_out_rows, int32_t ncols, int32_t up, int32_t down,
+                                    int32_t per_phase, int32_t n_pre_remove, void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (n_rec < 0 || ncols < 1 || up < 1 || down < 1 || per_phase < 1 || n_pre_remove < 0 || max_out_rows < 0 ||
+      (n_rec && (!x || !y || !taps_dev || !in0_dev || !out0_dev)))
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "resample_poly: bad arguments");
+  const size_t smem = (size_t)up * per_phase * sizeof(double);
+  if (smem > 200 * 1024) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "resample_poly: %zu bytes of taps do not fit in shared memory", smem);
+  if (n_rec == 0 || max_out_rows == 0) return SCGRHC_OK;
+  if (n_rec > 65535) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "resample_poly: at most 65535 records per call");
+  ResampleParams P;
+  P.x = x; P.y = y; P.taps = taps_dev; P.in0 = reinterpret_cast<const long long*>(in0_dev);
+  P.out0 = reinterpret_cast<const long long*>(out0_dev);
+  P.n_rec = n_rec; P.ncols = ncols; P.up = up; P.down = down; P.per_phase = per_phase; P.n_pre_remove = n_pre_remove;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(resample_poly_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)std::min<long long>((max_out_rows + 255) / 256, 1024), (unsigned)n_rec);
+  resample_poly_kernel<<<grid, 256, smem, st>>>(P);
   CUDA_TRY(ctx, cudaGetLastError());
   return SCGRHC_OK;
 }

@@ -156,14 +156,15 @@ __global__ void minmax_final_kernel(const double* __restrict__ partial, int npar
   out[0] = v0; out[1] = v1; out[2] = v2; out[3] = v3;
 }
 
-// ---- batch collate: out[b] = store[slot[b]], window_bytes a multiple of 8 -------------------------
+// ---- batch collate: out[b] = store[slot[b]]; WordT = 8-byte words when window_bytes allows, else 4-byte -------
+template <typename WordT>
 __global__ void __launch_bounds__(256) gather_windows_kernel(const unsigned char* __restrict__ store,
                                                              const long long* __restrict__ slots, long long n,
                                                              long long window_bytes, unsigned char* __restrict__ out) {
-  const long long words = window_bytes >> 3;
+  const long long words = window_bytes / (long long)sizeof(WordT);
   for (long long b = blockIdx.x; b < n; b += gridDim.x) {
-    const uint2* src = reinterpret_cast<const uint2*>(store + slots[b] * window_bytes);
-    uint2* dst = reinterpret_cast<uint2*>(out + b * window_bytes);
+    const WordT* src = reinterpret_cast<const WordT*>(store + slots[b] * window_bytes);
+    WordT* dst = reinterpret_cast<WordT*>(out + b * window_bytes);
     for (long long i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldcs(src + i);
   }
 }

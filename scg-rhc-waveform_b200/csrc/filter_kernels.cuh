@@ -100,3 +100,47 @@ __global__ void __launch_bounds__(128) sosfilt_pass_kernel(const __grid_constant
 }
 
 }  // namespace scgrhc
+
+namespace scgrhc {
+
+// Extension: polyphase rational resampling with scipy.signal.resample_poly / upfirdn semantics (zero padding).  The
+// host passes scipy's transposed-flipped coefficient table h_trans_flip (up phases x per_phase taps, _upfirdn.py:_pad_h);
+// output sample m of a record is  sum_k x[x_idx - per_phase + 1 + k] * h_trans_flip[t*per_phase + k]  with
+// x_idx = (m*down)/up, t = (m*down)%up, accumulated oldest-sample-first with separately rounded multiply and add,
+// exactly like the compiled loop in _upfirdn_apply.pyx, so the result is bit-identical to scipy.  Taps are staged
+// in shared memory; every thread produces one output row (all columns are resampled: the rate change must keep the
+// channels aligned).
+struct ResampleParams {
+  const double* x;         // (rows_in, ncols)
+  double* y;               // (rows_out, ncols)
+  const double* taps;      // device, up * per_phase
+  const long long* in0;    // device, n_rec + 1
+  const long long* out0;   // device, n_rec + 1
+  int n_rec, ncols, up, down, per_phase, n_pre_remove;
+};
+
+__global__ void __launch_bounds__(256) resample_poly_kernel(const __grid_constant__ ResampleParams P) {
+  extern __shared__ double s_taps[];
+  const int ntaps = P.up * P.per_phase;
+  for (int i = threadIdx.x; i < ntaps; i += blockDim.x) s_taps[i] = P.taps[i];
+  __syncthreads();
+  const int rec = blockIdx.y;
+  const long long i0 = P.in0[rec], len_x = P.in0[rec + 1] - i0;
+  const long long o0 = P.out0[rec], n_out = P.out0[rec + 1] - o0;
+  for (long long mo = (long long)blockIdx.x * blockDim.x + threadIdx.x; mo < n_out; mo += (long long)gridDim.x * blockDim.x) {
+    const long long m = mo + P.n_pre_remove;
+    const long long x_idx = (m * P.down) / P.up;
+    const int t = (int)((m * P.down) % P.up);
+    const double* h = s_taps + t * P.per_phase;
+    for (int c = 0; c < P.ncols; ++c) {
+      double acc = 0.0;
+      for (int k = 0; k < P.per_phase; ++k) {
+        const long long xi = x_idx - P.per_phase + 1 + k;
+        if (xi >= 0 && xi < len_x) acc = __dadd_rn(acc, __dmul_rn(P.x[(i0 + xi) * P.ncols + c], h[k]));
+      }
+      P.y[(o0 + mo) * P.ncols + c] = acc;
+    }
+  }
+}
+
+}  // namespace scgrhc

@@ -41,7 +41,7 @@ def event_table(meta, chamber):
   return times, match
 
 
-def plan_record(meta, chamber, T, W, rec_base_row=0, rec_id=0, cand_base=0, stride=0):
+def plan_record(meta, chamber, T, W, rec_base_row=0, rec_id=0, cand_base=0, stride=0, fs=0.0):
   """(intervals structured array, n_cand, bounds) for one record via the C planner."""
   tab = event_table(meta, chamber)
   if tab is None or len(tab[0]) < 2:
@@ -52,7 +52,7 @@ def plan_record(meta, chamber, T, W, rec_base_row=0, rec_id=0, cand_base=0, stri
   bounds = (C.c_int64 * (2 * n))()
   n_out, n_b, n_cand = C.c_int(0), C.c_int(0), C.c_int64(0)
   rc = N.lib().scgrhc_plan_record(times.ctypes.data_as(C.POINTER(C.c_double)),
-                                  match.ctypes.data_as(C.POINTER(C.c_uint8)), n, int(T), int(W), int(stride),
+                                  match.ctypes.data_as(C.POINTER(C.c_uint8)), n, int(T), int(W), int(stride), float(fs),
                                   int(rec_base_row), int(rec_id), int(cand_base), out, n,
                                   C.byref(n_out), C.byref(n_cand), bounds, n, C.byref(n_b))
   if rc != N.OK:
@@ -80,11 +80,11 @@ class Plan:
     return self._dev
 
 
-def plan_cohort(metas, chamber, T_rows, W, record_names=None, stride=0):
+def plan_cohort(metas, chamber, T_rows, W, record_names=None, stride=0, fs=0.0):
   """Plan for records stored back to back in the arena; ``T_rows[r]`` rows each."""
   ivs, base, cand = [], 0, 0
   for r, meta in enumerate(metas):
-    iv, n, _ = plan_record(meta, chamber, T_rows[r], W, base, r, cand, stride)
+    iv, n, _ = plan_record(meta, chamber, T_rows[r], W, base, r, cand, stride, fs)
     ivs.append(iv)
     base += int(T_rows[r])
     cand += n

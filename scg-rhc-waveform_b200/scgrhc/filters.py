@@ -74,3 +74,69 @@ def sosfiltfilt(arena, record_rows, sos, columns):
                                         zi.ctypes.data_as(C.POINTER(C.c_double)), sos.shape[0], edge,
                                         ops._stream(dev.index)))
   return out
+
+
+def _output_len(len_h, in_len, up, down):
+  """scipy.signal._upfirdn_apply._output_len."""
+  in_len_copy = in_len + (len_h + (-len_h % up)) // up - 1
+  nt = in_len_copy * up
+  return nt // down + (1 if nt % down else 0)
+
+
+def resample_design(n_in, up, down, window=('kaiser', 5.0)):
+  """Everything scipy.signal.resample_poly derives before calling upfirdn, for an input of n_in samples:
+  (up, down) reduced, n_out, transposed-flipped taps, taps per phase, n_pre_remove (needs scipy for firwin)."""
+  import math
+  from scipy.signal import firwin
+  g = math.gcd(int(up), int(down))
+  up, down = int(up) // g, int(down) // g
+  n_out = n_in * up
+  n_out = n_out // down + bool(n_out % down)
+  max_rate = max(up, down)
+  half_len = 10 * max_rate
+  h = firwin(2 * half_len + 1, 1.0 / max_rate, window=window).astype(np.float64)
+  h *= up
+  n_pre_pad = down - half_len % down
+  n_post_pad = 0
+  n_pre_remove = (half_len + n_pre_pad) // down
+  while _output_len(len(h) + n_pre_pad + n_post_pad, n_in, up, down) < n_out + n_pre_remove:
+    n_post_pad += 1
+  h = np.concatenate([np.zeros(n_pre_pad), h, np.zeros(n_post_pad)])
+  padlen = len(h) + (-len(h) % up)                       # _upfirdn.py:_pad_h
+  h_full = np.zeros(padlen)
+  h_full[:len(h)] = h
+  taps = np.ascontiguousarray(h_full.reshape(-1, up).T[:, ::-1]).ravel()
+  return up, down, n_out, taps, padlen // up, n_pre_remove, n_post_pad
+
+
+def resample_poly(arena, record_rows, up, down, window=('kaiser', 5.0)):
+  """Resample every record of ``arena`` ((rows, ncols) fp64 CUDA) by up/down; returns (new_arena, new_record_rows).
+  ``up == down`` after reduction returns a copy, as scipy does."""
+  import math
+  if not arena.is_cuda:
+    raise RuntimeError('resample_poly needs a CUDA arena (no CPU fallback)')
+  rows = [int(r) for r in record_rows]
+  g = math.gcd(int(up), int(down))
+  if up // g == down // g == 1:
+    return arena.clone(), rows
+  lengths = sorted(set(rows))
+  designs = dict(zip(lengths, [resample_design(n, up, down, window) for n in lengths]))
+  first = designs[lengths[0]]
+  if any(d[6] != first[6] for d in designs.values()):
+    # the FIR is post-padded only when the output would otherwise come out short; scipy notes "we should rarely need
+    # to do this given our filter lengths" and it has not been observed with the kaiser design used here
+    raise NotImplementedError('records whose lengths need different FIR post-padding in one cohort')
+  out_rows = [designs[n][2] for n in rows]
+  dev = arena.device
+  in0 = torch.from_numpy(np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)).to(dev)
+  out0_h = np.concatenate([[0], np.cumsum(out_rows)]).astype(np.int64)
+  out0 = torch.from_numpy(out0_h).to(dev)
+  out = torch.empty((int(out0_h[-1]), arena.shape[1]), dtype=torch.float64, device=dev)
+  taps = torch.from_numpy(first[3]).to(dev)
+  c = ops.ctx(dev.index)
+  for lo in range(0, len(rows), 65535):
+    n = min(65535, len(rows) - lo)
+    N.check(c, N.lib().scgrhc_resample_poly(c, ops._ptr(arena), ops._ptr(out), ops._ptr(taps), ops._ptr(in0[lo:]), ops._ptr(out0[lo:]),
+                                            n, max(out_rows[lo:lo + n]), arena.shape[1], first[0], first[1], first[4], first[5],
+                                            ops._stream(dev.index)))
+  return out, out_rows

@@ -46,3 +46,55 @@ def test_sosfiltfilt_rejects_short_records_like_scipy():
   from scgrhc._native import ScgrhcError
   with pytest.raises(ScgrhcError, match='greater than padlen'):
     filters.sosfiltfilt(arena, [20], sos, [0])
+
+
+@pytest.mark.parametrize('up,down', [(1, 2), (250, 500), (2, 5), (3, 2), (125, 500), (500, 500)])
+def test_resample_poly_matches_scipy(up, down):
+  sig = synth_ref.DEFAULT_SIG_NAMES
+  rows = [5000, 1234, 777]
+  recs = [synth_ref.gen_record(H.SEED, 70 + r, T, kinds=synth_ref.kinds_for(sig)) for r, T in enumerate(rows)]
+  arena = torch.from_numpy(np.concatenate(recs)).to(DEV)
+  out, out_rows = filters.resample_poly(arena, rows, up, down)
+  out = out.cpu().numpy()
+  at = 0
+  for p, n in zip(recs, out_rows):
+    want = signal.resample_poly(p, up, down, axis=0)
+    assert want.shape == (n, 4)
+    got = out[at:at + n]
+    assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
+    assert got.tobytes() == want.tobytes()                # in fact bit-identical: same taps, same summation order
+    at += n
+  assert at == out.shape[0]
+
+
+def test_filter_resample_window_pipeline_against_scipy_plus_oracle():
+  """All extensions chained the way recordutil does when the optional params keys are present: band-pass the SCG
+  columns, resample every column 500 -> 250 Hz, plan the chamber intervals at the new rate, window + normalise."""
+  import scgrhc
+  from oracle import scgrhc_oracle as orc
+  sig = synth_ref.DEFAULT_SIG_NAMES
+  T = 60000
+  p = synth_ref.gen_record(H.SEED, 90, T, kinds=synth_ref.kinds_for(sig))
+  meta = synth_ref.record_meta(120, events={'RA_1': 0, 'PA_1': 20.3, 'RV_1': 95})
+  sos = signal.butter(4, (1.0, 40.0), btype='bandpass', fs=500, output='sos')
+  arena = torch.from_numpy(p).to(DEV)
+  f = filters.sosfiltfilt(arena, [T], sos, [0, 1, 2])
+  r, rows = filters.resample_poly(f, [T], 250, 500)
+  fs, W = 250, int(1.5 * 250)
+  plan = scgrhc.plan_cohort([meta], 'PA', rows, W, fs=fs)
+  st = scgrhc.prepare_windows(r, plan, [0, 1, 2], 3, -50.0)
+  # the same chain with scipy + the oracle's per-window arithmetic
+  q = p.copy()
+  q[:, :3] = signal.sosfiltfilt(sos, p[:, :3], axis=0)
+  q = signal.resample_poly(q, 250, 500, axis=0)
+  a, b = int(20.3 * fs), int(95 * fs)
+  n = (b - a) // W
+  starts = a + np.arange(n) * W
+  idx = starts[:, None] + np.arange(W)[None, :]
+  rhc = q[:, 3][idx]
+  keep = ~((orc.flat_count(rhc) >= 2) | (orc.r_squared(rhc) > 0.8) | orc.below_floor(rhc, -50.0))
+  assert plan.n_cand == n and st.keep.cpu().numpy().astype(bool).tolist() == keep.tolist() and 0 < keep.sum() < n
+  scg = q[:, :3][idx][keep]
+  mm = scg.min(axis=(1, 2)), scg.max(axis=(1, 2))
+  want = ((scg - mm[0][:, None, None]) / (mm[1] - mm[0] + 0.0001)[:, None, None]).transpose(0, 2, 1).astype(np.float32)
+  assert st.materialise()[0].cpu().numpy().tobytes() == np.ascontiguousarray(want).tobytes()
