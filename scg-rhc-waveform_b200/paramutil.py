@@ -7,7 +7,8 @@ Same class, same attribute names, same ``Params(path)`` call.  Differences, all 
   * optional keys read with ``.data.get`` only (absent from all 37 shipped params.json, so shipped
     behaviour is unchanged): ``split_seed`` (reproducible train/valid/test split), ``segment_stride``
     (seconds between window starts; default = ``segment_size``, i.e. the reference's non-overlapping windows), ``noise_std`` / ``noise_seed`` (train-time
-    noise injection on SCG batches).
+    noise injection on SCG batches), ``bandpass`` / ``bandpass_order`` / ``bandpass_sos`` (zero-phase IIR filtering of the
+    SCG channels), ``resample_rate`` (model sampling rate).  With none of them present the path is the reference's.
 """
 import json
 import os
@@ -55,6 +56,10 @@ class Params:
     self.segment_stride = self.data.get('segment_stride')
     self.noise_std = self.data.get('noise_std')      # train-time Gaussian noise on SCG batches (extension, default off)
     self.noise_seed = self.data.get('noise_seed')
+    self.bandpass = self.data.get('bandpass')              # [low_hz, high_hz]: zero-phase Butterworth on the SCG channels
+    self.bandpass_order = self.data.get('bandpass_order')
+    self.bandpass_sos = self.data.get('bandpass_sos')      # or explicit second-order sections
+    self.resample_rate = self.data.get('resample_rate')    # model sampling rate in Hz (native: 500)
 
   def _get(self, key):
     if key in self.data or self.strict or key not in LEGACY_DEFAULTS:

@@ -41,7 +41,7 @@ from timelog import timelog
 from waveform_noise import has_noise  # noqa: F401  (re-exported like the reference, recordutil.py:17)
 
 from scgrhc import _native as N
-from scgrhc import engine, ops
+from scgrhc import engine, filters, ops
 
 SAMPLE_FREQ = 500
 
@@ -407,11 +407,14 @@ def prepare_cohort(params, record_names=None, chunk_records=32):
     else:
       host[at:at + n] = torch.from_numpy(np.ascontiguousarray(record.p_signal[:, sel], dtype=np.float64))
     at += n
-  if not params.use_global_min_max:
+  sos = _bandpass_sos(params)
+  rate = getattr(params, 'resample_rate', None)
+  extensions = sos is not None or (rate and int(rate) != SAMPLE_FREQ)
+  if not params.use_global_min_max and not extensions:
     ing = engine.HostIngest(plan, rows, C + 1, dev, chunk_records=chunk_records, digital_nsig=(C + 1) if digital else None)
     store = ing.run(host, list(range(C)), C, params.min_RHC, decode=(list(range(C + 1)), gains, bases) if digital else None)
     return store, names
-  # dataset-global pairs need the whole cohort resident for the second pass
+  # dataset-global pairs (second pass) and the optional filter / resample stages need the whole cohort resident
   if digital:
     d_dev = host.to(dev, non_blocking=True)
     arena = torch.empty((total, C + 1), dtype=torch.float64, device=dev)
@@ -421,8 +424,28 @@ def prepare_cohort(params, record_names=None, chunk_records=32):
       at += n
   else:
     arena = host.to(dev, non_blocking=True)
-  store = engine.prepare_windows(arena, plan, list(range(C)), C, params.min_RHC, use_global_min_max=True)
+  if sos is not None:                      # extension: zero-phase band-pass of the SCG channels (scipy sosfiltfilt semantics)
+    arena = filters.sosfiltfilt(arena, rows, sos, list(range(C)))
+  if rate and int(rate) != SAMPLE_FREQ:    # extension: every channel to the model rate (scipy resample_poly semantics)
+    arena, rows = filters.resample_poly(arena, rows, int(rate), SAMPLE_FREQ)
+    W = int(params.segment_size * int(rate))
+    plan = engine.plan_cohort(metas, params.chamber, rows, W, names, stride=int(stride_s * int(rate)) if stride_s else 0,
+                              fs=float(int(rate)))
+  store = engine.prepare_windows(arena, plan, list(range(C)), C, params.min_RHC,
+                                 use_global_min_max=bool(params.use_global_min_max))
   return store, names
+
+
+def _bandpass_sos(params):
+  """Optional params keys (absent from all shipped params.json): ``bandpass_sos`` = explicit second-order sections, or
+  ``bandpass`` = [low_hz, high_hz] (+ ``bandpass_order``, default 4) designed as a Butterworth band-pass at 500 Hz."""
+  sos = getattr(params, 'bandpass_sos', None)
+  if sos is not None:
+    return np.asarray(sos, dtype=np.float64)
+  band = getattr(params, 'bandpass', None)
+  if band:
+    return filters.butter_sos(float(band[0]), float(band[1]), SAMPLE_FREQ, int(getattr(params, 'bandpass_order', None) or 4))
+  return None
 
 
 def save_dataloaders(params):

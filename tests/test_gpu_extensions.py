@@ -98,3 +98,35 @@ def test_filter_resample_window_pipeline_against_scipy_plus_oracle():
   mm = scg.min(axis=(1, 2)), scg.max(axis=(1, 2))
   want = ((scg - mm[0][:, None, None]) / (mm[1] - mm[0] + 0.0001)[:, None, None]).transpose(0, 2, 1).astype(np.float32)
   assert st.materialise()[0].cpu().numpy().tobytes() == np.ascontiguousarray(want).tobytes()
+
+
+def test_recordutil_optional_keys_drive_the_extension_stages(tmp_path, monkeypatch):
+  """params.json with bandpass / resample_rate / segment_stride keys goes through filter -> resample -> windows."""
+  import json
+  import types
+  import recordutil
+  import scgrhc
+  from scgrhc import wfdbio
+  root = tmp_path / 'data'; root.mkdir()
+  monkeypatch.setattr(recordutil, 'PROCESSED_DATA_PATH', str(root))
+  monkeypatch.setattr(recordutil, 'wfdb', wfdbio)
+  sig = synth_ref.DEFAULT_SIG_NAMES
+  meta = synth_ref.record_meta(80, events={'PA_1': 2.0, 'RV_1': 70})
+  p = synth_ref.gen_record(H.SEED, 95, 40000, kinds=synth_ref.kinds_for(sig))
+  wfdbio.wrsamp('rec0', 500, ['g', 'g', 'g', 'mmHg'], sig, p, write_dir=str(root))
+  (root / 'rec0.json').write_text(json.dumps(meta))
+  base = dict(in_channels=sig[:3], chamber='PA', segment_size=1.5, min_RHC=-50, use_global_min_max=False)
+  plain, _ = recordutil.prepare_cohort(types.SimpleNamespace(**base))
+  ext, _ = recordutil.prepare_cohort(types.SimpleNamespace(bandpass=[1.0, 40.0], resample_rate=250, segment_stride=0.75, **base))
+  q = wfdbio.rdrecord(str(root / 'rec0')).p_signal
+  sos = signal.butter(4, (1.0, 40.0), btype='bandpass', fs=500, output='sos')
+  q[:, :3] = signal.sosfiltfilt(sos, q[:, :3], axis=0)
+  q = signal.resample_poly(q, 250, 500, axis=0)
+  a, b, W, S = int(2.0 * 250), int(70 * 250), 375, 187
+  n = (b - a - W) // S + 1
+  assert ext.n_cand == n and plain.n_cand == (35000 - 1000) // 750
+  assert ext.start_idx.cpu().tolist() == (np.nonzero(ext.keep.cpu().numpy())[0] * S).tolist()
+  k0 = int(ext.kept_idx[0])
+  win = q[a + k0 * S: a + k0 * S + W, :3]
+  want = ((win - win.min()) / (win.max() - win.min() + 0.0001)).T.astype(np.float32)
+  assert ext.materialise()[0][0].cpu().numpy().tobytes() == np.ascontiguousarray(want).tobytes()
