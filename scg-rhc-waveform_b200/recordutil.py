@@ -212,6 +212,8 @@ class WindowLoader:
   ``.batch_size``) with device-side batch assembly: a shuffled index permutation + one gather kernel per
   batch instead of per-item collation (recordutil.py:198-200: shuffle=True, drop_last=False)."""
 
+  noise_std, noise_seed, _batches_served = 0.0, 0, 0      # defaults for loaders pickled before the noise extension existed
+
   def __init__(self, dataset, batch_size=1, shuffle=False, generator=None, noise_std=0.0, noise_seed=0):
     self.dataset, self.batch_size, self.shuffle, self.generator = dataset, int(batch_size), shuffle, generator
     # extension (absent from the reference, default off): Gaussian noise on the SCG inputs of every batch, drawn from a
