@@ -382,11 +382,20 @@ extern "C" int scgrhc_sosfiltfilt(scgrhc_ctx* ctx, const double* x, double* y, d
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  const int cpw = 32 / nsec, groups = (ncf + cpw - 1) / cpw;
+  // The recurrence is latency bound, so prefer many warps: as few columns per warp as still fills the GPU
+  int cpw = 32 / nsec;
+  while (cpw > 1 && (long long)n_rec * ((ncf + cpw - 2) / (cpw - 1)) <= (long long)ctx->sm_count * 48) --cpw;
+  P.cpw = cpw;
+  for (int r = 0; r < n_rec; ++r)
+    if (row0_host[r + 1] - row0_host[r] + 2LL * edge >= INT32_MAX) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "sosfiltfilt: record too long");
+  const int groups = (ncf + cpw - 1) / cpw;
   const long long warps = (long long)n_rec * groups;
   const unsigned grid = (unsigned)((warps + 3) / 4);
-  sosfilt_pass_kernel<0><<<grid, 128, 0, st>>>(P);
-  sosfilt_pass_kernel<1><<<grid, 128, 0, st>>>(P);
+  const size_t smem = (size_t)4 * kRing * kTileRows * cpw * sizeof(double);   // 4 warps per CTA
+  CUDA_TRY(ctx, cudaFuncSetAttribute(sosfilt_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(sosfilt_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sosfilt_pass_kernel<0><<<grid, 128, smem, st>>>(P);
+  sosfilt_pass_kernel<1><<<grid, 128, smem, st>>>(P);
   CUDA_TRY(ctx, cudaGetLastError());
   return SCGRHC_OK;
 }
@@ -398,19 +407,33 @@ extern "C" int scgrhc_resample_poly(scgrhc_ctx* ctx, const double* x, double* y,
   if (n_rec < 0 || ncols < 1 || up < 1 || down < 1 || per_phase < 1 || n_pre_remove < 0 || max_out_rows < 0 ||
       (n_rec && (!x || !y || !taps_dev || !in0_dev || !out0_dev)))
     return fail(ctx, SCGRHC_ERR_BAD_ARG, "resample_poly: bad arguments");
-  const size_t smem = (size_t)up * per_phase * sizeof(double);
-  if (smem > 200 * 1024) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "resample_poly: %zu bytes of taps do not fit in shared memory", smem);
+  const int tile_rows = (int)(((long long)(kResTile - 1) * down) / up) + 2 + per_phase;
+  const size_t smem = ((((size_t)up * per_phase + 1) & ~size_t(1)) + (size_t)(tile_rows | 1) * ncols) * sizeof(double);
+  if (smem > 200 * 1024) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "resample_poly: %zu bytes of taps + staged rows do not fit in shared memory", smem);
   if (n_rec == 0 || max_out_rows == 0) return SCGRHC_OK;
   if (n_rec > 65535) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "resample_poly: at most 65535 records per call");
   ResampleParams P;
   P.x = x; P.y = y; P.taps = taps_dev; P.in0 = reinterpret_cast<const long long*>(in0_dev);
   P.out0 = reinterpret_cast<const long long*>(out0_dev);
   P.n_rec = n_rec; P.ncols = ncols; P.up = up; P.down = down; P.per_phase = per_phase; P.n_pre_remove = n_pre_remove;
+  P.tile_rows = tile_rows;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  CUDA_TRY(ctx, cudaFuncSetAttribute(resample_poly_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)std::min<long long>((max_out_rows + 255) / 256, 1024), (unsigned)n_rec);
-  resample_poly_kernel<<<grid, 256, smem, st>>>(P);
+  dim3 grid((unsigned)std::min<long long>((max_out_rows + kResTile - 1) / kResTile, 1024), (unsigned)n_rec);
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kResTile, smem, st>>>(P);
+    return cudaSuccess;
+  };
+  switch (ncols) {
+    case 1: CUDA_TRY(ctx, launch(resample_poly_kernel<1>)); break;
+    case 2: CUDA_TRY(ctx, launch(resample_poly_kernel<2>)); break;
+    case 3: CUDA_TRY(ctx, launch(resample_poly_kernel<3>)); break;
+    case 4: CUDA_TRY(ctx, launch(resample_poly_kernel<4>)); break;
+    case 5: CUDA_TRY(ctx, launch(resample_poly_kernel<5>)); break;
+    default: CUDA_TRY(ctx, launch(resample_poly_kernel<0>)); break;
+  }
   CUDA_TRY(ctx, cudaGetLastError());
   return SCGRHC_OK;
 }

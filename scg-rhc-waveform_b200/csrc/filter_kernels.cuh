@@ -16,7 +16,8 @@ namespace scgrhc {
 
 constexpr int kMaxSections = 8;
 constexpr int kMaxFilterCols = 8;
-constexpr int kPrefetch = 8;
+constexpr int kTileRows = 32;   // samples per staged tile
+constexpr int kRing = 8;        // tiles in flight per warp (256 samples ahead)
 
 struct SosParams {
   const double* x;        // (rows, ncols) arena
@@ -24,6 +25,7 @@ struct SosParams {
   double* tmp;            // forward-pass output: per record (T + 2 edge) rows x ncf columns
   const long long* row0;  // device, n_rec + 1 record boundaries (rows)
   int n_rec, ncols, nsec, edge, ncf;
+  int cpw;                // filtered columns per warp (1 .. 32 / nsec): fewer columns per warp = more warps in flight
   int fcols[kMaxFilterCols];
   double sos[kMaxSections][6];
   double zi[kMaxSections][2];
@@ -32,7 +34,7 @@ struct SosParams {
 template <int PASS>  // 0: forward over the odd extension, x -> tmp; 1: backward over reversed tmp -> y (trimmed)
 __global__ void __launch_bounds__(128) sosfilt_pass_kernel(const __grid_constant__ SosParams P) {
   const int lane = threadIdx.x & 31;
-  const int cpw = 32 / P.nsec;                              // columns per warp
+  const int cpw = P.cpw;
   const int groups = (P.ncf + cpw - 1) / cpw;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= (long long)P.n_rec * groups) return;
@@ -41,61 +43,83 @@ __global__ void __launch_bounds__(128) sosfilt_pass_kernel(const __grid_constant
   const int j = grp * cpw + ci;                             // filtered-column slot
   const bool live = ci < cpw && j < P.ncf;
   const int col = live ? P.fcols[j] : 0;
-  const long long r0 = P.row0[rec], T = P.row0[rec + 1] - r0;
-  const long long Lext = T + 2LL * P.edge;
+  const long long r0 = P.row0[rec];
+  const int T = (int)(P.row0[rec + 1] - r0);                // host guarantees T + 2 edge < 2^31
+  const int Lext = T + 2 * P.edge;
   const long long tbase = (r0 + 2LL * P.edge * rec) * P.ncf;   // this record's rows in tmp
   const double b0 = P.sos[s][0], b1 = P.sos[s][1], b2 = P.sos[s][2], a1 = P.sos[s][4], a2 = P.sos[s][5];
 
-  auto X = [&](long long t) { return P.x[(r0 + t) * P.ncols + col]; };
-  auto input = [&](long long e) -> double {                  // sample e of this pass's input sequence
+  auto input = [&](int e, int slot, int column) -> double {   // sample e of this pass's input sequence
     if (PASS == 0) {
-      if (e < P.edge) return __dsub_rn(2.0 * X(0), X(P.edge - e));                      // 2*x[0] - x[edge:0:-1]
-      if (e < P.edge + T) return X(e - P.edge);
-      return __dsub_rn(2.0 * X(T - 1), X(T - 2 - (e - P.edge - T)));                    // 2*x[-1] - x[-2:-(edge+2):-1]
+      const double* xc = P.x + r0 * P.ncols + column;
+      if (e < P.edge) return __dsub_rn(2.0 * xc[0], xc[(long long)(P.edge - e) * P.ncols]);          // 2*x[0] - x[edge:0:-1]
+      if (e < P.edge + T) return xc[(long long)(e - P.edge) * P.ncols];
+      return __dsub_rn(2.0 * xc[(long long)(T - 1) * P.ncols], xc[(long long)(T - 2 - (e - P.edge - T)) * P.ncols]);
     }
-    return P.tmp[tbase + (Lext - 1 - e) * P.ncf + j];
+    return P.tmp[tbase + (long long)(Lext - 1 - e) * P.ncf + slot];
   };
 
   double z0 = 0.0, z1 = 0.0;
   if (live) {
-    const double first = input(0);                           // zi * x_0 (forward) / zi * y_0 (backward)
+    const double first = input(0, j, col);                   // zi * x_0 (forward) / zi * y_0 (backward)
     z0 = __dmul_rn(P.zi[s][0], first);
     z1 = __dmul_rn(P.zi[s][1], first);
   }
-  double cur[kPrefetch], nxt[kPrefetch];
-  const bool feeder = live && s == 0;
+  // Input staging: the whole warp loads tiles of kTileRows samples x (this warp's columns) into a shared-memory ring,
+  // kRing tiles ahead of the sample being filtered, so the serial recurrence never waits on a global load.
+  extern __shared__ double s_ring[];
+  const int wcols = min(cpw, P.ncf - grp * cpw);            // filtered columns handled by this warp
+  double* ring = s_ring + (size_t)(threadIdx.x >> 5) * kRing * kTileRows * cpw;
+  auto load_tile = [&](int tile) {
+    double* dst = ring + (size_t)(tile % kRing) * kTileRows * cpw;
+    double v[4];
 #pragma unroll
-  for (int u = 0; u < kPrefetch; ++u) cur[u] = (feeder && u < Lext) ? input(u) : 0.0;
-  double x_new = 0.0;
-  const long long iters = Lext + P.nsec - 1;
-  for (long long base = 0; base < iters; base += kPrefetch) {
-#pragma unroll
-    for (int u = 0; u < kPrefetch; ++u) {
-      const long long e = base + kPrefetch + u;
-      nxt[u] = (feeder && e < Lext) ? input(e) : 0.0;
+    for (int i = 0; i < 4; ++i) {                            // issue the loads first, then the stores
+      const int q = lane + 32 * i;
+      const int row = q / wcols, jj = q - row * wcols, e = tile * kTileRows + row;
+      v[i] = (q < kTileRows * wcols && e < Lext) ? input(e, grp * cpw + jj, P.fcols[grp * cpw + jj]) : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < kPrefetch; ++u) {
-      const long long it = base + u;
+    for (int i = 0; i < 4; ++i) {
+      const int q = lane + 32 * i;
+      const int row = q / wcols, jj = q - row * wcols;
+      if (q < kTileRows * wcols) dst[row * cpw + jj] = v[i];
+    }
+    for (int q = lane + 128; q < kTileRows * wcols; q += 32) {   // more than 4 columns per warp: plain loop
+      const int row = q / wcols, jj = q - row * wcols, e = tile * kTileRows + row;
+      dst[row * cpw + jj] = e < Lext ? input(e, grp * cpw + jj, P.fcols[grp * cpw + jj]) : 0.0;
+    }
+  };
+  const int ntiles = (Lext + kTileRows - 1) / kTileRows;
+  for (int tl = 0; tl < kRing - 1 && tl < ntiles; ++tl) load_tile(tl);
+  __syncwarp();
+  double x_new = 0.0;
+  const int iters = Lext + P.nsec - 1;
+  const bool last = live && s == P.nsec - 1;
+  // output cursor of the last section: forward -> tmp row n; backward -> y row Lext-1-edge-n (reverse + trim)
+  double* outp = PASS == 0 ? P.tmp + tbase + j - (long long)s * P.ncf
+                           : P.y + (r0 + (long long)(Lext - 1 - P.edge + s)) * P.ncols + col;
+  const long long ostep = PASS == 0 ? (long long)P.ncf : -(long long)P.ncols;
+  for (int tile = 0; tile * kTileRows < iters; ++tile) {
+    if (tile + kRing - 1 < ntiles) load_tile(tile + kRing - 1);   // slot (tile-1) % kRing: its reads finished last round
+    const double* src = ring + (size_t)(tile % kRing) * kTileRows * cpw + (live ? ci : 0);   // idle lanes stay in bounds
+#pragma unroll 8
+    for (int u = 0; u < kTileRows; ++u) {
+      const int n = tile * kTileRows + u - s;
       const double from_prev = __shfl_up_sync(kFull, x_new, 1);
-      const long long n = it - s;
-      if (live && n >= 0 && n < Lext) {
-        const double x_cur = s == 0 ? cur[u] : from_prev;
+      const double x_cur = s == 0 ? src[u * cpw] : from_prev;
+      if (live && (unsigned)n < (unsigned)Lext) {
         x_new = __dadd_rn(__dmul_rn(b0, x_cur), z0);
         z0 = __dadd_rn(__dsub_rn(__dmul_rn(b1, x_cur), __dmul_rn(a1, x_new)), z1);
         z1 = __dsub_rn(__dmul_rn(b2, x_cur), __dmul_rn(a2, x_new));
-        if (s == P.nsec - 1) {
-          if (PASS == 0) {
-            P.tmp[tbase + n * P.ncf + j] = x_new;
-          } else {
-            const long long t = Lext - 1 - P.edge - n;       // reverse again and trim the padding
-            if (t >= 0 && t < T) P.y[(r0 + t) * P.ncols + col] = x_new;
-          }
+        if (last) {
+          if (PASS == 0) *outp = x_new;
+          else if (n >= P.edge && n < P.edge + T) *outp = x_new;
         }
       }
+      outp += ostep;
     }
-#pragma unroll
-    for (int u = 0; u < kPrefetch; ++u) cur[u] = nxt[u];
+    __syncwarp();                                            // the tile just consumed may be overwritten next round
   }
 }
 
@@ -117,28 +141,71 @@ struct ResampleParams {
   const long long* in0;    // device, n_rec + 1
   const long long* out0;   // device, n_rec + 1
   int n_rec, ncols, up, down, per_phase, n_pre_remove;
+  int tile_rows;           // input rows staged per CTA: (255 * down) / up + 1 + per_phase
 };
 
-__global__ void __launch_bounds__(256) resample_poly_kernel(const __grid_constant__ ResampleParams P) {
-  extern __shared__ double s_taps[];
+constexpr int kResTile = 256;   // output rows per CTA tile (one per thread)
+
+// NC = compile-time column count (0: runtime, processed in predicated chunks of 8)
+template <int NC>
+__global__ void __launch_bounds__(kResTile) resample_poly_kernel(const __grid_constant__ ResampleParams P) {
+  extern __shared__ double s_res[];
+  double* s_taps = s_res;
   const int ntaps = P.up * P.per_phase;
+  const int ncols = NC ? NC : P.ncols;
+  const int pitch = P.tile_rows | 1;                        // column-major staging, odd pitch
+  double* s_x = s_res + ((ntaps + 1) & ~1);                 // s_x[c * pitch + r]
   for (int i = threadIdx.x; i < ntaps; i += blockDim.x) s_taps[i] = P.taps[i];
-  __syncthreads();
   const int rec = blockIdx.y;
   const long long i0 = P.in0[rec], len_x = P.in0[rec + 1] - i0;
   const long long o0 = P.out0[rec], n_out = P.out0[rec + 1] - o0;
-  for (long long mo = (long long)blockIdx.x * blockDim.x + threadIdx.x; mo < n_out; mo += (long long)gridDim.x * blockDim.x) {
-    const long long m = mo + P.n_pre_remove;
-    const long long x_idx = (m * P.down) / P.up;
-    const int t = (int)((m * P.down) % P.up);
-    const double* h = s_taps + t * P.per_phase;
-    for (int c = 0; c < P.ncols; ++c) {
-      double acc = 0.0;
-      for (int k = 0; k < P.per_phase; ++k) {
-        const long long xi = x_idx - P.per_phase + 1 + k;
-        if (xi >= 0 && xi < len_x) acc = __dadd_rn(acc, __dmul_rn(P.x[(i0 + xi) * P.ncols + c], h[k]));
+  for (long long tile0 = (long long)blockIdx.x * kResTile; tile0 < n_out; tile0 += (long long)gridDim.x * kResTile) {
+    // input rows this tile touches: [first, first + tile_rows), zero outside the record (upfirdn's zero padding).
+    // Staged column-major so that neighbouring threads (neighbouring output rows) read words `down` apart instead of
+    // `down * ncols` apart: at most a `down`-way bank conflict instead of 16-way.
+    const long long first = ((tile0 + P.n_pre_remove) * P.down) / P.up - P.per_phase + 1;
+    __syncthreads();
+    for (int q = threadIdx.x; q < P.tile_rows * ncols; q += blockDim.x) {
+      const int r = q / ncols, c = q - r * ncols;
+      const long long xi = first + r;
+      s_x[c * pitch + r] = (xi >= 0 && xi < len_x) ? P.x[(i0 + xi) * ncols + c] : 0.0;
+    }
+    __syncthreads();
+    const long long mo = tile0 + threadIdx.x;
+    if (mo < n_out) {
+      const long long m = mo + P.n_pre_remove;
+      const int base = (int)((m * P.down) / P.up - P.per_phase + 1 - first);
+      const double* h = s_taps + (int)((m * P.down) % P.up) * P.per_phase;
+      // each column is summed oldest-sample-first with separately rounded multiply and add, as scipy's compiled loop
+      // does (zero-padded rows add an exact +0); columns are independent chains and advance together
+      if constexpr (NC > 0) {
+        double acc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+        const double* col0 = s_x + base;
+#pragma unroll 4
+        for (int k = 0; k < P.per_phase; ++k) {
+          const double hk = h[k];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) acc[c] = __dadd_rn(acc[c], __dmul_rn(col0[c * pitch + k], hk));
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) P.y[(o0 + mo) * NC + c] = acc[c];
+      } else {
+        for (int c0 = 0; c0 < ncols; c0 += 8) {
+          double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          const int nc = min(8, ncols - c0);
+          for (int k = 0; k < P.per_phase; ++k) {
+            const double hk = h[k];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c < nc) acc[c] = __dadd_rn(acc[c], __dmul_rn(s_x[(c0 + c) * pitch + base + k], hk));
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c < nc) P.y[(o0 + mo) * ncols + c0 + c] = acc[c];
+        }
       }
-      P.y[(o0 + mo) * P.ncols + c] = acc;
     }
   }
 }
