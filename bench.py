@@ -194,31 +194,69 @@ def cpu_fast(n_rec, threads):
   return int(keep.sum()), len(rs), dt
 
 
+UNIT_WINDOWS = 50                      # reference-arm work unit: 50 candidate windows = 75 s of one record
+UNIT_ROWS = UNIT_WINDOWS * W
+UNITS_PER_RECORD = T_ROWS // UNIT_ROWS
+
+
+def _unit_meta():
+  return {'MacStTime': '1/1/2020 10:00:00', 'MacEndTime': '1/1/2020 10:01:15', 'ChamEvents_in_s': dict(EVENTS)}
+
+
+def _cpu_run_unit(unit):
+  from oracle import ref_port
+  rec, u = divmod(unit, UNITS_PER_RECORD)
+  p = _worker_cache[rec][u * UNIT_ROWS:(u + 1) * UNIT_ROWS]
+  out, n_cand = ref_port.prepare_record(p, SIG, _unit_meta(), IN_CHANNELS, 'PA', 1.5, MIN_RHC)
+  return len(out), n_cand
+
+
 def run_reference(args):
   """Reference arm: the reference's CPU implementation of the path (its port, oracle/ref_port.py —
-  /root/reference is Python and cannot travel to the GPU box) on all host cores, sharded by record."""
+  /root/reference is Python and cannot travel to the GPU box) on all host cores, sharded by record.  Each step is a
+  bounded sample of the workload (whole 50-window pieces of records), sized after one calibration pass so that the
+  K timed steps take about a minute whatever K is."""
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
   import multiprocessing as mp
   cores = os.cpu_count() or 1
-  per_step = max(cores, 8) * 2                       # records per step: ~1-2 s of wall clock per step
   ctx = mp.get_context('fork')
-  recs = list(range(per_step))
-  with ctx.Pool(min(cores, 32), initializer=_cpu_worker_init) as pool:      # generate the inputs in parallel ...
-    for rec, arr in pool.imap_unordered(_cpu_gen_return, recs, chunksize=1):
-      _worker_cache[rec] = arr
-  with ctx.Pool(cores, initializer=_cpu_worker_init) as pool:               # ... and fork the timed workers after,
-    for _ in range(args.warmup):                                            # so every worker sees every record (copy-on-write)
-      pool.map(_cpu_run, recs, chunksize=1)
+
+  def generate(recs):
+    with ctx.Pool(min(cores, 32), initializer=_cpu_worker_init) as pool:
+      for rec, arr in pool.imap_unordered(_cpu_gen_return, recs, chunksize=1):
+        _worker_cache[rec] = arr
+
+  n_rec = max(2, -(-cores // UNITS_PER_RECORD))
+  generate(range(n_rec))
+  with ctx.Pool(cores, initializer=_cpu_worker_init) as pool:          # calibration: one unit per core, second (warm) pass
+    pool.map(_cpu_run_unit, list(range(cores)), chunksize=1)
+    t0 = time.perf_counter()
+    pool.map(_cpu_run_unit, list(range(cores)), chunksize=1)
+    t_unit = time.perf_counter() - t0
+  # steps of >= 1 s keep the pool efficient (the arm must not be handicapped); the whole run is capped near 4 minutes
+  k = max(args.steps, 1)
+  target_step = min(max(1.0, 60.0 / k), 240.0 / k)
+  per_core = min(64, max(1, int(round(target_step / max(t_unit, 1e-3)))))
+  units_per_step = cores * per_core
+  need = -(-units_per_step // UNITS_PER_RECORD)
+  if need > n_rec:
+    generate(range(n_rec, need))
+    n_rec = need
+  units = list(range(units_per_step))
+  with ctx.Pool(cores, initializer=_cpu_worker_init) as pool:          # forked after generation: workers share the records
+    for _ in range(args.warmup):
+      pool.map(_cpu_run_unit, units, chunksize=1)
     t0 = time.perf_counter()
     kept = cand = 0
     for _ in range(args.steps):
-      for k, c in pool.map(_cpu_run, recs, chunksize=1):
+      for k, c in pool.map(_cpu_run_unit, units, chunksize=1):
         kept += k; cand += c
     dt = time.perf_counter() - t0
   value = kept / dt
-  sample = '%d records/step (%d candidate windows) of the %d-record workload, %d steps' % (per_step, per_step * 400, args.records, args.steps)
+  sample = ('%d candidate windows/step (%d pieces of %d windows from %d of the %d records), %d steps'
+            % (units_per_step * UNIT_WINDOWS, units_per_step, UNIT_WINDOWS, n_rec, args.records, args.steps))
   line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
           'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
           'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
