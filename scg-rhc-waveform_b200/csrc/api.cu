@@ -400,6 +400,67 @@ extern "C" int scgrhc_sosfiltfilt(scgrhc_ctx* ctx, const double* x, double* y, d
   return SCGRHC_OK;
 }
 
+template <int NSEC, int NCF>
+static int sos_scan_launch(scgrhc_ctx* ctx, const SosScanParams& P, long long total_chunks, cudaStream_t st) {
+  const unsigned cgrid = (unsigned)((total_chunks + 127) / 128), sgrid = (unsigned)((P.n_rec * P.ncf + 63) / 64);
+  sosfilt_chunk_kernel<0, 0, NSEC, NCF><<<cgrid, 128, 0, st>>>(P, total_chunks);
+  sosfilt_scan_kernel<0, NSEC><<<sgrid, 64, 0, st>>>(P);
+  sosfilt_chunk_kernel<0, 1, NSEC, NCF><<<cgrid, 128, 0, st>>>(P, total_chunks);
+  sosfilt_chunk_kernel<1, 0, NSEC, NCF><<<cgrid, 128, 0, st>>>(P, total_chunks);
+  sosfilt_scan_kernel<1, NSEC><<<sgrid, 64, 0, st>>>(P);
+  sosfilt_chunk_kernel<1, 1, NSEC, NCF><<<cgrid, 128, 0, st>>>(P, total_chunks);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+template <int NSEC>
+static int sos_scan_ncf(scgrhc_ctx* ctx, const SosScanParams& P, long long total_chunks, cudaStream_t st) {
+  switch (P.ncf) {
+    case 1: return sos_scan_launch<NSEC, 1>(ctx, P, total_chunks, st);
+    case 2: return sos_scan_launch<NSEC, 2>(ctx, P, total_chunks, st);
+    case 3: return sos_scan_launch<NSEC, 3>(ctx, P, total_chunks, st);
+    case 4: return sos_scan_launch<NSEC, 4>(ctx, P, total_chunks, st);
+    default: return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "sosfiltfilt_scan: 1..4 filtered columns per call (got %d)", P.ncf);
+  }
+}
+
+extern "C" int scgrhc_sosfiltfilt_scan(scgrhc_ctx* ctx, const double* x, double* y, double* tmp, double* fstate,
+                                       const int64_t* row0_dev, const int64_t* row0_host, const int64_t* chunk0_dev,
+                                       int64_t total_chunks, int32_t chunk, const double* M_dev, int32_t n_rec, int32_t ncols,
+                                       const int32_t* fcols, int32_t ncf, const double* sos, const double* zi, int32_t nsec,
+                                       int32_t edge, void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (n_rec < 0 || ncols < 1 || ncf < 1 || ncf > 4 || nsec < 1 || nsec > 4 || edge < 0 || chunk < 1 || !sos || !zi || !fcols ||
+      (n_rec && (!x || !y || !tmp || !fstate || !row0_dev || !row0_host || !chunk0_dev || !M_dev)))
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "sosfiltfilt_scan: bad arguments (1..4 sections, 1..4 filtered columns)");
+  if (n_rec == 0) return SCGRHC_OK;
+  SosScanParams P;
+  P.x = x; P.y = y; P.tmp = tmp; P.fstate = fstate; P.M = M_dev;
+  P.row0 = reinterpret_cast<const long long*>(row0_dev); P.chunk0 = reinterpret_cast<const long long*>(chunk0_dev);
+  P.n_rec = n_rec; P.ncols = ncols; P.nsec = nsec; P.edge = edge; P.ncf = ncf; P.chunk = chunk;
+  for (int r = 0; r < n_rec; ++r) {
+    const long long T = row0_host[r + 1] - row0_host[r];
+    if (T <= edge) return fail(ctx, SCGRHC_ERR_BAD_ARG, "The length of the input vector x must be greater than padlen, which is %d.", edge);
+    if (T + 2LL * edge >= INT32_MAX) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "sosfiltfilt_scan: record too long");
+  }
+  for (int j = 0; j < ncf; ++j) {
+    if (fcols[j] < 0 || fcols[j] >= ncols) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "sosfiltfilt_scan: column %d outside 0..%d", fcols[j], ncols - 1);
+    P.fcols[j] = fcols[j];
+  }
+  for (int s = 0; s < nsec; ++s) {
+    if (sos[6 * s + 3] != 1.0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "sos[:, 3] should be all ones");
+    for (int k = 0; k < 6; ++k) P.sos[s][k] = sos[6 * s + k];
+    P.zi[s][0] = zi[2 * s]; P.zi[s][1] = zi[2 * s + 1];
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  switch (nsec) {
+    case 1: return sos_scan_ncf<1>(ctx, P, total_chunks, st);
+    case 2: return sos_scan_ncf<2>(ctx, P, total_chunks, st);
+    case 3: return sos_scan_ncf<3>(ctx, P, total_chunks, st);
+    default: return sos_scan_ncf<4>(ctx, P, total_chunks, st);
+  }
+}
+
 extern "C" int scgrhc_resample_poly(scgrhc_ctx* ctx, const double* x, double* y, const double* taps_dev, const int64_t* in0_dev,
                                     const int64_t* out0_dev, int32_t n_rec, int64_t max_out_rows, int32_t ncols, int32_t up, int32_t down,
                                     int32_t per_phase, int32_t n_pre_remove, void* stream) {

@@ -59,6 +59,7 @@ class Params:
     self.bandpass = self.data.get('bandpass')              # [low_hz, high_hz]: zero-phase Butterworth on the SCG channels
     self.bandpass_order = self.data.get('bandpass_order')
     self.bandpass_sos = self.data.get('bandpass_sos')      # or explicit second-order sections
+    self.bandpass_mode = self.data.get('bandpass_mode')    # 'exact' (default, bit-identical to scipy) | 'scan' (time-parallel)
     self.resample_rate = self.data.get('resample_rate')    # model sampling rate in Hz (native: 500)
 
   def _get(self, key):

@@ -427,7 +427,7 @@ def prepare_cohort(params, record_names=None, chunk_records=32):
   else:
     arena = host.to(dev, non_blocking=True)
   if sos is not None:                      # extension: zero-phase band-pass of the SCG channels (scipy sosfiltfilt semantics)
-    arena = filters.sosfiltfilt(arena, rows, sos, list(range(C)))
+    arena = filters.sosfiltfilt(arena, rows, sos, list(range(C)), exact=getattr(params, 'bandpass_mode', None) != 'scan')
   if rate and int(rate) != SAMPLE_FREQ:    # extension: every channel to the model rate (scipy resample_poly semantics)
     arena, rows = filters.resample_poly(arena, rows, int(rate), SAMPLE_FREQ)
     W = int(params.segment_size * int(rate))
