@@ -333,3 +333,37 @@ def test_strided_windows_extension(stride):
   s_o, r_o, mm_o = orc.normalise_record(p, sig, sig[:3], rw)
   scg, rhc = st.materialise()
   assert scg.cpu().numpy().tobytes() == s_o.tobytes() and rhc.cpu().numpy().tobytes() == r_o.tobytes()
+
+
+def test_host_ingest_chunked_equals_resident(tmp_path):
+  """Ragged record lengths, chunk boundaries that split the cohort unevenly, records without windows: the
+  double-buffered host pipeline (fp64 and int16/format-16 inputs) yields exactly the resident result."""
+  from scgrhc.engine import HostIngest
+  sig = synth_ref.DEFAULT_SIG_NAMES
+  kinds = synth_ref.kinds_for(sig)
+  rows = [30011, 752, 15000, 40000, 1500, 8000, 22222]
+  metas = [synth_ref.record_meta(90, events=e) for e in
+           ({'PA_1': 0.2, 'RV_1': 50}, {'PA_1': 0}, {'RA_1': 0}, {'RV_1': 1, 'PA_1': 20, 'RA_1': 60, 'PA_2': 70}, {'PA_1': 0.5},
+            {'PA_1': 10}, {'PA_1': 3.3})]
+  recs = [synth_ref.gen_record(H.SEED, 200 + r, T, kinds=kinds) for r, T in enumerate(rows)]
+  host = torch.from_numpy(np.concatenate(recs)).pin_memory()
+  plan = scgrhc.plan_cohort(metas, 'PA', rows, 750)
+  ref = scgrhc.prepare_windows(host.to(DEV), plan, [0, 1, 2], 3, -50.0)
+  for chunk in (1, 2, 3, 100):
+    st = HostIngest(plan, rows, 4, DEV, chunk_records=chunk).run(host, [0, 1, 2], 3, -50.0)
+    assert st.n_kept == ref.n_kept > 0 and torch.equal(st.kept_idx, ref.kept_idx) and torch.equal(st.rec_id, ref.rec_id)
+    assert torch.equal(st.start_idx, ref.start_idx) and torch.equal(st.minmax[st.kept_idx], ref.minmax[ref.kept_idx])
+    a, b = st.materialise(), ref.materialise()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+  # format-16 digital frames with per-record calibration
+  gains = [[1e5 + 10 * r, 2e5, 1.5e5, 400.0 + r] for r in range(len(rows))]
+  bases = [[3.0 * r, -7.0, 0.0, 100.0 - r] for r in range(len(rows))]
+  d = [np.clip(np.round(p * np.array(g) + np.array(b)), -32767, 32767).astype(np.int16) for p, g, b in zip(recs, gains, bases)]
+  phys = [(x.astype(np.float64) - np.array(b)) / np.array(g) for x, g, b in zip(d, gains, bases)]
+  ref2 = scgrhc.prepare_windows(torch.from_numpy(np.concatenate(phys)).to(DEV), plan, [0, 1, 2], 3, -50.0)
+  hostd = torch.from_numpy(np.concatenate(d)).pin_memory()
+  st = HostIngest(plan, rows, 4, DEV, chunk_records=2, digital_nsig=4).run(hostd, [0, 1, 2], 3, -50.0,
+                                                                          decode=([0, 1, 2, 3], gains, bases))
+  assert st.n_kept == ref2.n_kept > 0 and torch.equal(st.kept_idx, ref2.kept_idx)
+  a, b = st.materialise(), ref2.materialise()
+  assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])

@@ -118,3 +118,36 @@ def test_gloo_minmax_allreduce_and_sharding():
                        capture_output=True, text=True, env=env, timeout=300)
   assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
   assert 'DIST_OK' in out.stdout
+
+
+def test_planner_property_random_sidecars():
+  """Randomised side-cars (unsorted, duplicated, negative, fractional, past-the-end times; random T / W / stride / rate):
+  the C planner enumerates exactly the windows the oracle's restatement of recordutil.py:93-110,138-146 does."""
+  from hypothesis import given, settings, strategies as st
+
+  times = st.one_of(st.integers(-50, 700), st.floats(-20, 700, allow_nan=False, width=32).map(lambda v: round(v, 4)))
+  keys = st.sampled_from(['PA_1', 'PA_2', 'PA_3', 'RV_1', 'RA_1', 'RA_2', 'PCW_1', 'PAX_1', 'pa_1', 'PA', 'X'])
+
+  @settings(max_examples=300, deadline=None)
+  @given(st.dictionaries(keys, times, max_size=7), st.integers(0, 86399), st.integers(0, 86399), st.integers(0, 400000),
+         st.sampled_from([1, 2, 50, 375, 750, 1000]), st.sampled_from([0, 1, 100, 750, 1500]), st.sampled_from([0.0, 250.0, 500.0]),
+         st.sampled_from(['PA', 'RA', 'RV', 'PCW']))
+  def check(events, t_start, t_end, T, W, stride, fs, chamber):
+    fmt = lambda s: 'd %02d:%02d:%02d' % (s // 3600, (s // 60) % 60, s % 60)
+    meta = {'MacStTime': fmt(t_start), 'MacEndTime': fmt(t_end), 'ChamEvents_in_s': events}
+    rate = fs or 500.0
+    orc_fs = orc.SAMPLE_FREQ
+    try:
+      orc.SAMPLE_FREQ = rate if rate != 500.0 else 500
+      ivals = orc.chamber_intervals(meta, chamber)
+    finally:
+      orc.SAMPLE_FREQ = orc_fs
+    a, r, w = orc.candidate_windows(ivals, T, W, stride or None)
+    iv, n, bounds = scgrhc.plan_record(meta, chamber, T, W, rec_base_row=7, rec_id=3, cand_base=11, stride=stride, fs=fs)
+    assert [tuple(b) for b in bounds] == ivals
+    st_ = stride or W
+    mine = np.concatenate([i['row0'] - 7 + np.arange(i['n_win']) * st_ for i in iv]) if len(iv) else np.zeros(0, np.int64)
+    assert n == len(a) and (mine == a).all()
+    assert (iv['n_win'] > 0).all() and (len(iv) == 0 or iv['cand0'][0] == 11)
+
+  check()
