@@ -151,3 +151,20 @@ def test_planner_property_random_sidecars():
     assert (iv['n_win'] > 0).all() and (len(iv) == 0 or iv['cand0'][0] == 11)
 
   check()
+
+
+def test_params_optional_extension_keys_default_off(tmp_path):
+  from paramutil import Params
+  base = dict(in_channels=['patch_ACC_lat'], chamber='PA', segment_size=1.5, batch_size=8, dir_path='w', train_path='a',
+              valid_path='b', test_path='c', checkpoint_dir_path='d', comparison_dir_path='e', pred_top_dir_path='f',
+              pred_rand_dir_path='g', alpha=1, beta1=1, beta2=1, n_critic=1, lambda_gp=1, lambda_aux=1, total_epochs=1,
+              min_RHC=-50, use_global_min_max=False)
+  p = tmp_path / 'p.json'
+  p.write_text(json.dumps(base))
+  q = Params(str(p), strict=True)
+  for k in ('split_seed', 'segment_stride', 'noise_std', 'noise_seed', 'bandpass', 'bandpass_order', 'bandpass_sos',
+            'bandpass_mode', 'resample_rate'):
+    assert getattr(q, k) is None
+  p.write_text(json.dumps(dict(base, bandpass=[1, 40], resample_rate=250, segment_stride=0.5, noise_std=0.01)))
+  q = Params(str(p))
+  assert q.bandpass == [1, 40] and q.resample_rate == 250 and q.segment_stride == 0.5 and q.noise_std == 0.01
