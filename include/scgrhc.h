@@ -55,6 +55,8 @@ typedef enum {
 #define SCGRHC_USE_KEPT_LIST  4u  /* iterate kept_idx[0..n_items) instead of all candidates; skip predicates;
                                      slot = list position (dense output).  Pass B of use_global_min_max. */
 #define SCGRHC_NORM_GLOBAL    8u  /* normalise with job->global_minmax instead of per-window pairs (recordutil.py:58-59) */
+#define SCGRHC_KEEP_ERRORS   32u  /* do not clear the context's error word first: several launches (chunks of one cohort)
+                                     accumulate into one scgrhc_check_errors() */
 #define SCGRHC_KEEP_ALL      16u  /* evaluate the predicates (reason bits) but keep and normalise every window:
                                      SCGDataset(segments, ...) on caller-chosen segments, no has_noise, no error */
 

@@ -216,8 +216,10 @@ extern "C" int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, co
   if (!pred_only && (!out->scg_out || !out->rhc_out) && items) return fail(ctx, SCGRHC_ERR_BAD_ARG, "scg_out/rhc_out are required");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  CUDA_TRY(ctx, cudaMemsetAsync(ctx->err_dev, 0, sizeof(unsigned long long), st));
-  CUDA_TRY(ctx, cudaMemsetAsync(ctx->err_dev + 1, 0xFF, sizeof(unsigned long long), st));
+  if (!(J.flags & SCGRHC_KEEP_ERRORS)) {
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->err_dev, 0, sizeof(unsigned long long), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->err_dev + 1, 0xFF, sizeof(unsigned long long), st));
+  }
   if (items == 0) return SCGRHC_OK;
   if (!J.intervals || J.n_intervals == 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "candidates without intervals");
 

@@ -301,6 +301,7 @@ class HostIngest:
     kept_idx, start_idx, stop_idx = (buf(k, (n,), torch.int64) for k in ('kept_idx', 'start_idx', 'stop_idx'))
     rec_id, n_kept_t = buf('rec_id', (n,), torch.int32), buf('n_kept', (1,), torch.int64)
     flags = N.OUT_F64 if out_dtype == torch.float64 else 0
+    launched = 0
     compute = torch.cuda.current_stream(dev)
     done = [None, None]
     self.copy_stream.wait_stream(compute)
@@ -327,15 +328,16 @@ class HostIngest:
         else:
           ops.decode_fmt16(stage, list(cols), [float(v) for v in gain], [float(v) for v in baseline], dst)
       if nc:
-        ops.process_windows(dst, iv, nc, W, plan.stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
+        ops.process_windows(dst, iv, nc, W, plan.stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold),
+                            flags | (N.KEEP_ERRORS if launched else 0),
                             [0.0] * 4, None, 0, scg[cand_lo:], rhc[cand_lo:], minmax[cand_lo:], keep[cand_lo:],
                             reason[cand_lo:], cand_win[cand_lo:], cand_rec[cand_lo:])
+        launched += 1
       done[k & 1] = torch.cuda.Event()
       done[k & 1].record(compute)
     ops.compact_kept(keep, cand_win, cand_rec, n, W, plan.stride, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
+    if n and launched:
+      ops.check_errors(dev.index)      # raises ValueError like the reference if a non-finite RHC window reached the regression
     n_kept = int(n_kept_t.item())      # device -> host read of the step's result
-    nonfinite = bool(((reason & N.REASON_NONFINITE) != 0).logical_and((reason & N.REASON_FLAT) == 0).any()) if n else False
-    if nonfinite:
-      raise ValueError('Input y contains NaN.')
     return WindowStore(scg, rhc, minmax, keep, reason, kept_idx[:n_kept], start_idx[:n_kept], stop_idx[:n_kept],
                        rec_id[:n_kept], n_kept, n, False, None)
