@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "aux_kernels.cuh"
 #include "filter_kernels.cuh"
 #include "window_kernel.cuh"
@@ -28,6 +30,12 @@ struct scgrhc_ctx {
 };
 
 static std::string g_create_error;
+
+// NVTX range per C-ABI call: shows up in Nsight timelines, costs nothing when no tool is attached
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 static int fail(scgrhc_ctx* ctx, int code, const char* fmt, ...) {
   char buf[512];
@@ -193,6 +201,7 @@ static int dispatch_nsig(scgrhc_ctx* ctx, const KParams& P, long long items, cud
 }
 
 extern "C" int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, const scgrhc_outputs* out, void* stream) {
+  NvtxRange nvtx_range("scgrhc_process_windows");
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
   if (!job || !out) return fail(ctx, SCGRHC_ERR_BAD_ARG, "job/out is NULL");
   const scgrhc_job& J = *job;
@@ -266,6 +275,7 @@ static int ensure_scan(scgrhc_ctx* ctx, long long nblocks) {
 
 extern "C" int scgrhc_compact_kept(scgrhc_ctx* ctx, const uint8_t* keep, const int32_t* cand_win, const int32_t* cand_rec,
                                    int64_t n_cand, int32_t W, const scgrhc_compact* out, void* stream) {
+  NvtxRange nvtx_range("scgrhc_compact_kept");
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
   if (!out || !out->n_kept || n_cand < 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "compact: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -288,6 +298,7 @@ extern "C" int scgrhc_compact_kept(scgrhc_ctx* ctx, const uint8_t* keep, const i
 
 extern "C" int scgrhc_global_minmax(scgrhc_ctx* ctx, const double* minmax, const uint8_t* keep, int64_t n_cand,
                                     double* mm_out, void* stream) {
+  NvtxRange nvtx_range("scgrhc_global_minmax");
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
   if (!mm_out || n_cand < 0 || (n_cand && (!minmax || !keep))) return fail(ctx, SCGRHC_ERR_BAD_ARG, "global_minmax: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -301,6 +312,7 @@ extern "C" int scgrhc_global_minmax(scgrhc_ctx* ctx, const double* minmax, const
 
 extern "C" int scgrhc_gather_windows(scgrhc_ctx* ctx, const void* store, const int64_t* slots, int64_t n,
                                      int64_t window_bytes, void* out, void* stream) {
+  NvtxRange nvtx_range("scgrhc_gather_windows");
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
   if (n < 0 || window_bytes <= 0 || (window_bytes & 3) || (n && (!store || !slots || !out)))
     return fail(ctx, SCGRHC_ERR_BAD_ARG, "gather: bad arguments (window_bytes must be a positive multiple of 4)");
@@ -322,6 +334,7 @@ extern "C" int scgrhc_gather_windows(scgrhc_ctx* ctx, const void* store, const i
 extern "C" int scgrhc_gather_windows_noise(scgrhc_ctx* ctx, const float* store, const int64_t* slots, int64_t n,
                                            int64_t window_elems, float* out, float sigma, uint64_t seed, uint64_t offset,
                                            void* stream) {
+  NvtxRange nvtx_range("scgrhc_gather_windows_noise");
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
   if (n < 0 || window_elems <= 0 || (n && (!store || !slots || !out)))
     return fail(ctx, SCGRHC_ERR_BAD_ARG, "gather_windows_noise: bad arguments");
@@ -348,6 +361,7 @@ extern "C" int scgrhc_philox_words(scgrhc_ctx* ctx, uint64_t seed, uint64_t offs
 
 extern "C" int scgrhc_window_metrics(scgrhc_ctx* ctx, const float* real, const float* pred, const double* minmax, int64_t n,
                                      int32_t W, double* out, void* stream) {
+  NvtxRange nvtx_range("scgrhc_window_metrics");
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
   if (n < 0 || W < 2 || (n && (!real || !pred || !minmax || !out))) return fail(ctx, SCGRHC_ERR_BAD_ARG, "window_metrics: bad arguments");
   if (n == 0) return SCGRHC_OK;
@@ -362,6 +376,7 @@ extern "C" int scgrhc_window_metrics(scgrhc_ctx* ctx, const float* real, const f
 extern "C" int scgrhc_sosfiltfilt(scgrhc_ctx* ctx, const double* x, double* y, double* tmp, const int64_t* row0_dev,
                                   const int64_t* row0_host, int32_t n_rec, int32_t ncols, const int32_t* fcols, int32_t ncf,
                                   const double* sos, const double* zi, int32_t nsec, int32_t edge, void* stream) {
+  NvtxRange nvtx_range("scgrhc_sosfiltfilt");
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
   if (n_rec < 0 || ncols < 1 || ncf < 1 || ncf > kMaxFilterCols || nsec < 1 || nsec > kMaxSections || edge < 0 || !sos || !zi || !fcols ||
       (n_rec && (!x || !y || !tmp || !row0_dev || !row0_host)))
@@ -430,6 +445,7 @@ extern "C" int scgrhc_sosfiltfilt_scan(scgrhc_ctx* ctx, const double* x, double*
                                        int64_t total_chunks, int32_t chunk, const double* M_dev, int32_t n_rec, int32_t ncols,
                                        const int32_t* fcols, int32_t ncf, const double* sos, const double* zi, int32_t nsec,
                                        int32_t edge, void* stream) {
+  NvtxRange nvtx_range("scgrhc_sosfiltfilt_scan");
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
   if (n_rec < 0 || ncols < 1 || ncf < 1 || ncf > 4 || nsec < 1 || nsec > 4 || edge < 0 || chunk < 1 || !sos || !zi || !fcols ||
       (n_rec && (!x || !y || !tmp || !fstate || !row0_dev || !row0_host || !chunk0_dev || !M_dev)))
@@ -466,6 +482,7 @@ extern "C" int scgrhc_sosfiltfilt_scan(scgrhc_ctx* ctx, const double* x, double*
 extern "C" int scgrhc_resample_poly(scgrhc_ctx* ctx, const double* x, double* y, const double* taps_dev, const int64_t* in0_dev,
                                     const int64_t* out0_dev, int32_t n_rec, int64_t max_out_rows, int32_t ncols, int32_t up, int32_t down,
                                     int32_t per_phase, int32_t n_pre_remove, void* stream) {
+  NvtxRange nvtx_range("scgrhc_resample_poly");
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
   if (n_rec < 0 || ncols < 1 || up < 1 || down < 1 || per_phase < 1 || n_pre_remove < 0 || max_out_rows < 0 ||
       (n_rec && (!x || !y || !taps_dev || !in0_dev || !out0_dev)))
@@ -515,6 +532,7 @@ extern "C" int scgrhc_rolling_range_lt(scgrhc_ctx* ctx, const double* y, int64_t
 
 extern "C" int scgrhc_decode_fmt16(scgrhc_ctx* ctx, const int16_t* d, int64_t T, int32_t nsig_in, const int32_t* cols,
                                    int32_t ncols, const double* gain, const double* baseline, double* out, void* stream) {
+  NvtxRange nvtx_range("scgrhc_decode_fmt16");
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
   if (T < 0 || nsig_in < 1 || ncols < 1 || ncols > SCGRHC_MAX_C + 1 || !cols || !gain || !baseline || (T && (!d || !out)))
     return fail(ctx, SCGRHC_ERR_BAD_ARG, "decode_fmt16: bad arguments (1..%d output columns)", SCGRHC_MAX_C + 1);
@@ -550,6 +568,7 @@ extern "C" int scgrhc_waveform_stats(scgrhc_ctx* ctx, const double* y, int64_t n
 
 extern "C" int scgrhc_synth_records(scgrhc_ctx* ctx, uint64_t seed, int64_t rec0, int64_t n_rec, int64_t T, int32_t nsig,
                                     const int32_t* kinds, int32_t defect_scale, int32_t grid, double* out, void* stream) {
+  NvtxRange nvtx_range("scgrhc_synth_records");
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
   if (n_rec < 0 || T < 0 || nsig < 1 || nsig > SCGRHC_MAX_NSIG || !kinds || grid < 1 || (n_rec * T && !out))
     return fail(ctx, SCGRHC_ERR_BAD_ARG, "synth: bad arguments");

@@ -32,7 +32,7 @@ def build(force=False, verbose=False):
          '-Xcompiler', '-fPIC', '-shared', '-I' + os.path.join(ROOT, 'include'), '-I' + CSRC]
   if verbose:
     cmd += ['-Xptxas', '-v']
-  cmd += SOURCES + ['-o', LIB]
+  cmd += SOURCES + ['-o', LIB, '-ldl']
   subprocess.run(cmd, check=True)
   return LIB
 

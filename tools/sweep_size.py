@@ -12,10 +12,14 @@ import scgrhc  # noqa: E402
 from scgrhc import ops  # noqa: E402
 
 
-def run(n_rec, iters=10, flags=0):
+def run(n_rec, iters=10, flags=0, quantised=False):
   dev = torch.device('cuda', 0)
   arena = torch.empty((n_rec * bench.T_ROWS, 4), dtype=torch.float64, device=dev)
   ops.synth_records(arena, bench.SEED, 0, n_rec, bench.T_ROWS, bench.KINDS, 16, bench.W)
+  if quantised:   # what a format-16 record decodes to: RHC on a 2e-3 mmHg grid (coarser than the 1e-3 flat-line threshold)
+    g = torch.tensor([2e5, 2e5, 2e5, 500.0], dtype=torch.float64, device=dev)
+    for r0 in range(0, arena.shape[0], 50 * bench.T_ROWS):
+      arena[r0:r0 + 50 * bench.T_ROWS] = torch.round(arena[r0:r0 + 50 * bench.T_ROWS] * g) / g
   plan = scgrhc.plan_uniform(bench.meta(), 'PA', bench.T_ROWS, bench.W, n_rec)
   n, W, C = plan.n_cand, bench.W, 3
   iv = plan.device_intervals(dev)
@@ -40,7 +44,7 @@ def run(n_rec, iters=10, flags=0):
   nk = int(keep.sum())
   alg = bench.algorithmic_bytes(n, nk, C, 4)
   peak = bench.measured_peak()[0]
-  r = dict(n_rec=n_rec, ms_min=ms[0], ms_med=ms[len(ms) // 2], ms_max=ms[-1], frac_med=alg / ms[len(ms) // 2] / 1e6 / peak,
+  r = dict(quantised=quantised, kept=nk, n_rec=n_rec, ms_min=ms[0], ms_med=ms[len(ms) // 2], ms_max=ms[-1], frac_med=alg / ms[len(ms) // 2] / 1e6 / peak,
            mcand_s=n / ms[len(ms) // 2] / 1e3)
   print(json.dumps(r), flush=True)
   del arena, scg, rhc
@@ -48,5 +52,6 @@ def run(n_rec, iters=10, flags=0):
 
 
 if __name__ == '__main__':
-  for n_rec in [int(a) for a in sys.argv[1:]] or [125, 250, 500, 1000, 1500]:
-    run(n_rec)
+  q = '--quantised' in sys.argv
+  for n_rec in [int(a) for a in sys.argv[1:] if not a.startswith('--')] or [125, 250, 500, 1000, 1500]:
+    run(n_rec, quantised=q)
