@@ -181,6 +181,19 @@ class SCGDataset(Dataset):
     return st
 
   def __setstate__(self, st):
+    if 'scg' not in st:      # a pickle written by the reference's own SCGDataset: just `segment_size` and `segments`
+      segs = st['segments']
+      self.segment_size = st['segment_size']
+      self.device = torch.device('cpu')
+      self._names = [s[2] for s in segs]
+      self._start = np.array([int(s[3]) for s in segs], dtype=np.int64)
+      self._stop = np.array([int(s[4]) for s in segs], dtype=np.int64)
+      self._mm = np.array([[s[5][0], s[5][1], s[6][0], s[6][1]] for s in segs], dtype=np.float64).reshape(len(segs), 4)
+      C = segs[0][0].shape[0] if segs else 0
+      self.scg = torch.stack([s[0].contiguous() for s in segs]) if segs else torch.zeros((0, C, self.segment_size))
+      self.rhc = torch.stack([s[1].contiguous() for s in segs]) if segs else torch.zeros((0, 1, self.segment_size))
+      self._segments = segs
+      return
     self.__dict__.update(st)
     want = torch.device(st['device'])
     self.device = want if (want.type == 'cpu' or torch.cuda.is_available()) else torch.device('cpu')

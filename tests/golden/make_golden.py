@@ -234,8 +234,29 @@ def run_configs(h):
   print('configs: %d (%d load in the reference)' % (len(res), sum(v['reference_params_error'] is None for v in res.values())))
 
 
+def run_reference_pickle(h):
+  """A DataLoader pickled by the reference itself (recordutil.py:198-209): the drop-in's load_dataloader must read it."""
+  import pickle
+  from torch.utils.data import DataLoader
+  sig = synth_ref.SIG_NAMES_5
+  p = synth_ref.gen_record(SEED, 3, 45000, kinds=synth_ref.kinds_for(sig))
+  meta = synth_ref.record_meta(100, events={'RA_1': 0.5, 'RV_1': 15.001, 'PA_1': 30, 'PCW_1': 55.25, 'PA_2': 61.7})
+  h.add_record('small', sig, p, meta)
+  params = h.params('waveform_19')
+  segs = h.recordutil.get_segments(params, record_name='small')
+  ds = h.recordutil.SCGDataset(segs, params.segment_size, None, None)
+  with open(os.path.join(HERE, 'reference_loader.pickle'), 'wb') as f:
+    pickle.dump(DataLoader(ds, batch_size=2, shuffle=True), f)
+  print('reference_loader.pickle: %d items' % len(ds))
+
+
 if __name__ == '__main__':
+  if len(sys.argv) > 1 and sys.argv[1] == 'pickle':
+    with ReferenceHarness() as h:
+      run_reference_pickle(h)
+    sys.exit(0)
   with ReferenceHarness() as h:
+    run_reference_pickle(h)
     run_configs(h)
     run_intervals(h)
     run_predicates(h)

@@ -168,3 +168,22 @@ def test_params_optional_extension_keys_default_off(tmp_path):
   p.write_text(json.dumps(dict(base, bandpass=[1, 40], resample_rate=250, segment_stride=0.5, noise_std=0.01)))
   q = Params(str(p))
   assert q.bandpass == [1, 40] and q.resample_rate == 250 and q.segment_stride == 0.5 and q.noise_std == 0.01
+
+
+def test_load_dataloader_reads_pickles_written_by_the_reference():
+  """A user switching over has loader pickles made by the reference's own recordutil: they must keep loading."""
+  for name in ('recordutil', 'waveform_noise'):
+    sys.modules.pop(name, None)
+  import recordutil
+  assert os.path.dirname(recordutil.__file__).endswith('scg-rhc-waveform_b200')
+  loader = recordutil.load_dataloader(os.path.join(H.GOLDEN, 'reference_loader.pickle'))
+  g = np.load(os.path.join(H.GOLDEN, 'record_small.npz'))
+  ds = loader.dataset
+  assert isinstance(ds, recordutil.SCGDataset) and len(ds) == len(g['waveform_19.start']) == 3
+  for i, item in enumerate(ds):
+    assert item[0].numpy().tobytes() == g['waveform_19.scg'][i].tobytes() and item[3] == g['waveform_19.start'][i]
+    assert [item[5][0], item[5][1], item[6][0], item[6][1]] == g['waveform_19.minmax'][i].tolist()
+  batches = list(loader)                                   # the reference's torch DataLoader object, our dataset class
+  assert sum(b[0].shape[0] for b in batches) == 3 and batches[0][0].shape[1:] == (3, 750)
+  col = ds.collate(torch.tensor([2, 0]))
+  assert col[0].shape == (2, 3, 750) and col[3].tolist() == [int(g['waveform_19.start'][2]), int(g['waveform_19.start'][0])]
