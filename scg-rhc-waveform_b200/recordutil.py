@@ -425,11 +425,12 @@ def prepare_cohort(params, record_names=None, chunk_records=32):
   sos = _bandpass_sos(params)
   rate = getattr(params, 'resample_rate', None)
   extensions = sos is not None or (rate and int(rate) != SAMPLE_FREQ)
-  if not params.use_global_min_max and not extensions:
+  if not extensions:
     ing = engine.HostIngest(plan, rows, C + 1, dev, chunk_records=chunk_records, digital_nsig=(C + 1) if digital else None)
-    store = ing.run(host, list(range(C)), C, params.min_RHC, decode=(list(range(C + 1)), gains, bases) if digital else None)
+    store = ing.run(host, list(range(C)), C, params.min_RHC, decode=(list(range(C + 1)), gains, bases) if digital else None,
+                    use_global_min_max=bool(params.use_global_min_max))
     return store, names
-  # dataset-global pairs (second pass) and the optional filter / resample stages need the whole cohort resident
+  # the optional filter / resample stages work on a resident cohort
   if digital:
     d_dev = host.to(dev, non_blocking=True)
     arena = torch.empty((total, C + 1), dtype=torch.float64, device=dev)

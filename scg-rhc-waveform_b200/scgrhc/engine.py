@@ -280,36 +280,18 @@ class HostIngest:
     self.copy_stream = torch.cuda.Stream(self.device)
     self.h2d_bytes = self.total_rows * (digital_nsig * 2 if digital_nsig else nsig * 8)
 
-  def run(self, host_arena, scg_cols, rhc_col, min_rhc, out_dtype=torch.float32, flat_threshold=FLAT_THRESHOLD,
-          buffers=None, decode=None):
-    """``host_arena``: (total_rows, nsig) fp64 CPU tensor (pinned for an asynchronous copy), or — with
-    ``digital_nsig`` — (total_rows, digital_nsig) int16 frames plus ``decode = (cols, gain, baseline)`` where
-    gain/baseline are one list per selected column (all records) or one such list per record."""
-    plan, dev = self.plan, self.device
-    n, W, Cn = plan.n_cand, plan.W, len(scg_cols)
-    b = buffers if buffers is not None else {}
-
-    def buf(name, shape, dtype):
-      t = b.get(name)
-      if t is None or t.shape != torch.Size(shape) or t.dtype != dtype:
-        t = b[name] = torch.empty(shape, dtype=dtype, device=dev)
-      return t
-
-    scg, rhc = buf('scg', (n, Cn, W), out_dtype), buf('rhc', (n, 1, W), out_dtype)
-    minmax, keep, reason = buf('minmax', (n, 4), torch.float64), buf('keep', (n,), torch.uint8), buf('reason', (n,), torch.uint8)
-    cand_win, cand_rec = buf('cand_win', (n,), torch.int32), buf('cand_rec', (n,), torch.int32)
-    kept_idx, start_idx, stop_idx = (buf(k, (n,), torch.int64) for k in ('kept_idx', 'start_idx', 'stop_idx'))
-    rec_id, n_kept_t = buf('rec_id', (n,), torch.int32), buf('n_kept', (1,), torch.int64)
-    flags = N.OUT_F64 if out_dtype == torch.float64 else 0
-    launched = 0
+  def _stream(self, host_arena, decode, body):
+    """Copy (and, for digital cohorts, decode) chunk after chunk, double buffered, and hand each resident chunk to
+    ``body(dst, chunk)`` on the compute stream."""
+    dev = self.device
     compute = torch.cuda.current_stream(dev)
     done = [None, None]
     self.copy_stream.wait_stream(compute)
-    bad = False
     digital = self.digital_nsig is not None
     if digital and decode is None:
       raise ValueError('digital cohort: decode=(cols, gain, baseline) is required')
-    for k, (lo, hi, cand_lo, nc, iv, r0, r1) in enumerate(self.chunks):
+    for k, chunk in enumerate(self.chunks):
+      lo, hi, cand_lo, nc, iv, r0, r1 = chunk
       dst = self.bufs[k & 1][:hi - lo]
       stage = self.dbufs[k & 1][:hi - lo] if digital else dst
       with torch.cuda.stream(self.copy_stream):
@@ -328,16 +310,74 @@ class HostIngest:
         else:
           ops.decode_fmt16(stage, list(cols), [float(v) for v in gain], [float(v) for v in baseline], dst)
       if nc:
-        ops.process_windows(dst, iv, nc, W, plan.stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold),
-                            flags | (N.KEEP_ERRORS if launched else 0),
-                            [0.0] * 4, None, 0, scg[cand_lo:], rhc[cand_lo:], minmax[cand_lo:], keep[cand_lo:],
-                            reason[cand_lo:], cand_win[cand_lo:], cand_rec[cand_lo:])
-        launched += 1
+        body(dst, chunk)
       done[k & 1] = torch.cuda.Event()
       done[k & 1].record(compute)
+
+  def run(self, host_arena, scg_cols, rhc_col, min_rhc, out_dtype=torch.float32, flat_threshold=FLAT_THRESHOLD,
+          buffers=None, decode=None, use_global_min_max=False, group=None):
+    """``host_arena``: (total_rows, nsig) fp64 CPU tensor (pinned for an asynchronous copy), or — with
+    ``digital_nsig`` — (total_rows, digital_nsig) int16 frames plus ``decode = (cols, gain, baseline)`` where
+    gain/baseline are one list per selected column (all records) or one such list per record.
+
+    ``use_global_min_max`` (recordutil.py:185-186) streams the cohort twice — predicates + per-window pairs, the
+    dataset-level reduction (+ all-reduce over ``group``), then normalisation of the kept windows with the global pairs
+    into dense outputs — so cohorts larger than HBM (BASELINE configs[3]: 100k records) never have to be resident."""
+    plan, dev = self.plan, self.device
+    n, W, Cn = plan.n_cand, plan.W, len(scg_cols)
+    b = buffers if buffers is not None else {}
+
+    def buf(name, shape, dtype):
+      t = b.get(name)
+      if t is None or t.shape != torch.Size(shape) or t.dtype != dtype:
+        t = b[name] = torch.empty(shape, dtype=dtype, device=dev)
+      return t
+
+    minmax, keep, reason = buf('minmax', (n, 4), torch.float64), buf('keep', (n,), torch.uint8), buf('reason', (n,), torch.uint8)
+    cand_win, cand_rec = buf('cand_win', (n,), torch.int32), buf('cand_rec', (n,), torch.int32)
+    kept_idx, start_idx, stop_idx = (buf(k, (n,), torch.int64) for k in ('kept_idx', 'start_idx', 'stop_idx'))
+    rec_id, n_kept_t = buf('rec_id', (n,), torch.int32), buf('n_kept', (1,), torch.int64)
+    base_flags = N.OUT_F64 if out_dtype == torch.float64 else 0
+    scg = rhc = None
+    if not use_global_min_max:
+      scg, rhc = buf('scg', (n, Cn, W), out_dtype), buf('rhc', (n, 1, W), out_dtype)
+    launched = [0]
+
+    def pass_a(dst, chunk):
+      lo, hi, cand_lo, nc, iv, r0, r1 = chunk
+      flags = base_flags | (N.PREDICATES_ONLY if use_global_min_max else 0) | (N.KEEP_ERRORS if launched[0] else 0)
+      ops.process_windows(dst, iv, nc, W, plan.stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
+                          [0.0] * 4, None, 0, None if scg is None else scg[cand_lo:], None if rhc is None else rhc[cand_lo:],
+                          minmax[cand_lo:], keep[cand_lo:], reason[cand_lo:], cand_win[cand_lo:], cand_rec[cand_lo:])
+      launched[0] += 1
+
+    self._stream(host_arena, decode, pass_a)
     ops.compact_kept(keep, cand_win, cand_rec, n, W, plan.stride, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
-    if n and launched:
+    gmm = None
+    if use_global_min_max:
+      gmm = buf('gmm', (4,), torch.float64)
+      ops.global_minmax(minmax, keep, n, gmm)
+      gmm = allreduce_minmax(gmm, group)
+    if n and launched[0]:
       ops.check_errors(dev.index)      # raises ValueError like the reference if a non-finite RHC window reached the regression
     n_kept = int(n_kept_t.item())      # device -> host read of the step's result
+    if use_global_min_max:
+      scg, rhc = buf('scg', (n_kept, Cn, W), out_dtype), buf('rhc', (n_kept, 1, W), out_dtype)
+      kept = kept_idx[:n_kept]
+      edges = torch.tensor([c[2] for c in self.chunks] + [n], dtype=torch.int64, device=dev)
+      pos = torch.searchsorted(kept, edges).cpu().tolist()        # kept-list range of every chunk (plumbing, not arithmetic)
+      gm = gmm.cpu().tolist()
+      order = {id(c): i for i, c in enumerate(self.chunks)}
+
+      def pass_b(dst, chunk):
+        lo, hi, cand_lo, nc, iv, r0, r1 = chunk
+        a, e = pos[order[id(chunk)]], pos[order[id(chunk)] + 1]
+        if e > a:
+          ops.process_windows(dst, iv, nc, W, plan.stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold),
+                              base_flags | N.USE_KEPT_LIST | N.NORM_GLOBAL, gm, (kept[a:e] - cand_lo).contiguous(), e - a,
+                              scg[a:], rhc[a:], None, None, None, None, None)
+
+      if n_kept:
+        self._stream(host_arena, decode, pass_b)
     return WindowStore(scg, rhc, minmax, keep, reason, kept_idx[:n_kept], start_idx[:n_kept], stop_idx[:n_kept],
-                       rec_id[:n_kept], n_kept, n, False, None)
+                       rec_id[:n_kept], n_kept, n, bool(use_global_min_max), gmm)

@@ -355,6 +355,11 @@ def test_host_ingest_chunked_equals_resident(tmp_path):
     assert torch.equal(st.start_idx, ref.start_idx) and torch.equal(st.minmax[st.kept_idx], ref.minmax[ref.kept_idx])
     a, b = st.materialise(), ref.materialise()
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+  # dataset-global pairs over a streamed cohort (two passes over the host data) == the resident two-pass result
+  refg = scgrhc.prepare_windows(host.to(DEV), plan, [0, 1, 2], 3, -50.0, use_global_min_max=True)
+  stg = HostIngest(plan, rows, 4, DEV, chunk_records=2).run(host, [0, 1, 2], 3, -50.0, use_global_min_max=True)
+  assert stg.dense and stg.n_kept == refg.n_kept and torch.equal(stg.global_minmax, refg.global_minmax)
+  assert torch.equal(stg.scg[:stg.n_kept], refg.scg[:refg.n_kept]) and torch.equal(stg.rhc[:stg.n_kept], refg.rhc[:refg.n_kept])
   # format-16 digital frames with per-record calibration
   gains = [[1e5 + 10 * r, 2e5, 1.5e5, 400.0 + r] for r in range(len(rows))]
   bases = [[3.0 * r, -7.0, 0.0, 100.0 - r] for r in range(len(rows))]
