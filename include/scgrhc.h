@@ -181,16 +181,18 @@ int scgrhc_sosfiltfilt(scgrhc_ctx* ctx, const double* x, double* y, double* tmp,
                        const int64_t* row0_host, int32_t n_rec, int32_t ncols, const int32_t* fcols, int32_t ncf,
                        const double* sos, const double* zi, int32_t nsec, int32_t edge, void* stream);
 
-/* ---- the same filter, time-parallel: every record is cut into chunks of `chunk` samples filtered concurrently; the
- *      chunk-boundary states follow S_{k+1} = M S_k + f_k with M = A^chunk ((2 nsec)^2 doubles, device), A the state
- *      matrix of the cascade.  fstate: device scratch, total_chunks * ncf * 2 * nsec doubles; chunk0: device, n_rec+1
- *      prefix of chunks per record (ceil((T + 2 edge) / chunk)).  Up to 4 sections and 4 columns per call.  Not
- *      bit-identical to scipy (different rounding at chunk boundaries): within 1e-10 of full scale. */
-int scgrhc_sosfiltfilt_scan(scgrhc_ctx* ctx, const double* x, double* y, double* tmp, double* fstate,
-                            const int64_t* row0_dev, const int64_t* row0_host, const int64_t* chunk0_dev,
-                            int64_t total_chunks, int32_t chunk, const double* M_dev, int32_t n_rec, int32_t ncols,
-                            const int32_t* fcols, int32_t ncf, const double* sos, const double* zi, int32_t nsec,
-                            int32_t edge, void* stream);
+/* ---- the same filter, time-parallel (the brief's "warp-level parallel linear-recurrence scan over biquad state"): one
+ *      CTA per record (a warp per filtered column) walks it in spans of 32 * chunk rows; every lane filters its own chunk, the chunk-boundary
+ *      states follow S_(t+1) = A^chunk S_t + f_t through a Kogge-Stone scan over the lanes (A = state matrix of the
+ *      cascade, tables built on the host from sos).  Forward pass x -> y (whole rows, so the other columns are copied
+ *      through), backward pass over y in place: no scratch.  y may be x itself (in place); otherwise they must not
+ *      overlap.  chunk = rows per lane per span (0 = library default, <= 32), nbuf = staging buffers per CTA (0 =
+ *      default 1; 2 prefetches one span ahead at half the chunk length).  Up to 4 sections and 4 filtered columns per call, edge <= 32.  Not bit-identical to scipy (FMA,
+ *      different rounding order at chunk boundaries): within 1e-10 of full scale for SCG/RHC pass bands at 500 Hz. */
+int scgrhc_sosfiltfilt_scan(scgrhc_ctx* ctx, const double* x, double* y, const int64_t* row0_dev,
+                            const int64_t* row0_host, int32_t n_rec, int32_t ncols, const int32_t* fcols, int32_t ncf,
+                            const double* sos, const double* zi, int32_t nsec, int32_t edge, int32_t chunk, int32_t nbuf,
+                            void* stream);
 
 /* ---- extension (named by the project brief, ABSENT from the reference; default off): rational resampling of every
  *      record of the arena, scipy.signal.resample_poly semantics (polyphase upfirdn, zero padding).  taps: device,

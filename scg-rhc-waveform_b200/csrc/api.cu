@@ -12,6 +12,7 @@
 
 #include "aux_kernels.cuh"
 #include "filter_kernels.cuh"
+#include "filter_scan_kernel.cuh"
 #include "window_kernel.cuh"
 
 using namespace scgrhc;
@@ -417,44 +418,94 @@ extern "C" int scgrhc_sosfiltfilt(scgrhc_ctx* ctx, const double* x, double* y, d
   return SCGRHC_OK;
 }
 
-template <int NSEC, int NCF>
-static int sos_scan_launch(scgrhc_ctx* ctx, const SosScanParams& P, long long total_chunks, cudaStream_t st) {
-  const unsigned cgrid = (unsigned)((total_chunks + 127) / 128), sgrid = (unsigned)((P.n_rec * P.ncf + 63) / 64);
-  sosfilt_chunk_kernel<0, 0, NSEC, NCF><<<cgrid, 128, 0, st>>>(P, total_chunks);
-  sosfilt_scan_kernel<0, NSEC><<<sgrid, 64, 0, st>>>(P);
-  sosfilt_chunk_kernel<0, 1, NSEC, NCF><<<cgrid, 128, 0, st>>>(P, total_chunks);
-  sosfilt_chunk_kernel<1, 0, NSEC, NCF><<<cgrid, 128, 0, st>>>(P, total_chunks);
-  sosfilt_scan_kernel<1, NSEC><<<sgrid, 64, 0, st>>>(P);
-  sosfilt_chunk_kernel<1, 1, NSEC, NCF><<<cgrid, 128, 0, st>>>(P, total_chunks);
+// host tables of the time-parallel filter: A = the cascade's state matrix (column i = one zero-input step from the
+// i-th unit state), B = one unit-input step from the zero state; G[i] = A^(L-1-i) B, Mp[k] = A^(L 2^k).  long double
+// products, rounded once.
+static void tp_tables(const double* sos, int nsec, int L, SosTpParams& P) {
+  typedef long double ld;
+  const int D = 2 * nsec;
+  auto step = [&](ld* z, ld u) {
+    for (int s = 0; s < nsec; ++s) {
+      const ld b0 = sos[6 * s], b1 = sos[6 * s + 1], b2 = sos[6 * s + 2], a1 = sos[6 * s + 4], a2 = sos[6 * s + 5];
+      const ld xn = b0 * u + z[2 * s];
+      z[2 * s] = b1 * u - a1 * xn + z[2 * s + 1];
+      z[2 * s + 1] = b2 * u - a2 * xn;
+      u = xn;
+    }
+  };
+  ld A[8][8] = {}, B[8] = {}, z[8];
+  for (int i = 0; i < D; ++i) {
+    for (int a = 0; a < D; ++a) z[a] = a == i ? 1.0L : 0.0L;
+    step(z, 0.0L);
+    for (int a = 0; a < D; ++a) A[a][i] = z[a];
+  }
+  for (int a = 0; a < D; ++a) z[a] = 0.0L;
+  step(z, 1.0L);
+  for (int a = 0; a < D; ++a) B[a] = z[a];
+  auto matmul = [&](const ld X[8][8], const ld Y[8][8], ld Z[8][8]) {
+    ld R[8][8];
+    for (int a = 0; a < D; ++a)
+      for (int b = 0; b < D; ++b) {
+        ld acc = 0.0L;
+        for (int k = 0; k < D; ++k) acc += X[a][k] * Y[k][b];
+        R[a][b] = acc;
+      }
+    for (int a = 0; a < D; ++a)
+      for (int b = 0; b < D; ++b) Z[a][b] = R[a][b];
+  };
+  memset(P.G, 0, sizeof P.G);
+  memset(P.Mp, 0, sizeof P.Mp);
+  ld g[8];
+  for (int a = 0; a < D; ++a) g[a] = B[a];
+  for (int i = L - 1; i >= 0; --i) {                       // G[L-1] = B, G[i] = A G[i+1]
+    for (int a = 0; a < D; ++a) P.G[i][a] = (double)g[a];
+    ld n[8];
+    for (int a = 0; a < D; ++a) {
+      ld acc = 0.0L;
+      for (int k = 0; k < D; ++k) acc += A[a][k] * g[k];
+      n[a] = acc;
+    }
+    for (int a = 0; a < D; ++a) g[a] = n[a];
+  }
+  ld M[8][8] = {};
+  for (int a = 0; a < D; ++a) M[a][a] = 1.0L;
+  for (int i = 0; i < L; ++i) matmul(A, M, M);            // A^L
+  for (int k = 0; k < 5; ++k) {
+    for (int a = 0; a < D; ++a)
+      for (int b = 0; b < D; ++b) P.Mp[k][a][b] = (double)M[a][b];
+    matmul(M, M, M);
+  }
+}
+
+template <int NSEC, int LT>
+static int sos_tp_launch_l(scgrhc_ctx* ctx, const SosTpParams& P, int ncf, size_t smem, cudaStream_t st) {
+  CUDA_TRY(ctx, cudaFuncSetAttribute(sosfilt_tp_kernel<NSEC, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sosfilt_tp_kernel<NSEC, LT><<<(unsigned)P.n_rec, 32 * ncf, smem, st>>>(P);
   CUDA_TRY(ctx, cudaGetLastError());
   return SCGRHC_OK;
 }
 template <int NSEC>
-static int sos_scan_ncf(scgrhc_ctx* ctx, const SosScanParams& P, long long total_chunks, cudaStream_t st) {
-  switch (P.ncf) {
-    case 1: return sos_scan_launch<NSEC, 1>(ctx, P, total_chunks, st);
-    case 2: return sos_scan_launch<NSEC, 2>(ctx, P, total_chunks, st);
-    case 3: return sos_scan_launch<NSEC, 3>(ctx, P, total_chunks, st);
-    case 4: return sos_scan_launch<NSEC, 4>(ctx, P, total_chunks, st);
-    default: return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "sosfiltfilt_scan: 1..4 filtered columns per call (got %d)", P.ncf);
-  }
+static int sos_tp_launch(scgrhc_ctx* ctx, const SosTpParams& P, int ncf, size_t smem, cudaStream_t st) {
+  if (P.L == 24) return sos_tp_launch_l<NSEC, 24>(ctx, P, ncf, smem, st);   // the default for 32-byte rows: unrolled
+  return sos_tp_launch_l<NSEC, 0>(ctx, P, ncf, smem + kTpMaxL * 2 * NSEC * 8, st);
 }
 
-extern "C" int scgrhc_sosfiltfilt_scan(scgrhc_ctx* ctx, const double* x, double* y, double* tmp, double* fstate,
-                                       const int64_t* row0_dev, const int64_t* row0_host, const int64_t* chunk0_dev,
-                                       int64_t total_chunks, int32_t chunk, const double* M_dev, int32_t n_rec, int32_t ncols,
-                                       const int32_t* fcols, int32_t ncf, const double* sos, const double* zi, int32_t nsec,
-                                       int32_t edge, void* stream) {
+extern "C" int scgrhc_sosfiltfilt_scan(scgrhc_ctx* ctx, const double* x, double* y, const int64_t* row0_dev,
+                                       const int64_t* row0_host, int32_t n_rec, int32_t ncols, const int32_t* fcols,
+                                       int32_t ncf, const double* sos, const double* zi, int32_t nsec, int32_t edge,
+                                       int32_t chunk, int32_t nbuf, void* stream) {
   NvtxRange nvtx_range("scgrhc_sosfiltfilt_scan");
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
-  if (n_rec < 0 || ncols < 1 || ncf < 1 || ncf > 4 || nsec < 1 || nsec > 4 || edge < 0 || chunk < 1 || !sos || !zi || !fcols ||
-      (n_rec && (!x || !y || !tmp || !fstate || !row0_dev || !row0_host || !chunk0_dev || !M_dev)))
-    return fail(ctx, SCGRHC_ERR_BAD_ARG, "sosfiltfilt_scan: bad arguments (1..4 sections, 1..4 filtered columns)");
+  if (n_rec < 0 || ncols < 1 || ncf < 1 || ncf > kTpMaxCols || nsec < 1 || nsec > kTpMaxSec || edge < 1 || edge > kTpMaxEdge ||
+      chunk < 0 || chunk > kTpMaxL || nbuf < 0 || nbuf > 2 || !sos || !zi || !fcols || (n_rec && (!x || !y || !row0_dev || !row0_host)))
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "sosfiltfilt_scan: bad arguments (1..%d sections, 1..%d filtered columns, edge 1..%d, chunk 0..%d)",
+                kTpMaxSec, kTpMaxCols, kTpMaxEdge, kTpMaxL);
   if (n_rec == 0) return SCGRHC_OK;
-  SosScanParams P;
-  P.x = x; P.y = y; P.tmp = tmp; P.fstate = fstate; P.M = M_dev;
-  P.row0 = reinterpret_cast<const long long*>(row0_dev); P.chunk0 = reinterpret_cast<const long long*>(chunk0_dev);
-  P.n_rec = n_rec; P.ncols = ncols; P.nsec = nsec; P.edge = edge; P.ncf = ncf; P.chunk = chunk;
+  if (ncols > SCGRHC_MAX_NSIG) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "sosfiltfilt_scan: at most %d signals per row", SCGRHC_MAX_NSIG);
+  SosTpParams P;
+  memset(&P, 0, sizeof P);
+  P.x = x; P.y = y; P.row0 = reinterpret_cast<const long long*>(row0_dev);
+  P.n_rec = n_rec; P.ncols = ncols; P.edge = edge;
   for (int r = 0; r < n_rec; ++r) {
     const long long T = row0_host[r + 1] - row0_host[r];
     if (T <= edge) return fail(ctx, SCGRHC_ERR_BAD_ARG, "The length of the input vector x must be greater than padlen, which is %d.", edge);
@@ -466,16 +517,32 @@ extern "C" int scgrhc_sosfiltfilt_scan(scgrhc_ctx* ctx, const double* x, double*
   }
   for (int s = 0; s < nsec; ++s) {
     if (sos[6 * s + 3] != 1.0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "sos[:, 3] should be all ones");
-    for (int k = 0; k < 6; ++k) P.sos[s][k] = sos[6 * s + k];
+    P.c[s][0] = sos[6 * s]; P.c[s][1] = sos[6 * s + 1]; P.c[s][2] = sos[6 * s + 2];
+    P.c[s][3] = -sos[6 * s + 4]; P.c[s][4] = -sos[6 * s + 5];
     P.zi[s][0] = zi[2 * s]; P.zi[s][1] = zi[2 * s + 1];
   }
+  // Shape of the staging: one buffer per CTA and as many rows per lane as keep it near 25 KB of shared memory, i.e. 8
+  // CTAs per SM (32-byte rows: L = 24); measured faster than two buffers of half the chunk length
+  const int rb = ncols * 8;
+  P.nbuf = nbuf ? nbuf : 1;
+  int L = chunk;
+  if (!L) {
+    L = (25600 / (P.nbuf * 32) - 16) / rb;
+    if (L >= 4) L &= ~3;                                   // L * row bytes a multiple of 128: conflict-free lane pitch
+    L = std::max(2, std::min(kTpMaxL, L));
+  }
+  P.L = L;
+  P.bulk = (ncols % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0);
+  const size_t smem = 16 + 5 * (2 * nsec) * (2 * nsec) * 8 + (size_t)P.nbuf * 32 * ((size_t)L * rb + 16);
+  if (smem + kTpMaxL * 2 * kTpMaxSec * 8 > 220 * 1024) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "sosfiltfilt_scan: chunk %d x %d signals does not fit in shared memory", L, ncols);
+  tp_tables(sos, nsec, L, P);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   switch (nsec) {
-    case 1: return sos_scan_ncf<1>(ctx, P, total_chunks, st);
-    case 2: return sos_scan_ncf<2>(ctx, P, total_chunks, st);
-    case 3: return sos_scan_ncf<3>(ctx, P, total_chunks, st);
-    default: return sos_scan_ncf<4>(ctx, P, total_chunks, st);
+    case 1: return sos_tp_launch<1>(ctx, P, ncf, smem, st);
+    case 2: return sos_tp_launch<2>(ctx, P, ncf, smem, st);
+    case 3: return sos_tp_launch<3>(ctx, P, ncf, smem, st);
+    default: return sos_tp_launch<4>(ctx, P, ncf, smem, st);
   }
 }
 

@@ -211,126 +211,3 @@ __global__ void __launch_bounds__(kResTile) resample_poly_kernel(const __grid_co
 }
 
 }  // namespace scgrhc
-
-namespace scgrhc {
-
-// ---- time-parallel variant of the same filter (the brief's "parallel linear-recurrence scan over biquad state") ----
-// The cascade is one linear system  S' = A S + B x  (S = the 2*nsec delay elements).  A sequence is cut into chunks of
-// `chunk` samples; thread (record, chunk) filters its chunk for ALL filtered columns
-//   pass A: from a zero state, keeping only the final state f_k                       (sosfilt_chunk_kernel<.,0>)
-//   scan  : S_{k+1} = M S_k + f_k with M = A^chunk (host, fp64), S_0 = zi * x_0        (sosfilt_scan_kernel)
-//   pass B: again from the true S_k, writing the outputs                               (sosfilt_chunk_kernel<.,1>)
-// Work doubles, but parallelism is records x chunks instead of records, and a thread consumes whole 32-byte rows.
-// Inside a chunk every operation is rounded as in the exact kernel; only the chunk-boundary states come from the
-// matrix recurrence, so the result differs from scipy by rounding noise (measured <= 1e-13 of full scale, bar 1e-10).
-struct SosScanParams {
-  const double* x; double* y; double* tmp;
-  const long long* row0;
-  double* fstate;           // (total_chunks, ncf, 2*nsec): final zero-state of pass A, then S_k for pass B (in place)
-  const long long* chunk0;  // device, n_rec + 1: first chunk index of every record
-  const double* M;          // device, (2*nsec)^2 row-major
-  int n_rec, ncols, nsec, edge, ncf, chunk;
-  int fcols[kMaxFilterCols];
-  double sos[kMaxSections][6];
-  double zi[kMaxSections][2];
-};
-
-template <int PASS>
-__device__ __forceinline__ double sos_input(const SosScanParams& P, long long r0, int T, int Lext, long long tbase, int e, int j) {
-  if (PASS == 0) {
-    const double* xc = P.x + r0 * P.ncols + P.fcols[j];
-    if (e < P.edge) return __dsub_rn(2.0 * xc[0], xc[(long long)(P.edge - e) * P.ncols]);
-    if (e < P.edge + T) return xc[(long long)(e - P.edge) * P.ncols];
-    return __dsub_rn(2.0 * xc[(long long)(T - 1) * P.ncols], xc[(long long)(T - 2 - (e - P.edge - T)) * P.ncols]);
-  }
-  return P.tmp[tbase + (long long)(Lext - 1 - e) * P.ncf + j];
-}
-
-// PASS: 0 forward / 1 backward (as in the exact kernel);  PHASE: 0 zero-state (final state only) / 1 true state + outputs
-template <int PASS, int PHASE, int NSEC, int NCF>
-__global__ void __launch_bounds__(128) sosfilt_chunk_kernel(const __grid_constant__ SosScanParams P, long long total_chunks) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total_chunks) return;
-  int lo = 0, hi = P.n_rec - 1;                            // record of this chunk: last r with chunk0[r] <= gid
-  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (P.chunk0[mid] <= gid) lo = mid; else hi = mid - 1; }
-  const int rec = lo;
-  const int k = (int)(gid - P.chunk0[rec]);
-  const long long r0 = P.row0[rec];
-  const int T = (int)(P.row0[rec + 1] - r0), Lext = T + 2 * P.edge;
-  const long long tbase = (r0 + 2LL * P.edge * rec) * P.ncf;
-  const int e0 = k * P.chunk, e1 = min(Lext, e0 + P.chunk);
-  double z[NCF][NSEC][2];
-  double* st = P.fstate + gid * (long long)(NCF * NSEC * 2);
-#pragma unroll
-  for (int j = 0; j < NCF; ++j)
-#pragma unroll
-    for (int s = 0; s < NSEC; ++s) {
-      z[j][s][0] = PHASE ? st[(j * NSEC + s) * 2] : 0.0;
-      z[j][s][1] = PHASE ? st[(j * NSEC + s) * 2 + 1] : 0.0;
-    }
-  for (int e = e0; e < e1; ++e) {
-#pragma unroll
-    for (int j = 0; j < NCF; ++j) {
-      double v = sos_input<PASS>(P, r0, T, Lext, tbase, e, j);
-#pragma unroll
-      for (int s = 0; s < NSEC; ++s) {
-        const double xn = __dadd_rn(__dmul_rn(P.sos[s][0], v), z[j][s][0]);
-        z[j][s][0] = __dadd_rn(__dsub_rn(__dmul_rn(P.sos[s][1], v), __dmul_rn(P.sos[s][4], xn)), z[j][s][1]);
-        z[j][s][1] = __dsub_rn(__dmul_rn(P.sos[s][2], v), __dmul_rn(P.sos[s][5], xn));
-        v = xn;
-      }
-      if (PHASE) {
-        if (PASS == 0) {
-          P.tmp[tbase + (long long)e * P.ncf + j] = v;
-        } else {
-          const int t = Lext - 1 - P.edge - e;
-          if (t >= 0 && t < T) P.y[(r0 + t) * P.ncols + P.fcols[j]] = v;
-        }
-      }
-    }
-  }
-  if (!PHASE) {
-#pragma unroll
-    for (int j = 0; j < NCF; ++j)
-#pragma unroll
-      for (int s = 0; s < NSEC; ++s) { st[(j * NSEC + s) * 2] = z[j][s][0]; st[(j * NSEC + s) * 2 + 1] = z[j][s][1]; }
-  }
-}
-
-// one thread per (record, column): S_{k+1} = M S_k + f_k over the record's chunks, in place (f_k -> S_k)
-template <int PASS, int NSEC>
-__global__ void sosfilt_scan_kernel(const __grid_constant__ SosScanParams P) {
-  const int id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= P.n_rec * P.ncf) return;
-  const int rec = id / P.ncf, j = id - rec * P.ncf;
-  const long long r0 = P.row0[rec];
-  const int T = (int)(P.row0[rec + 1] - r0), Lext = T + 2 * P.edge;
-  const long long tbase = (r0 + 2LL * P.edge * rec) * P.ncf;
-  constexpr int D = 2 * NSEC;
-  double S[D], Mr[D][D];
-#pragma unroll
-  for (int a = 0; a < D; ++a)
-#pragma unroll
-    for (int b = 0; b < D; ++b) Mr[a][b] = P.M[a * D + b];
-  const double first = sos_input<PASS>(P, r0, T, Lext, tbase, 0, j);
-#pragma unroll
-  for (int s = 0; s < NSEC; ++s) { S[2 * s] = __dmul_rn(P.zi[s][0], first); S[2 * s + 1] = __dmul_rn(P.zi[s][1], first); }
-  const long long c0 = P.chunk0[rec], c1 = P.chunk0[rec + 1];
-  for (long long c = c0; c < c1; ++c) {
-    double* st = P.fstate + (c * P.ncf + j) * D;
-    double f[D], nx[D];
-#pragma unroll
-    for (int a = 0; a < D; ++a) { f[a] = st[a]; st[a] = S[a]; }
-#pragma unroll
-    for (int a = 0; a < D; ++a) {
-      double acc = f[a];
-#pragma unroll
-      for (int b = 0; b < D; ++b) acc = __fma_rn(Mr[a][b], S[b], acc);
-      nx[a] = acc;
-    }
-#pragma unroll
-    for (int a = 0; a < D; ++a) S[a] = nx[a];
-  }
-}
-
-}  // namespace scgrhc

@@ -441,7 +441,8 @@ def prepare_cohort(params, record_names=None, chunk_records=32):
   else:
     arena = host.to(dev, non_blocking=True)
   if sos is not None:                      # extension: zero-phase band-pass of the SCG channels (scipy sosfiltfilt semantics)
-    arena = filters.sosfiltfilt(arena, rows, sos, list(range(C)), exact=getattr(params, 'bandpass_mode', None) != 'scan')
+    scan = getattr(params, 'bandpass_mode', None) == 'scan'      # time-parallel kernel: filters the staged cohort in place
+    arena = filters.sosfiltfilt(arena, rows, sos, list(range(C)), exact=not scan, inplace=scan and len(sos) <= 4)
   if rate and int(rate) != SAMPLE_FREQ:    # extension: every channel to the model rate (scipy resample_poly semantics)
     arena, rows = filters.resample_poly(arena, rows, int(rate), SAMPLE_FREQ)
     W = int(params.segment_size * int(rate))

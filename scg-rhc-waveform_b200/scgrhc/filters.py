@@ -48,32 +48,15 @@ def butter_sos(low_hz, high_hz, fs, order=4):
   return butter(order, [low_hz, high_hz], btype='bandpass', fs=fs, output='sos')
 
 
-def cascade_state_matrix(sos):
-  """A of the cascade's state recurrence S' = A S + B x (S = the 2 n delay elements of the DF2T sections, in order):
-  column i is one filter step applied to the i-th unit state with zero input."""
-  sos = np.asarray(sos, dtype=np.float64)
-  n = sos.shape[0]
-  A = np.zeros((2 * n, 2 * n))
-  for i in range(2 * n):
-    z = np.zeros((n, 2))
-    z[i // 2, i % 2] = 1.0
-    v = 0.0
-    for s in range(n):
-      xn = sos[s, 0] * v + z[s, 0]
-      z[s, 0] = sos[s, 1] * v - sos[s, 4] * xn + z[s, 1]
-      z[s, 1] = sos[s, 2] * v - sos[s, 5] * xn
-      v = xn
-    A[:, i] = z.reshape(-1)
-  return A
-
-
-def sosfiltfilt(arena, record_rows, sos, columns, exact=True, chunk=2048):
+def sosfiltfilt(arena, record_rows, sos, columns, exact=True, chunk=0, nbuf=0, inplace=False):
   """Filter ``columns`` of every record of ``arena`` ((rows, ncols) fp64 CUDA; records back to back, ``record_rows``
   rows each) forward-backward; returns a new arena whose other columns are copied unchanged.
 
-  ``exact=True``: serial-in-time systolic kernel, bit-identical to scipy.  ``exact=False``: time-parallel chunked scan
-  (chunks of ``chunk`` samples, boundary states through the matrix recurrence), several times faster, equal to scipy
-  within rounding noise (<= 1e-10 of full scale); up to 4 sections / 4 columns per launch (more columns are looped)."""
+  ``exact=True``: serial-in-time systolic kernel, bit-identical to scipy.  ``exact=False``: time-parallel scan (one warp
+  per record, lanes filter chunks of ``chunk`` rows concurrently, chunk-boundary states through a scan over the lanes),
+  an order of magnitude faster, equal to scipy within rounding noise (<= 1e-10 of full scale); up to 4 sections, 4
+  columns per launch (more columns are looped, the later groups in place).  ``inplace=True`` (scan only) filters
+  ``arena`` itself and returns it."""
   if not arena.is_cuda:
     raise RuntimeError('sosfiltfilt needs a CUDA arena (no CPU fallback)')
   sos = np.ascontiguousarray(sos, dtype=np.float64)
@@ -85,32 +68,32 @@ def sosfiltfilt(arena, record_rows, sos, columns, exact=True, chunk=2048):
   row0 = np.ascontiguousarray(np.concatenate([[0], np.cumsum(rows)]).astype(np.int64))
   if row0[-1] != arena.shape[0]:
     raise ValueError('record_rows do not add up to the arena')
+  if not arena.is_contiguous() or arena.dtype != torch.float64:
+    raise ValueError('arena must be a contiguous float64 tensor')
   dev = arena.device
-  out = arena.clone()
   row0_dev = torch.from_numpy(row0).to(dev)
   c = ops.ctx(dev.index)
   p_sos, p_zi = sos.ctypes.data_as(C.POINTER(C.c_double)), zi.ctypes.data_as(C.POINTER(C.c_double))
   p_row0 = row0.ctypes.data_as(C.POINTER(C.c_int64))
   if exact or sos.shape[0] > 4:
+    if inplace:
+      raise ValueError('inplace filtering needs the time-parallel kernel (exact=False, at most 4 sections)')
+    out = arena.clone()
     cols = (C.c_int32 * len(columns))(*columns)
     tmp = torch.empty((int(row0[-1]) + 2 * edge * len(rows)) * len(columns), dtype=torch.float64, device=dev)
     N.check(c, N.lib().scgrhc_sosfiltfilt(c, ops._ptr(arena), ops._ptr(out), ops._ptr(tmp), ops._ptr(row0_dev), p_row0,
                                           len(rows), arena.shape[1], cols, len(columns), p_sos, p_zi, sos.shape[0], edge,
                                           ops._stream(dev.index)))
     return out
-  nchunks = -(-(rows + 2 * edge) // chunk)
-  chunk0 = np.concatenate([[0], np.cumsum(nchunks)]).astype(np.int64)
-  chunk0_dev = torch.from_numpy(chunk0).to(dev)
-  M = torch.from_numpy(np.ascontiguousarray(np.linalg.matrix_power(cascade_state_matrix(sos), chunk))).to(dev)
+  out = arena if inplace else torch.empty_like(arena)
+  src = arena
   for g0 in range(0, len(columns), 4):
     grp = list(columns[g0:g0 + 4])
     cols = (C.c_int32 * len(grp))(*grp)
-    tmp = torch.empty((int(row0[-1]) + 2 * edge * len(rows)) * len(grp), dtype=torch.float64, device=dev)
-    fstate = torch.empty(int(chunk0[-1]) * len(grp) * 2 * sos.shape[0], dtype=torch.float64, device=dev)
-    N.check(c, N.lib().scgrhc_sosfiltfilt_scan(c, ops._ptr(arena), ops._ptr(out), ops._ptr(tmp), ops._ptr(fstate),
-                                               ops._ptr(row0_dev), p_row0, ops._ptr(chunk0_dev), int(chunk0[-1]), chunk,
-                                               ops._ptr(M), len(rows), arena.shape[1], cols, len(grp), p_sos, p_zi,
-                                               sos.shape[0], edge, ops._stream(dev.index)))
+    N.check(c, N.lib().scgrhc_sosfiltfilt_scan(c, ops._ptr(src), ops._ptr(out), ops._ptr(row0_dev), p_row0, len(rows),
+                                               arena.shape[1], cols, len(grp), p_sos, p_zi, sos.shape[0], edge, int(chunk),
+                                               int(nbuf), ops._stream(dev.index)))
+    src = out                                              # the first launch copied every other column through
   return out
 
 

@@ -40,30 +40,39 @@ def test_sosfiltfilt_matches_scipy(order, band, btype):
   print('sosfiltfilt max scaled error', worst)
 
 
-@pytest.mark.parametrize('order,band,btype,chunk,tol', [(4, (1.0, 40.0), 'bandpass', 2048, 1e-10), (2, (0.5, 20.0), 'bandpass', 512, 1e-9),
-                                                        (4, 30.0, 'low', 1000, 1e-10), (3, 2.0, 'high', 64, 1e-10)])
-def test_sosfiltfilt_time_parallel_scan_within_1e_10(order, band, btype, chunk, tol):
-  """The chunked-scan variant (BASELINE north_star: fp64 device mode within 1e-10) against scipy and the exact kernel."""
+@pytest.mark.parametrize('order,band,btype,chunk,nbuf,tol', [(4, (1.0, 40.0), 'bandpass', 0, 0, 1e-10), (2, (0.5, 20.0), 'bandpass', 24, 1, 1e-9),
+                                                             (4, 30.0, 'low', 7, 2, 1e-10), (3, 2.0, 'high', 32, 1, 1e-10),
+                                                             (1, 5.0, 'low', 3, 2, 1e-10), (4, (1.0, 40.0), 'bandpass', 12, 2, 1e-10)])
+def test_sosfiltfilt_time_parallel_scan_within_1e_10(order, band, btype, chunk, nbuf, tol):
+  """The time-parallel variant (BASELINE north_star: fp64 device mode within 1e-10) against scipy and the exact kernel:
+  5 signals per row (40-byte rows: plain warp copies, two column groups, the second in place) and 4 signals per row
+  (32-byte rows: bulk async copies); records shorter than one span, of exactly one span, and of many spans + a ragged
+  last chunk."""
   sos = signal.butter(order, band, btype=btype, fs=500, output='sos')
-  sig = synth_ref.SIG_NAMES_5
-  rows = [30000, 311, 20001, 4096]
-  recs = [synth_ref.gen_record(H.SEED, 50 + r, T, kinds=synth_ref.kinds_for(sig)) for r, T in enumerate(rows)]
-  arena = torch.from_numpy(np.concatenate(recs)).to(DEV)
-  cols = [0, 1, 2, 3, 4]
-  fast = filters.sosfiltfilt(arena, rows, sos, cols, exact=False, chunk=chunk).cpu().numpy()
-  exact = filters.sosfiltfilt(arena, rows, sos, cols, exact=True).cpu().numpy()
-  at, worst = 0, 0.0
-  for p in recs:
-    want = signal.sosfiltfilt(sos, p, axis=0)
-    assert exact[at:at + len(p)].tobytes() == want.tobytes()
-    scale = np.abs(want).max(axis=0)
-    worst = max(worst, float((np.abs(fast[at:at + len(p)] - want) / scale).max()))
-    at += len(p)
-  # 1e-10 of full scale (BASELINE north_star) for the designs a 500 Hz SCG/RHC pipeline uses; a 0.5 Hz corner puts the
-  # poles at |z| = 0.997 and the delay elements at ~1e6 x the output scale on the channel with a 25 mmHg offset, so any
-  # reordering of roundings (ours vs scipy's, or scipy's vs exact arithmetic) moves the output by ~1e-10: bar 1e-9 there
-  assert worst <= tol, worst
-  print('scan max scaled error', worst)
+  L = chunk or 24                                                          # the library default for 32-byte rows
+  for sig, cols in ((synth_ref.SIG_NAMES_5, [0, 1, 2, 3, 4]), (synth_ref.DEFAULT_SIG_NAMES, [0, 1, 2]), (synth_ref.DEFAULT_SIG_NAMES, [3, 1])):
+    rows = [30000, 311, 20001, 32 * L, 64 * L + 1, 4096]
+    recs = [synth_ref.gen_record(H.SEED, 50 + r, T, kinds=synth_ref.kinds_for(sig)) for r, T in enumerate(rows)]
+    arena = torch.from_numpy(np.concatenate(recs)).to(DEV)
+    fast = filters.sosfiltfilt(arena, rows, sos, cols, exact=False, chunk=chunk, nbuf=nbuf).cpu().numpy()
+    exact = filters.sosfiltfilt(arena, rows, sos, cols, exact=True).cpu().numpy()
+    inpl = filters.sosfiltfilt(arena.clone(), rows, sos, cols, exact=False, chunk=chunk, nbuf=nbuf, inplace=True).cpu().numpy()
+    assert inpl.tobytes() == fast.tobytes()                                 # in place == out of place
+    at, worst = 0, 0.0
+    for p in recs:
+      want = p.copy()
+      want[:, cols] = signal.sosfiltfilt(sos, p[:, cols], axis=0)
+      assert exact[at:at + len(p)].tobytes() == want.tobytes()
+      other = [c for c in range(p.shape[1]) if c not in cols]
+      assert (fast[at:at + len(p)][:, other] == p[:, other]).all()          # untouched columns copied through
+      scale = np.abs(want[:, cols]).max(axis=0)
+      worst = max(worst, float((np.abs(fast[at:at + len(p)][:, cols] - want[:, cols]) / scale).max()))
+      at += len(p)
+    # 1e-10 of full scale (BASELINE north_star) for the designs a 500 Hz SCG/RHC pipeline uses; a 0.5 Hz corner puts the
+    # poles at |z| = 0.997 and the delay elements at ~1e6 x the output scale on the channel with a 25 mmHg offset, so any
+    # reordering of roundings (ours vs scipy's, or scipy's vs exact arithmetic) moves the output by ~1e-10: bar 1e-9 there
+    assert worst <= tol, worst
+    print('scan max scaled error', len(sig), cols, worst)
 
 
 def test_sosfiltfilt_rejects_short_records_like_scipy():
@@ -156,3 +165,9 @@ def test_recordutil_optional_keys_drive_the_extension_stages(tmp_path, monkeypat
   win = q[a + k0 * S: a + k0 * S + W, :3]
   want = ((win - win.min()) / (win.max() - win.min() + 0.0001)).T.astype(np.float32)
   assert ext.materialise()[0][0].cpu().numpy().tobytes() == np.ascontiguousarray(want).tobytes()
+  # bandpass_mode 'scan' = the time-parallel filter (in place on the staged cohort): same windows, samples within fp32 noise
+  fast, _ = recordutil.prepare_cohort(types.SimpleNamespace(bandpass=[1.0, 40.0], bandpass_mode='scan', resample_rate=250,
+                                                            segment_stride=0.75, **base))
+  assert fast.kept_idx.cpu().tolist() == ext.kept_idx.cpu().tolist()
+  a, b = fast.materialise()[0].cpu().numpy(), ext.materialise()[0].cpu().numpy()
+  assert np.abs(a - b).max() <= 1e-5                                       # normalised samples lie in [0, 1]

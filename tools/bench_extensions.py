@@ -17,7 +17,10 @@ def timed(fn, reps=3):
   fn(); torch.cuda.synchronize()
   a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   a.record()
-  for _ in range(reps): out = fn()
+  out = None
+  for _ in range(reps):
+    out = None                       # release the previous result first: the caching allocator then reuses its block
+    out = fn()
   b.record(); torch.cuda.synchronize()
   return a.elapsed_time(b) / reps, out
 
@@ -26,7 +29,7 @@ sos = signal.butter(4, (1.0, 40.0), btype='bandpass', fs=500, output='sos')
 ms, f = timed(lambda: filters.sosfiltfilt(arena, rows, sos, [0, 1, 2]))
 print(json.dumps(dict(stage='sosfiltfilt order-4 bandpass (4 sections), 3 of 4 columns', records=n_rec, ms=ms, records_per_s=n_rec / ms * 1e3, input_gb=gb)))
 ms2, _ = timed(lambda: filters.sosfiltfilt(arena, rows, sos, [0, 1, 2], exact=False))
-print(json.dumps(dict(stage='sosfiltfilt time-parallel scan (chunk 2048), same filter', records=n_rec, ms=ms2, records_per_s=n_rec / ms2 * 1e3)))
+print(json.dumps(dict(stage='sosfiltfilt time-parallel scan (CTA per record, warp per column), same filter', records=n_rec, ms=ms2, records_per_s=n_rec / ms2 * 1e3)))
 ms, (r, rrows) = timed(lambda: filters.resample_poly(f, rows, 250, 500))
 print(json.dumps(dict(stage='resample_poly 500->250 Hz, 4 columns', records=n_rec, ms=ms, records_per_s=n_rec / ms * 1e3, gbs=(gb * 1.5) / ms * 1e3)))
 d = torch.clamp(torch.round(arena * torch.tensor([2e5, 2e5, 2e5, 500.0], device=dev, dtype=torch.float64)), -32767, 32767).to(torch.int16)
