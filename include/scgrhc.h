@@ -57,6 +57,10 @@ typedef enum {
 #define SCGRHC_NORM_GLOBAL    8u  /* normalise with job->global_minmax instead of per-window pairs (recordutil.py:58-59) */
 #define SCGRHC_KEEP_ERRORS   32u  /* do not clear the context's error word first: several launches (chunks of one cohort)
                                      accumulate into one scgrhc_check_errors() */
+#define SCGRHC_NORM_ZSCORE   64u  /* extension (named by the project brief, ABSENT from the reference; default off): per-window
+                                     z-score instead of min-max: (x - mean) / (std + 0.0001), mean and population std taken
+                                     jointly over the (W, C) SCG block and over the RHC window; the minmax output then holds
+                                     {scg_mean, scg_std, rhc_mean, rhc_std}.  Not combinable with NORM_GLOBAL / USE_KEPT_LIST. */
 #define SCGRHC_KEEP_ALL      16u  /* evaluate the predicates (reason bits) but keep and normalise every window:
                                      SCGDataset(segments, ...) on caller-chosen segments, no has_noise, no error */
 

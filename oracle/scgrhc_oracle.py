@@ -239,6 +239,23 @@ def normalise_record(p_signal, sig_name, in_channels, rw, global_minmax=None, ou
           r[:, None, :].astype(out_dtype), mm)
 
 
+def zscore_record(p_signal, sig_name, in_channels, rw, out_dtype=np.float32):
+  """Extension (ABSENT from the reference — parity unpinned; plain numpy is the definition): per-window z-score of the kept
+  windows, (x - mean) / (std + 0.0001) with mean / population std taken jointly over the (W, C) SCG block, as the
+  reference takes its min/max (recordutil.py:58), and over the RHC window.  Returns scg, rhc and (n_kept, 4) rows
+  {scg_mean, scg_std, rhc_mean, rhc_std}."""
+  cols = [list(sig_name).index(n) for n in in_channels]
+  rcol = list(sig_name).index(RHC_NAME)
+  k = np.nonzero(rw.keep)[0]
+  idx = rw.abs_start[k][:, None] + np.arange(rw.W)[None, :]
+  scg = p_signal[:, cols][idx]
+  rhc = p_signal[:, rcol][idx]
+  ms = np.stack([scg.mean(axis=(1, 2)), scg.std(axis=(1, 2)), rhc.mean(axis=1), rhc.std(axis=1)], axis=1)
+  s = (scg - ms[:, 0, None, None]) / (ms[:, 1, None, None] + 0.0001)
+  r = (rhc - ms[:, 2, None]) / (ms[:, 3, None] + 0.0001)
+  return (np.ascontiguousarray(s.transpose(0, 2, 1)).astype(out_dtype), r[:, None, :].astype(out_dtype), ms)
+
+
 def global_minmax(minmax_rows):
   """get_global_minmax_vals (recordutil.py:152-169) over the kept windows' (n,4) rows."""
   m = np.asarray(minmax_rows, dtype=np.float64)

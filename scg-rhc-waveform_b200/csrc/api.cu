@@ -219,6 +219,8 @@ extern "C" int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, co
   if ((reinterpret_cast<uintptr_t>(J.arena) & 15) != 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "arena must be 16-byte aligned");
   const long long items = use_list ? J.n_items : J.n_cand;
   if (use_list && pred_only) return fail(ctx, SCGRHC_ERR_BAD_ARG, "USE_KEPT_LIST and PREDICATES_ONLY are exclusive");
+  if ((J.flags & SCGRHC_NORM_ZSCORE) && (use_list || (J.flags & SCGRHC_NORM_GLOBAL)))
+    return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "NORM_ZSCORE is a per-window mode: not combinable with NORM_GLOBAL / USE_KEPT_LIST");
   if (use_list && !J.kept_list && items) return fail(ctx, SCGRHC_ERR_BAD_ARG, "kept_list is NULL");
   if (!use_list && (!out->keep || !out->reason || !out->minmax || !out->cand_win || !out->cand_rec) && items)
     return fail(ctx, SCGRHC_ERR_BAD_ARG, "keep/reason/minmax/cand_win/cand_rec outputs are required");

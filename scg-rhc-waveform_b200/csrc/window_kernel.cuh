@@ -66,6 +66,7 @@ struct Scratch {
   uint32_t a49[RMAX * NWARP];
   int slow_cnt;
   int slow_flag;
+  double zred[NWARP][2];             // extension: shifted SCG sums of the z-score mode
 };
 
 // Correctly rounded a/d from the correctly rounded reciprocal inv = RN(1/d) (Markstein): two FMA
@@ -93,6 +94,14 @@ struct Normaliser {
     // Inf, huge ranges) takes the IEEE-division loop.
     slow = !(d >= 0x1p-14 && d <= 0x1p60 && fabs(mn_) >= 0x1p-900);
     quick = !slow && fabs(mn_) >= 0x1p-10;   // see tier 1 of the normalisation below
+  }
+  // extension (absent from the reference): (x - mean) / (std + 0.0001); same tiers, same validity conditions
+  __device__ __forceinline__ void init_z(double mean, double sd) {
+    mn = mean;
+    d = __dadd_rn(sd, 0.0001);
+    inv = __drcp_rn(d);
+    slow = !(d >= 0x1p-14 && d <= 0x1p60 && fabs(mean) >= 0x1p-900);
+    quick = !slow && fabs(mean) >= 0x1p-10;
   }
   __device__ __forceinline__ double fast(double x) const { return div_by_recip(__dsub_rn(x, mn), d, inv); }
   __device__ __forceinline__ double exact(double x) const { return __ddiv_rn(__dsub_rn(x, mn), d); }
@@ -202,6 +211,7 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
   const bool pred_only = (J.flags & SCGRHC_PREDICATES_ONLY) != 0;
   const bool norm_global = (J.flags & SCGRHC_NORM_GLOBAL) != 0;
   const bool keep_all = (J.flags & SCGRHC_KEEP_ALL) != 0;
+  const bool zscore = (J.flags & SCGRHC_NORM_ZSCORE) != 0;
   const double thr = J.flat_threshold, min_rhc = J.min_rhc;
   const int rcol = IDENT ? C : J.rhc_col;
   int col[C];
@@ -466,6 +476,45 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
           atomicMin(P.err + 1, (unsigned long long)M.cand);
         }
       }
+      if (zscore && keep && !pred_only) {
+        // extension: joint mean / population std of the SCG block (as the reference takes its min/max jointly) and of
+        // the RHC window; sums shifted by a sample of the window, so the cancellation is bounded by the element count.
+        // CTA-uniform and outside the unrolled statistics pass: the default mode pays one predicate.
+        const double Ks = win[col[0]];
+        double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const int t = tid + k * NT;
+          const bool valid = WCT ? ((k + 1) * NT <= WCT || t < WCT) : (t < W);
+          if (valid) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const double dv = __dsub_rn(x[k][c], Ks);
+              t1 = __dadd_rn(t1, dv);
+              t2 = __fma_rn(dv, dv, t2);
+            }
+          }
+        }
+        t1 = warp_sum(t1); t2 = warp_sum(t2);
+        if (lane == 0) { S.zred[warp][0] = t1; S.zred[warp][1] = t2; }
+        __syncthreads();
+        t1 = S.zred[0][0]; t2 = S.zred[0][1];
+#pragma unroll
+        for (int w = 1; w < NWARP; ++w) { t1 = __dadd_rn(t1, S.zred[w][0]); t2 = __dadd_rn(t2, S.zred[w][1]); }
+        __syncthreads();                                  // zred is free again before the next window writes it
+        const double inv_n = 1.0 / ((double)W * (double)C);
+        const double var_s = __dmul_rn(__dsub_rn(t2, __dmul_rn(__dmul_rn(t1, t1), inv_n)), inv_n);
+        const double var_y = __dmul_rn(syy, inv_w);
+        smin = __fma_rn(t1, inv_n, Ks);                   // from here on the four scalars are mean, std, mean, std
+        smax = sqrt(var_s > 0.0 ? var_s : 0.0);
+        ymin = __fma_rn(s1, inv_w, K);
+        ymax = sqrt(var_y > 0.0 ? var_y : 0.0);
+        if (tid == 0) {
+          double2* mm = reinterpret_cast<double2*>(P.out.minmax + 4 * M.cand);
+          mm[0] = make_double2(smin, smax);
+          mm[1] = make_double2(ymin, ymax);
+        }
+      }
       par2 ^= 1;
     } else {
       __syncthreads();  // all rows are in registers before the stage is refilled
@@ -484,8 +533,8 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
     if (keep && !pred_only) {
       if (norm_global) { smin = J.global_minmax[0]; smax = J.global_minmax[1]; ymin = J.global_minmax[2]; ymax = J.global_minmax[3]; }
       Normaliser ns, nr;
-      ns.init(smin, smax);
-      nr.init(ymin, ymax);
+      if (zscore) { ns.init_z(smin, smax); nr.init_z(ymin, ymax); }
+      else { ns.init(smin, smax); nr.init(ymin, ymax); }
       OutT* so = reinterpret_cast<OutT*>(P.out.scg_out) + (size_t)M.slot * C * W + tid;
       OutT* ro = reinterpret_cast<OutT*>(P.out.rhc_out) + (size_t)M.slot * W + tid;
       // Tier 1 (fp32 output, per-window pairs): q0 = RN(a * RN(1/d)) is within 2.5 ulp64 of the correctly

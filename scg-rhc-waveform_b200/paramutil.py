@@ -7,7 +7,7 @@ Same class, same attribute names, same ``Params(path)`` call.  Differences, all 
   * optional keys read with ``.data.get`` only (absent from all 37 shipped params.json, so shipped
     behaviour is unchanged): ``split_seed`` (reproducible train/valid/test split), ``segment_stride``
     (seconds between window starts; default = ``segment_size``, i.e. the reference's non-overlapping windows), ``noise_std`` / ``noise_seed`` (train-time
-    noise injection on SCG batches), ``bandpass`` / ``bandpass_order`` / ``bandpass_sos`` (zero-phase IIR filtering of the
+    noise injection on SCG batches), ``normalisation`` ('zscore': per-window mean/std instead of min-max), ``bandpass`` / ``bandpass_order`` / ``bandpass_sos`` (zero-phase IIR filtering of the
     SCG channels), ``resample_rate`` (model sampling rate).  With none of them present the path is the reference's.
 """
 import json
@@ -61,6 +61,7 @@ class Params:
     self.bandpass_sos = self.data.get('bandpass_sos')      # or explicit second-order sections
     self.bandpass_mode = self.data.get('bandpass_mode')    # 'exact' (default, bit-identical to scipy) | 'scan' (time-parallel)
     self.resample_rate = self.data.get('resample_rate')    # model sampling rate in Hz (native: 500)
+    self.normalisation = self.data.get('normalisation')    # 'minmax' (default = the reference) | 'zscore' (per-window mean/std)
 
   def _get(self, key):
     if key in self.data or self.strict or key not in LEGACY_DEFAULTS:

@@ -428,7 +428,7 @@ def prepare_cohort(params, record_names=None, chunk_records=32):
   if not extensions:
     ing = engine.HostIngest(plan, rows, C + 1, dev, chunk_records=chunk_records, digital_nsig=(C + 1) if digital else None)
     store = ing.run(host, list(range(C)), C, params.min_RHC, decode=(list(range(C + 1)), gains, bases) if digital else None,
-                    use_global_min_max=bool(params.use_global_min_max))
+                    use_global_min_max=bool(params.use_global_min_max), normalisation=getattr(params, 'normalisation', None))
     return store, names
   # the optional filter / resample stages work on a resident cohort
   if digital:
@@ -449,7 +449,8 @@ def prepare_cohort(params, record_names=None, chunk_records=32):
     plan = engine.plan_cohort(metas, params.chamber, rows, W, names, stride=int(stride_s * int(rate)) if stride_s else 0,
                               fs=float(int(rate)))
   store = engine.prepare_windows(arena, plan, list(range(C)), C, params.min_RHC,
-                                 use_global_min_max=bool(params.use_global_min_max))
+                                 use_global_min_max=bool(params.use_global_min_max),
+                                 normalisation=getattr(params, 'normalisation', None))
   return store, names
 
 

@@ -12,7 +12,7 @@ OK = 0
 ERR_BAD_ARG, ERR_MISSING_CHANNEL, ERR_NONFINITE_RHC, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6
 
 REASON_FLAT, REASON_STRAIGHT, REASON_FLOOR, REASON_NONFINITE, REASON_AMBIGUOUS = 1, 2, 4, 8, 16
-OUT_F64, PREDICATES_ONLY, USE_KEPT_LIST, NORM_GLOBAL, KEEP_ALL, KEEP_ERRORS = 1, 2, 4, 8, 16, 32
+OUT_F64, PREDICATES_ONLY, USE_KEPT_LIST, NORM_GLOBAL, KEEP_ALL, KEEP_ERRORS, NORM_ZSCORE = 1, 2, 4, 8, 16, 32, 64
 
 
 class Interval(C.Structure):

@@ -157,7 +157,7 @@ def resolve_columns(sig_name, in_channels):
 
 def prepare_windows(arena, plan, scg_cols, rhc_col, min_rhc, use_global_min_max=False, out_dtype=torch.float32,
                     predicates_only=False, keep_all=False, flat_threshold=FLAT_THRESHOLD, group=None,
-                    check=True, buffers=None):
+                    check=True, buffers=None, normalisation='minmax'):
   """Run the hot path over every candidate window of ``plan``.
 
   Local normalisation (default): ONE fused kernel pass — predicates, min/max, normalise, transpose,
@@ -165,14 +165,19 @@ def prepare_windows(arena, plan, scg_cols, rhc_col, min_rhc, use_global_min_max=
   + per-window pairs), device reduction (+ MIN all-reduce of {min, -max} over ``group`` when
   torch.distributed is initialised, recordutil.py:152-169 seen across shards), pass B over the kept
   list writing dense outputs.
+
+  ``normalisation='zscore'`` (extension, absent from the reference): (x - mean) / (std + 1e-4) per window, mean and
+  population std taken jointly over the SCG block and over the RHC window; the store's ``minmax`` then holds
+  (scg_mean, scg_std, rhc_mean, rhc_std).
   """
   if not arena.is_cuda:
     raise RuntimeError('prepare_windows needs a CUDA arena (no CPU fallback)')
+  zflag = _norm_flag(normalisation, use_global_min_max)
   dev = arena.device
   n, W, Cn = plan.n_cand, plan.W, len(scg_cols)
   iv = plan.device_intervals(dev)
   f64 = out_dtype == torch.float64
-  base_flags = (N.OUT_F64 if f64 else 0) | (N.KEEP_ALL if keep_all else 0)
+  base_flags = (N.OUT_F64 if f64 else 0) | (N.KEEP_ALL if keep_all else 0) | zflag
   b = buffers if buffers is not None else {}
 
   def buf(name, shape, dtype):
@@ -221,6 +226,16 @@ def prepare_windows(arena, plan, scg_cols, rhc_col, min_rhc, use_global_min_max=
     dense = True
   return WindowStore(scg, rhc, minmax, keep, reason, kept_idx[:n_kept], start_idx[:n_kept], stop_idx[:n_kept],
                      rec_id[:n_kept], n_kept, n, dense, gmm)
+
+
+def _norm_flag(normalisation, use_global_min_max):
+  if normalisation in (None, 'minmax'):
+    return 0
+  if normalisation != 'zscore':
+    raise ValueError("normalisation must be 'minmax' (the reference) or 'zscore', got %r" % (normalisation,))
+  if use_global_min_max:
+    raise ValueError("normalisation='zscore' is per window; it cannot be combined with use_global_min_max")
+  return N.NORM_ZSCORE
 
 
 def allreduce_minmax(gmm, group=None):
@@ -315,7 +330,7 @@ class HostIngest:
       done[k & 1].record(compute)
 
   def run(self, host_arena, scg_cols, rhc_col, min_rhc, out_dtype=torch.float32, flat_threshold=FLAT_THRESHOLD,
-          buffers=None, decode=None, use_global_min_max=False, group=None):
+          buffers=None, decode=None, use_global_min_max=False, group=None, normalisation='minmax'):
     """``host_arena``: (total_rows, nsig) fp64 CPU tensor (pinned for an asynchronous copy), or — with
     ``digital_nsig`` — (total_rows, digital_nsig) int16 frames plus ``decode = (cols, gain, baseline)`` where
     gain/baseline are one list per selected column (all records) or one such list per record.
@@ -337,7 +352,7 @@ class HostIngest:
     cand_win, cand_rec = buf('cand_win', (n,), torch.int32), buf('cand_rec', (n,), torch.int32)
     kept_idx, start_idx, stop_idx = (buf(k, (n,), torch.int64) for k in ('kept_idx', 'start_idx', 'stop_idx'))
     rec_id, n_kept_t = buf('rec_id', (n,), torch.int32), buf('n_kept', (1,), torch.int64)
-    base_flags = N.OUT_F64 if out_dtype == torch.float64 else 0
+    base_flags = (N.OUT_F64 if out_dtype == torch.float64 else 0) | _norm_flag(normalisation, use_global_min_max)
     scg = rhc = None
     if not use_global_min_max:
       scg, rhc = buf('scg', (n, Cn, W), out_dtype), buf('rhc', (n, 1, W), out_dtype)

@@ -171,3 +171,35 @@ def test_recordutil_optional_keys_drive_the_extension_stages(tmp_path, monkeypat
   assert fast.kept_idx.cpu().tolist() == ext.kept_idx.cpu().tolist()
   a, b = fast.materialise()[0].cpu().numpy(), ext.materialise()[0].cpu().numpy()
   assert np.abs(a - b).max() <= 1e-5                                       # normalised samples lie in [0, 1]
+
+
+@pytest.mark.parametrize('sig,chans,out_dtype,W', [(synth_ref.DEFAULT_SIG_NAMES, [0, 1, 2], torch.float32, 750),
+                                                   (synth_ref.DEFAULT_SIG_NAMES, [2, 0], torch.float64, 750),
+                                                   (synth_ref.SIG_NAMES_5, [0, 1, 2, 4], torch.float32, 300)])
+def test_zscore_normalisation_matches_numpy(sig, chans, out_dtype, W):
+  """normalisation='zscore' (the brief's mean/std normalisation; the reference only has min-max): the same keep list as
+  the default mode, samples against plain numpy — fp64 outputs within 1e-10, fp32 within rel 1e-5 (BASELINE north_star)."""
+  import scgrhc
+  from oracle import scgrhc_oracle as orc
+  T = 60000
+  p = synth_ref.gen_record(H.SEED, 97, T, kinds=synth_ref.kinds_for(sig))
+  meta = synth_ref.record_meta(120, events={'RA_1': 0, 'PA_1': 4.1, 'RV_1': 110})
+  names = [sig[c] for c in chans]
+  arena = torch.from_numpy(p).to(DEV)
+  plan = scgrhc.plan_cohort([meta], 'PA', [T], W)
+  rcol = sig.index('RHC_pressure')
+  z = scgrhc.prepare_windows(arena, plan, chans, rcol, -50.0, out_dtype=out_dtype, normalisation='zscore')
+  d = scgrhc.prepare_windows(arena, plan, chans, rcol, -50.0, out_dtype=out_dtype)
+  assert z.kept_idx.cpu().tolist() == d.kept_idx.cpu().tolist() and 0 < z.n_kept < plan.n_cand
+  rw = orc.scan_record(p, sig, meta, names, 'PA', W / 500.0, -50.0)
+  s_o, r_o, ms = orc.zscore_record(p, sig, names, rw, out_dtype=np.float64)
+  scg, rhc = z.materialise()
+  scg, rhc = scg.cpu().numpy().astype(np.float64), rhc.cpu().numpy().astype(np.float64)
+  got_ms = z.kept_minmax().cpu().numpy()
+  assert np.abs(got_ms - ms).max() <= 1e-12 * np.abs(ms).max()
+  tol = 1e-10 if out_dtype == torch.float64 else 1e-5
+  scale = max(np.abs(s_o).max(), np.abs(r_o).max())                        # z-scores: a few units
+  assert np.abs(scg - s_o).max() <= tol * scale and np.abs(rhc - r_o).max() <= tol * scale
+  assert abs(float(scg.mean())) < 1e-2 and abs(float(scg.reshape(len(scg), -1).std(axis=1).mean()) - 1.0) < 5e-2
+  with pytest.raises(ValueError):
+    scgrhc.prepare_windows(arena, plan, chans, rcol, -50.0, use_global_min_max=True, normalisation='zscore')
