@@ -556,6 +556,38 @@ extern "C" int scgrhc_resample_poly(scgrhc_ctx* ctx, const double* x, double* y,
   if (n_rec < 0 || ncols < 1 || up < 1 || down < 1 || per_phase < 1 || n_pre_remove < 0 || max_out_rows < 0 ||
       (n_rec && (!x || !y || !taps_dev || !in0_dev || !out0_dev)))
     return fail(ctx, SCGRHC_ERR_BAD_ARG, "resample_poly: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (up == 1 && ncols <= 5 && n_rec > 0 && n_rec <= 65535 && max_out_rows > 0) {   // integer decimation: register-blocked kernel
+    const int PB = kDecR * down;
+    const int rows = kDecNT * PB + per_phase;                 // input rows a tile of kDecNT * kDecR outputs touches
+    const size_t dsmem = ((((size_t)per_phase + 1) & ~size_t(1)) + (size_t)(rows + rows / PB + 2) * ncols) * sizeof(double);
+    if (dsmem <= 200 * 1024 && (long long)rows * PB < (1LL << 31)) {
+      ResampleParams P;
+      P.x = x; P.y = y; P.taps = taps_dev; P.in0 = reinterpret_cast<const long long*>(in0_dev);
+      P.out0 = reinterpret_cast<const long long*>(out0_dev);
+      P.n_rec = n_rec; P.ncols = ncols; P.up = up; P.down = down; P.per_phase = per_phase; P.n_pre_remove = n_pre_remove;
+      P.tile_rows = rows;
+      const unsigned magic = (unsigned)(((1ULL << 32) + PB - 1) / PB);   // r / PB == umulhi(r, magic) while r * PB < 2^32
+      CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+      const int tile_out = kDecNT * kDecR;
+      dim3 grid((unsigned)std::min<long long>((max_out_rows + tile_out - 1) / tile_out, 1024), (unsigned)n_rec);
+      auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, kDecNT, dsmem, st>>>(P, magic);
+        return cudaSuccess;
+      };
+      switch (ncols) {
+        case 1: CUDA_TRY(ctx, launch(resample_decim_kernel<1>)); break;
+        case 2: CUDA_TRY(ctx, launch(resample_decim_kernel<2>)); break;
+        case 3: CUDA_TRY(ctx, launch(resample_decim_kernel<3>)); break;
+        case 4: CUDA_TRY(ctx, launch(resample_decim_kernel<4>)); break;
+        default: CUDA_TRY(ctx, launch(resample_decim_kernel<5>)); break;
+      }
+      CUDA_TRY(ctx, cudaGetLastError());
+      return SCGRHC_OK;
+    }
+  }
   const int tile_rows = (int)(((long long)(kResTile - 1) * down) / up) + 2 + per_phase;
   const size_t smem = ((((size_t)up * per_phase + 1) & ~size_t(1)) + (size_t)(tile_rows | 1) * ncols) * sizeof(double);
   if (smem > 200 * 1024) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "resample_poly: %zu bytes of taps + staged rows do not fit in shared memory", smem);
@@ -566,7 +598,6 @@ extern "C" int scgrhc_resample_poly(scgrhc_ctx* ctx, const double* x, double* y,
   P.out0 = reinterpret_cast<const long long*>(out0_dev);
   P.n_rec = n_rec; P.ncols = ncols; P.up = up; P.down = down; P.per_phase = per_phase; P.n_pre_remove = n_pre_remove;
   P.tile_rows = tile_rows;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   dim3 grid((unsigned)std::min<long long>((max_out_rows + kResTile - 1) / kResTile, 1024), (unsigned)n_rec);
   auto launch = [&](auto kern) -> cudaError_t {

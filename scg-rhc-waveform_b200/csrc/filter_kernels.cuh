@@ -211,3 +211,132 @@ __global__ void __launch_bounds__(kResTile) resample_poly_kernel(const __grid_co
 }
 
 }  // namespace scgrhc
+
+namespace scgrhc {
+
+// ---- integer decimation (up == 1 after reduction: 500 -> 250 / 125 / 100 Hz), the same arithmetic, register blocked ----
+// In the general kernel every output reads its per_phase input rows from shared memory again (per_phase * ncols * 8 bytes
+// per output: shared-memory bandwidth bound, 13.7 ms per 1,000 records).  Consecutive outputs of a decimator share all
+// but `down` of their input rows, so here a thread produces kDecR consecutive outputs from ONE sliding pass over
+// per_phase + (kDecR - 1) * down rows: each row is loaded once and feeds up to kDecR accumulators, each accumulator
+// still sums its own taps oldest-sample-first with separately rounded multiply and add => still bit-identical to scipy.
+// Threads start kDecR * down rows apart; one pad row per thread span makes that stride 32 bytes mod 128, and odd
+// groups of four lanes fetch the two halves of a 32-byte row in the opposite order: conflict-free 16-byte loads.
+constexpr int kDecR = 4;      // outputs per thread
+constexpr int kDecNT = 128;   // threads per CTA: a tile is 512 outputs
+
+template <int NC>
+__global__ void __launch_bounds__(kDecNT) resample_decim_kernel(const __grid_constant__ ResampleParams P, unsigned pb_magic) {
+  extern __shared__ __align__(16) double s_dec[];
+  double* s_taps = s_dec;
+  double* s_x = s_dec + ((P.per_phase + 1) & ~1);            // padded rows of NC doubles
+  const int down = P.down, pp = P.per_phase;
+  const int PB = kDecR * down;                                // rows between the starts of neighbouring threads
+  for (int i = threadIdx.x; i < pp; i += kDecNT) s_taps[i] = P.taps[i];
+  const int rec = blockIdx.y;
+  const long long i0 = P.in0[rec], len_x = P.in0[rec + 1] - i0;
+  const long long o0 = P.out0[rec], n_out = P.out0[rec + 1] - o0;
+  const int tid = threadIdx.x;
+  const int swap = (tid >> 2) & 1;
+  for (long long tile0 = (long long)blockIdx.x * (kDecNT * kDecR); tile0 < n_out; tile0 += (long long)gridDim.x * (kDecNT * kDecR)) {
+    const long long first = (tile0 + P.n_pre_remove) * down - pp + 1;   // input row of staged row 0
+    __syncthreads();
+    // stage tile_rows input rows (zero outside the record = upfirdn's zero padding); staged row r sits at r + r / PB
+    if constexpr (NC % 2 == 0) {
+      constexpr int CH = NC / 2;                                       // 16-byte chunks per row
+      const bool aligned = ((i0 * NC) & 1) == 0;                       // always for even NC
+      for (int q = tid; q < P.tile_rows * CH; q += kDecNT) {
+        const int r = q / CH, h = q - r * CH;
+        const long long xi = first + r;
+        double2 v = make_double2(0.0, 0.0);
+        if (xi >= 0 && xi < len_x && aligned) v = *reinterpret_cast<const double2*>(P.x + (i0 + xi) * NC + 2 * h);
+        const int pr = r + (int)__umulhi((unsigned)r, pb_magic);
+        *reinterpret_cast<double2*>(s_x + (size_t)pr * NC + 2 * h) = v;
+      }
+    } else {
+      for (int q = tid; q < P.tile_rows * NC; q += kDecNT) {
+        const int r = q / NC, c = q - r * NC;
+        const long long xi = first + r;
+        const int pr = r + (int)__umulhi((unsigned)r, pb_magic);
+        s_x[(size_t)pr * NC + c] = (xi >= 0 && xi < len_x) ? P.x[(i0 + xi) * NC + c] : 0.0;
+      }
+    }
+    __syncthreads();
+    const long long mo = tile0 + (long long)tid * kDecR;
+    if (mo < n_out) {
+      double acc[kDecR][NC];
+#pragma unroll
+      for (int r = 0; r < kDecR; ++r)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[r][c] = 0.0;
+      // staged row j of this thread: tid * PB + j, at padded position tid * (PB + 1) + j + j / PB
+      const double* base = s_x + (size_t)tid * (PB + 1) * NC;
+      auto load_row = [&](int j, double (&xv)[NC]) {
+        const double* p = base + (size_t)(j + (int)__umulhi((unsigned)j, pb_magic)) * NC;
+        if constexpr (NC == 4) {
+          const double2 a = *reinterpret_cast<const double2*>(p + (swap ? 2 : 0));
+          const double2 b = *reinterpret_cast<const double2*>(p + (swap ? 0 : 2));
+          xv[0] = swap ? b.x : a.x; xv[1] = swap ? b.y : a.y; xv[2] = swap ? a.x : b.x; xv[3] = swap ? a.y : b.y;
+        } else {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) xv[c] = p[c];
+        }
+      };
+      const int J = pp + (kDecR - 1) * down;
+      int j = 0;
+      for (; j < (kDecR - 1) * down && j < J; ++j) {          // ramp-up: output r joins at j = r * down
+        double xv[NC];
+        load_row(j, xv);
+#pragma unroll
+        for (int r = 0; r < kDecR; ++r) {
+          const int k = j - r * down;
+          if (k >= 0 && k < pp) {
+            const double hk = s_taps[k];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) acc[r][c] = __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
+          }
+        }
+      }
+#pragma unroll 2
+      for (; j < pp; ++j) {                                   // steady state: every output takes this row
+        double xv[NC];
+        load_row(j, xv);
+#pragma unroll
+        for (int r = 0; r < kDecR; ++r) {
+          const double hk = s_taps[j - r * down];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) acc[r][c] = __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
+        }
+      }
+      for (; j < J; ++j) {                                    // ramp-down
+        double xv[NC];
+        load_row(j, xv);
+#pragma unroll
+        for (int r = 0; r < kDecR; ++r) {
+          const int k = j - r * down;
+          if (k >= 0 && k < pp) {
+            const double hk = s_taps[k];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) acc[r][c] = __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kDecR; ++r) {
+        if (mo + r < n_out) {
+          double* o = P.y + (o0 + mo + r) * NC;
+          if constexpr (NC % 2 == 0) {
+#pragma unroll
+            for (int c = 0; c < NC; c += 2) __stcs(reinterpret_cast<double2*>(o + c), make_double2(acc[r][c], acc[r][c + 1]));
+          } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) __stcs(o + c, acc[r][c]);
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace scgrhc
+
