@@ -181,6 +181,9 @@ static int launch_window(scgrhc_ctx* ctx, const KParams& P, long long items, cud
 template <int C, bool NSIG4, bool IDENT, typename OutT>
 static int dispatch_w(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
   if (P.job.W == 750) return launch_window<C, NSIG4, IDENT, OutT, 750>(ctx, P, items, st);  // int(1.5 * 500): all 37 configs
+  if constexpr (NSIG4 && sizeof(OutT) == 4) {
+    if (P.job.W <= 3 * NT) return launch_window<C, NSIG4, IDENT, OutT, -3>(ctx, P, items, st);  // resampled cohorts (1.5 s at <= 250 Hz)
+  }
   return launch_window<C, NSIG4, IDENT, OutT, 0>(ctx, P, items, st);
 }
 template <int C, bool NSIG4, bool IDENT>

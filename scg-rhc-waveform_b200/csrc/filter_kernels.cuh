@@ -245,14 +245,18 @@ __global__ void __launch_bounds__(kDecNT) resample_decim_kernel(const __grid_con
     if constexpr (NC % 2 == 0) {
       constexpr int CH = NC / 2;                                       // 16-byte chunks per row
       const bool aligned = ((i0 * NC) & 1) == 0;                       // always for even NC
+      // 16-byte asynchronous copies (LDGSTS) with zero fill outside the record: every copy of the tile is in flight
+      // before the first one is waited for
       for (int q = tid; q < P.tile_rows * CH; q += kDecNT) {
         const int r = q / CH, h = q - r * CH;
         const long long xi = first + r;
-        double2 v = make_double2(0.0, 0.0);
-        if (xi >= 0 && xi < len_x && aligned) v = *reinterpret_cast<const double2*>(P.x + (i0 + xi) * NC + 2 * h);
+        const bool in = xi >= 0 && xi < len_x && aligned;
+        const double* src = P.x + (i0 + (in ? xi : 0)) * NC + 2 * h;
         const int pr = r + (int)__umulhi((unsigned)r, pb_magic);
-        *reinterpret_cast<double2*>(s_x + (size_t)pr * NC + 2 * h) = v;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(s_x + (size_t)pr * NC + 2 * h)), "l"(src),
+                     "r"(in ? 16 : 0) : "memory");
       }
+      asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
       for (int q = tid; q < P.tile_rows * NC; q += kDecNT) {
         const int r = q / NC, c = q - r * NC;

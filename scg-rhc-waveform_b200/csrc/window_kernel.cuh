@@ -190,11 +190,12 @@ __global__ void __launch_bounds__(256) selftest_div_kernel(unsigned long long se
 }
 
 // C      SCG channels;  NSIG4  rows are 4 doubles (16-byte shared loads);
-// IDENT  columns are (0..C-1 | C) in order (no selects);  WCT  compile-time window length (0: runtime)
+// IDENT  columns are (0..C-1 | C) in order (no selects);  WCT  > 0: compile-time window length; 0: runtime length, RMAX rows per thread;
+//        < 0: runtime length <= -WCT * NT with -WCT rows per thread (resampled cohorts: 375 samples = 3 rows)
 template <int C, bool NSIG4, bool IDENT, typename OutT, int WCT>
 __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ KParams P) {
   static_assert(SCGRHC_FLAT_WIN == 50, "run detection below is hard-wired to 49 = 32 + 16 + 1 pairs");
-  constexpr int R = WCT ? (WCT + NT - 1) / NT : RMAX;
+  constexpr int R = WCT > 0 ? (WCT + NT - 1) / NT : (WCT < 0 ? -WCT : RMAX);
   static_assert(R * NWARP <= 32 && R <= RMAX, "one mask word per lane");
   static_assert(!IDENT || (NSIG4 && C == 3), "identity mapping is the 3 SCG + RHC record");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
 
   const scgrhc_job& J = P.job;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int W = WCT ? WCT : J.W;
+  const int W = WCT > 0 ? WCT : J.W;
   const int nsig = NSIG4 ? 4 : J.nsig;
   const int nstage = P.stages;
   const int wstride = J.stride > 0 ? J.stride : W;
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       const int t = tid + k * NT;
-      const bool valid = WCT ? ((k + 1) * NT <= WCT || t < WCT) : (t < W);
+      const bool valid = WCT > 0 ? ((k + 1) * NT <= WCT || t < WCT) : (t < W);
       y[k] = 0.0; yn[k] = 0.0;
 #pragma unroll
       for (int c = 0; c < C; ++c) x[k][c] = 0.0;
@@ -335,8 +336,8 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         const int t = tid + k * NT;
-        const bool valid = WCT ? ((k + 1) * NT <= WCT || t < WCT) : (t < W);
-        const bool has_next = WCT ? ((k + 1) * NT < WCT || t + 1 < WCT) : (t + 1 < W);
+        const bool valid = WCT > 0 ? ((k + 1) * NT <= WCT || t < WCT) : (t < W);
+        const bool has_next = WCT > 0 ? ((k + 1) * NT < WCT || t + 1 < WCT) : (t + 1 < W);
         bool cb = false;
         if (valid) {
 #pragma unroll
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
 #pragma unroll
         for (int k = 0; k < R; ++k) {
           const int t = tid + k * NT;
-          const bool valid = WCT ? ((k + 1) * NT <= WCT || t < WCT) : (t < W);
+          const bool valid = WCT > 0 ? ((k + 1) * NT <= WCT || t < WCT) : (t < W);
           if (valid) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
 #pragma unroll
           for (int k = 0; k < R; ++k) {
             const int t = tid + k * NT;
-            const bool valid = WCT ? ((k + 1) * NT <= WCT || t < WCT) : (t < W);
+            const bool valid = WCT > 0 ? ((k + 1) * NT <= WCT || t < WCT) : (t < W);
             if (valid) {
 #pragma unroll
               for (int c = 0; c < C; ++c) {
@@ -571,7 +572,7 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
 #pragma unroll
         for (int k = 0; k < R; ++k) {
           const int t = tid + k * NT;
-          const bool valid = WCT ? ((k + 1) * NT <= WCT || t < WCT) : (t < W);
+          const bool valid = WCT > 0 ? ((k + 1) * NT <= WCT || t < WCT) : (t < W);
           if (valid) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
