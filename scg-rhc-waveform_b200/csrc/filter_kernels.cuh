@@ -273,56 +273,53 @@ __global__ void __launch_bounds__(kDecNT) resample_decim_kernel(const __grid_con
       for (int r = 0; r < kDecR; ++r)
 #pragma unroll
         for (int c = 0; c < NC; ++c) acc[r][c] = 0.0;
-      // staged row j of this thread: tid * PB + j, at padded position tid * (PB + 1) + j + j / PB
+      // staged row j of this thread: tid * PB + j, at padded position tid * (PB + 1) + j + j / PB.  NC == 4: lanes whose
+      // (tid >> 2) is odd fetch the two 16-byte halves of a row in the opposite order (conflict-free) and simply keep their
+      // accumulators in that order; the columns are put back once, at the store.
       const double* base = s_x + (size_t)tid * (PB + 1) * NC;
-      auto load_row = [&](int j, double (&xv)[NC]) {
-        const double* p = base + (size_t)(j + (int)__umulhi((unsigned)j, pb_magic)) * NC;
-        if constexpr (NC == 4) {
-          const double2 a = *reinterpret_cast<const double2*>(p + (swap ? 2 : 0));
-          const double2 b = *reinterpret_cast<const double2*>(p + (swap ? 0 : 2));
-          xv[0] = swap ? b.x : a.x; xv[1] = swap ? b.y : a.y; xv[2] = swap ? a.x : b.x; xv[3] = swap ? a.y : b.y;
-        } else {
-#pragma unroll
-          for (int c = 0; c < NC; ++c) xv[c] = p[c];
-        }
-      };
-      const int J = pp + (kDecR - 1) * down;
+      const int J = pp + (kDecR - 1) * down, ramp = (kDecR - 1) * down;
       int j = 0;
-      for (; j < (kDecR - 1) * down && j < J; ++j) {          // ramp-up: output r joins at j = r * down
-        double xv[NC];
-        load_row(j, xv);
+      for (int blk = 0; j < J; ++blk) {
+        const double* pb = base + ((size_t)blk * (PB + 1) - (size_t)blk * PB) * NC;   // row j of this block: pb + j * NC
+        const int jend = min(J, (blk + 1) * PB);
+#pragma unroll 4
+        for (; j < jend; ++j) {
+          double xv[NC];
+          const double* p = pb + (size_t)j * NC;
+          if constexpr (NC == 4) {
+            const double2 a = *reinterpret_cast<const double2*>(p + (swap ? 2 : 0));
+            const double2 b = *reinterpret_cast<const double2*>(p + (swap ? 0 : 2));
+            xv[0] = a.x; xv[1] = a.y; xv[2] = b.x; xv[3] = b.y;
+          } else {
 #pragma unroll
-        for (int r = 0; r < kDecR; ++r) {
-          const int k = j - r * down;
-          if (k >= 0 && k < pp) {
-            const double hk = s_taps[k];
+            for (int c = 0; c < NC; ++c) xv[c] = p[c];
+          }
+          if (j >= ramp && j < pp) {                          // steady state: every output takes this row
 #pragma unroll
-            for (int c = 0; c < NC; ++c) acc[r][c] = __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
+            for (int r = 0; r < kDecR; ++r) {
+              const double hk = s_taps[j - r * down];
+#pragma unroll
+              for (int c = 0; c < NC; ++c) acc[r][c] = __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
+            }
+          } else {                                            // ramp-up / ramp-down: output r takes rows r*down .. r*down + pp - 1
+#pragma unroll
+            for (int r = 0; r < kDecR; ++r) {
+              const int k = j - r * down;
+              if (k >= 0 && k < pp) {
+                const double hk = s_taps[k];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) acc[r][c] = __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
+              }
+            }
           }
         }
       }
-#pragma unroll 2
-      for (; j < pp; ++j) {                                   // steady state: every output takes this row
-        double xv[NC];
-        load_row(j, xv);
+      if constexpr (NC == 4) {
 #pragma unroll
         for (int r = 0; r < kDecR; ++r) {
-          const double hk = s_taps[j - r * down];
-#pragma unroll
-          for (int c = 0; c < NC; ++c) acc[r][c] = __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
-        }
-      }
-      for (; j < J; ++j) {                                    // ramp-down
-        double xv[NC];
-        load_row(j, xv);
-#pragma unroll
-        for (int r = 0; r < kDecR; ++r) {
-          const int k = j - r * down;
-          if (k >= 0 && k < pp) {
-            const double hk = s_taps[k];
-#pragma unroll
-            for (int c = 0; c < NC; ++c) acc[r][c] = __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
-          }
+          const double t0 = acc[r][0], t1 = acc[r][1];
+          acc[r][0] = swap ? acc[r][2] : t0; acc[r][1] = swap ? acc[r][3] : t1;
+          acc[r][2] = swap ? t0 : acc[r][2]; acc[r][3] = swap ? t1 : acc[r][3];
         }
       }
 #pragma unroll
