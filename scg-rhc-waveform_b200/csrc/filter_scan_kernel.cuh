@@ -223,8 +223,8 @@ struct TpWarp {
       }
       // inclusive scan over the lanes: f_t <- state at the END of chunk t (A is block lower triangular: a section's
       // delay elements depend on the sections before it only)
-#pragma unroll 1
-      for (int k = 0; k < 5; ++k) {                     // a real loop: five unrolled matrix steps would not fit the instruction cache
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {                     // unrolled: the next step's matrix loads overlap this step's FMAs
         double g[CPW][D];
 #pragma unroll
         for (int j = 0; j < CPW; ++j)
@@ -252,7 +252,7 @@ struct TpWarp {
           if (lane > 0) z[j][a >> 1][a & 1] = up;
         }
       // pass B: the chunk from its true state, outputs over the inputs
-#pragma unroll 2
+#pragma unroll 4
       for (int i = 0; i < l; ++i) {
         double* row = chunk + (PASS == 0 ? i : l - 1 - i) * nc;
         double v[CPW];
