@@ -545,8 +545,28 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
       // to tier 2 and rewrites its elements.  |mn| >= 2^-10 keeps every non-zero quotient >= 2^-124, above
       // the float subnormal range where the boundary pattern differs.
       bool redo = true;
+      if (zscore && !(ns.slow || nr.slow)) {
+        // extension: no bit-exact contract here; RN(a * RN(1/d)) is within 2.5 ulp64 of the quotient (1e-10 / 1e-5 bars)
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const int t = tid + k * NT;
+          const bool valid = WCT > 0 ? ((k + 1) * NT <= WCT || t < WCT) : (t < W);
+          if (valid) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              OutT o;
+              cvt_out(o, __dmul_rn(__dsub_rn(x[k][c], ns.mn), ns.inv));
+              st_cs(so + (size_t)c * W + k * NT, o);
+            }
+            OutT o;
+            cvt_out(o, __dmul_rn(__dsub_rn(y[k], nr.mn), nr.inv));
+            st_cs(ro + k * NT, o);
+          }
+        }
+        redo = false;
+      }
       if constexpr (sizeof(OutT) == 4) {
-        if (!use_list && !norm_global && ns.quick && nr.quick) {
+        if (!zscore && !use_list && !norm_global && ns.quick && nr.quick) {
           uint32_t acc = 0xffffffffu;
 #pragma unroll
           for (int k = 0; k < R; ++k) {
