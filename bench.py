@@ -282,6 +282,10 @@ def run_b200(args):
   world = int(os.environ.get('WORLD_SIZE', '1'))
   rank = int(os.environ.get('RANK', '0'))
   local = int(os.environ.get('LOCAL_RANK', '0'))
+  # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner) go to stderr
+  sys.stdout.flush()
+  json_fd = os.dup(1)
+  os.dup2(2, 1)
   if not torch.cuda.is_available():
     raise RuntimeError('bench.py needs a CUDA device: the hot path has no CPU fallback')
   torch.cuda.set_device(local)
@@ -568,7 +572,8 @@ def run_b200(args):
             'gpu_launches': args.steps * (4 + (2 if args.global_minmax else 0)),
             'launches_per_step': 'window_kernel + count_kept + scan_blocks + scatter_kept',
             'batch256': batch256, 'north_star_pipeline': pipeline, 'numa_bound_cpus': numa_cpus, 'clocks': clocks, 'clocks_e2e': clocks_e2e}
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + '\n').encode())
   if world > 1:
     dist.destroy_process_group()
 
