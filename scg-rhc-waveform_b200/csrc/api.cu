@@ -649,9 +649,24 @@ extern "C" int scgrhc_decode_fmt16(scgrhc_ctx* ctx, const int16_t* d, int64_t T,
   if (T == 0) return SCGRHC_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  const long long total = T * ncols;
-  const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16);
-  decode_fmt16_kernel<<<grid, 256, 0, st>>>(P);
+  bool fast = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  for (int j = 0; j < ncols; ++j)
+    fast = fast && std::fabs(gain[j]) >= 0x1p-40 && std::fabs(gain[j]) <= 0x1p60 && std::fabs(baseline[j]) < 65536.0 &&
+           baseline[j] == std::floor(baseline[j]);             // wfdb baselines are integers: d - baseline is exact
+  if (fast) {
+    const unsigned rgrid = (unsigned)std::min<long long>((T + 255) / 256, (long long)ctx->sm_count * 16);
+    switch (ncols) {
+      case 1: decode_fmt16_rows_kernel<1><<<rgrid, 256, 0, st>>>(P); break;
+      case 2: decode_fmt16_rows_kernel<2><<<rgrid, 256, 0, st>>>(P); break;
+      case 3: decode_fmt16_rows_kernel<3><<<rgrid, 256, 0, st>>>(P); break;
+      case 4: decode_fmt16_rows_kernel<4><<<rgrid, 256, 0, st>>>(P); break;
+      default: decode_fmt16_rows_kernel<5><<<rgrid, 256, 0, st>>>(P); break;
+    }
+  } else {
+    const long long total = T * ncols;
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16);
+    decode_fmt16_kernel<<<grid, 256, 0, st>>>(P);
+  }
   CUDA_TRY(ctx, cudaGetLastError());
   return SCGRHC_OK;
 }

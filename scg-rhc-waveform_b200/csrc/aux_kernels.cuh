@@ -191,6 +191,49 @@ __global__ void __launch_bounds__(256) decode_fmt16_kernel(const __grid_constant
   }
 }
 
+// One frame per thread: the frame's samples come in with one 8-byte load when it is 4 x int16 (else per column), every
+// output row goes out with 16-byte stores, and the IEEE quotient comes from the column's correctly rounded reciprocal
+// with two FMA residual corrections (div_by_recip, validated against __ddiv_rn in scgrhc_selftest_div) instead of a full
+// division per sample.  The host selects it when every gain is a normal number in [2^-40, 2^60] (then no intermediate
+// can underflow: |d - baseline| is 0 or >= 2^-36 for |baseline| < 2^16).
+template <int NC>
+__global__ void __launch_bounds__(256) decode_fmt16_rows_kernel(const __grid_constant__ DecodeParams P) {
+  double inv[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) inv[j] = __drcp_rn(P.gain[j]);
+  const bool frame4 = P.nsig_in == 4 && (reinterpret_cast<uintptr_t>(P.d) & 7) == 0;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < P.T; t += (long long)gridDim.x * blockDim.x) {
+    short dv[NC];
+    if (frame4) {
+      const short4 f = __ldcs(reinterpret_cast<const short4*>(P.d) + t);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int c = P.cols[j];
+        dv[j] = c == 0 ? f.x : (c == 1 ? f.y : (c == 2 ? f.z : f.w));
+      }
+    } else {
+      const short* row = P.d + t * P.nsig_in;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) dv[j] = row[P.cols[j]];
+    }
+    double v[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const double q = div_by_recip(__dsub_rn((double)dv[j], P.baseline[j]), P.gain[j], inv[j]);
+      v[j] = dv[j] == -32768 ? qnan : q;
+    }
+    double* o = P.out + t * NC;
+    if constexpr (NC % 2 == 0) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 2) __stcs(reinterpret_cast<double2*>(o + j), make_double2(v[j], v[j + 1]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) __stcs(o + j, v[j]);
+    }
+  }
+}
+
 // ---- extension (north star, absent from the reference): train-time noise injection fused into the batch gather.
 // Counter-based Philox4x32-10 (Salmon et al., Random123; the cuRAND-style 4x32 variant, NOT numpy's 4x64):
 // key = seed, counter = (block index of the element quad, stream offset).  Element j of the batch takes word j&3

@@ -72,6 +72,18 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Correctly rounded a/d from the correctly rounded reciprocal inv = RN(1/d) (Markstein): two FMA
+// residual corrections.  Valid when no intermediate underflows; the caller guarantees that per window
+// (see Normaliser::slow).  Validated against IEEE division in tests (scgrhc_selftest_div).
+__device__ __forceinline__ double div_by_recip(double a, double d, double inv) {
+  double q = __dmul_rn(a, inv);
+  double r = __fma_rn(-d, q, a);
+  q = __fma_rn(r, inv, q);
+  r = __fma_rn(-d, q, a);
+  q = __fma_rn(r, inv, q);
+  return q;
+}
+
 // streaming stores (outputs are written once and not re-read by this kernel)
 __device__ __forceinline__ void st_cs(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_cs(double* p, double v) { __stcs(p, v); }

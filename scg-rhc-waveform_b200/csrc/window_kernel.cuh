@@ -69,18 +69,6 @@ struct Scratch {
   double zred[NWARP][2];             // extension: shifted SCG sums of the z-score mode
 };
 
-// Correctly rounded a/d from the correctly rounded reciprocal inv = RN(1/d) (Markstein): two FMA
-// residual corrections.  Valid when no intermediate underflows; the caller guarantees that per window
-// (see Normaliser::slow).  Validated against IEEE division in tests (scgrhc_selftest_div).
-__device__ __forceinline__ double div_by_recip(double a, double d, double inv) {
-  double q = __dmul_rn(a, inv);
-  double r = __fma_rn(-d, q, a);
-  q = __fma_rn(r, inv, q);
-  r = __fma_rn(-d, q, a);
-  q = __fma_rn(r, inv, q);
-  return q;
-}
-
 struct Normaliser {
   double mn, d, inv;
   bool slow, quick;
