@@ -143,6 +143,24 @@ int scgrhc_plan_record(const double* event_time, const uint8_t* event_match, int
  *      waveform_noise.py:6-49).  Asynchronous. */
 int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, const scgrhc_outputs* out, void* stream);
 
+/* ---- sweep fan-out (the loadable waveform_NN configs are 4 chambers x 8 channel subsets; for one
+ *      chamber has_noise() looks at the RHC channel only, waveform_noise.py:44-49): after ONE predicate pass
+ *      (SCGRHC_PREDICATES_ONLY) and scgrhc_compact_kept, normalise every kept window for up to SCGRHC_MAX_SUBSETS channel
+ *      subsets in one pass: SCGDataset.init_segments (recordutil.py:55-66) per subset, the window read once.
+ *      job: scg_cols[0..C) = the superset of channels (C <= SCGRHC_MAX_C), kept_list / n_items = the kept candidates,
+ *      flags: only SCGRHC_OUT_F64 is looked at.  Subset k takes the superset columns member[0..C) (ascending) in that
+ *      channel order; scg_out (n_items, C, W), minmax (n_items, 4) dense in list order; rhc_out (n_items, 1, W) is
+ *      written once for all subsets.  Outputs are bit-identical to scgrhc_process_windows run per subset. */
+#define SCGRHC_MAX_SUBSETS 8
+typedef struct {
+  void* scg_out;                  /* device (n_items, C, W) fp32|fp64 */
+  double* minmax;                 /* device (n_items, 4) */
+  int32_t C;
+  int32_t member[SCGRHC_MAX_C];   /* indices into job->scg_cols, strictly ascending */
+} scgrhc_subset;
+int scgrhc_normalize_subsets(scgrhc_ctx* ctx, const scgrhc_job* job, const scgrhc_subset* subsets, int32_t n_subsets,
+                             void* rhc_out, void* stream);
+
 /* ---- ordered list of kept windows (the order of the list get_segments returns, recordutil.py:148) */
 int scgrhc_compact_kept(scgrhc_ctx* ctx, const uint8_t* keep, const int32_t* cand_win, const int32_t* cand_rec,
                         int64_t n_cand, int32_t W, const scgrhc_compact* out, void* stream);

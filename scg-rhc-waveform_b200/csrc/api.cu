@@ -14,6 +14,7 @@
 #include "filter_kernels.cuh"
 #include "filter_scan_kernel.cuh"
 #include "window_kernel.cuh"
+#include "subset_kernel.cuh"
 
 using namespace scgrhc;
 
@@ -251,6 +252,57 @@ extern "C" int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, co
     case 3: return dispatch_nsig<3>(ctx, P, items, st);
     default: return dispatch_nsig<4>(ctx, P, items, st);
   }
+}
+
+extern "C" int scgrhc_normalize_subsets(scgrhc_ctx* ctx, const scgrhc_job* job, const scgrhc_subset* subsets, int32_t n_subsets,
+                                        void* rhc_out, void* stream) {
+  NvtxRange nvtx_range("scgrhc_normalize_subsets");
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (!job || !subsets || n_subsets < 1 || n_subsets > SCGRHC_MAX_SUBSETS) return fail(ctx, SCGRHC_ERR_BAD_ARG, "normalize_subsets: 1..%d subsets", SCGRHC_MAX_SUBSETS);
+  const scgrhc_job& J = *job;
+  if (J.C < 1 || J.C > SCGRHC_MAX_C) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "C=%d superset channels (supported 1..%d)", J.C, SCGRHC_MAX_C);
+  if (J.nsig < 1 || J.nsig > SCGRHC_MAX_NSIG) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "nsig=%d (supported 1..%d)", J.nsig, SCGRHC_MAX_NSIG);
+  if (J.W < 2 || J.W > RMAX * NT) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "window of %d samples (supported 2..%d)", J.W, RMAX * NT);
+  if (J.rhc_col < 0 || J.rhc_col >= J.nsig) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "RHC column %d outside 0..%d", J.rhc_col, J.nsig - 1);
+  for (int c = 0; c < J.C; ++c)
+    if (J.scg_cols[c] < 0 || J.scg_cols[c] >= J.nsig) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "SCG column %d outside 0..%d", J.scg_cols[c], J.nsig - 1);
+  if (J.n_items < 0 || J.n_intervals < 0 || J.stride < 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "negative counts");
+  if ((reinterpret_cast<uintptr_t>(J.arena) & 15) != 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "arena must be 16-byte aligned");
+  if (J.arena_capacity_bytes < J.arena_rows * (int64_t)J.nsig * 8) return fail(ctx, SCGRHC_ERR_BAD_ARG, "arena_capacity_bytes smaller than the arena");
+  if (J.n_items == 0) return SCGRHC_OK;
+  if (!J.kept_list || !J.intervals || J.n_intervals == 0 || !rhc_out) return fail(ctx, SCGRHC_ERR_BAD_ARG, "normalize_subsets: kept_list, intervals and rhc_out are required");
+  SubsetParams P;
+  P.job = J;
+  P.rhc_out = rhc_out;
+  P.n_sub = n_subsets;
+  for (int k = 0; k < n_subsets; ++k) {
+    const scgrhc_subset& U = subsets[k];
+    if (U.C < 1 || U.C > J.C || !U.scg_out || !U.minmax) return fail(ctx, SCGRHC_ERR_BAD_ARG, "normalize_subsets: subset %d is malformed", k);
+    int mask = 0;
+    for (int i = 0; i < U.C; ++i) {
+      if (U.member[i] < 0 || U.member[i] >= J.C || (i && U.member[i] <= U.member[i - 1]))
+        return fail(ctx, SCGRHC_ERR_BAD_ARG, "normalize_subsets: subset %d members must be strictly ascending superset indices", k);
+      mask |= 1 << U.member[i];
+    }
+    P.sub[k].scg_out = U.scg_out; P.sub[k].minmax = U.minmax; P.sub[k].mask = mask; P.sub[k].C = U.C;
+  }
+  P.stage_elems = (int)(((long long)J.W * J.nsig + J.nsig + 2 + 1) & ~1LL);
+  P.arena_elems_cap = J.arena_capacity_bytes / 8;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t smem = ((sizeof(SubsetScratch) + 127) & ~size_t(127)) + (size_t)2 * P.stage_elems * sizeof(double);
+  auto launch = [&](auto kern) -> int {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    if (occ < 1) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "window of %d samples x %d signals does not fit in shared memory (%zu B/CTA)", J.W, J.nsig, smem);
+    const long long grid = std::min<long long>(J.n_items, (long long)ctx->sm_count * occ);
+    kern<<<(unsigned)grid, NT, smem, st>>>(P);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SCGRHC_OK;
+  };
+  if (J.flags & SCGRHC_OUT_F64) return launch(subset_norm_kernel<double>);
+  return launch(subset_norm_kernel<float>);
 }
 
 extern "C" int scgrhc_check_errors(scgrhc_ctx* ctx, void* stream, int64_t* first_bad_cand) {

@@ -429,12 +429,31 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
             for (int c = 0; c < C; ++c) if (x[k][c] != x[k][c]) fl |= 2;
           }
         }
+        if (s2_bad) {
+          // s2 carries the 0*v terms of the SCG columns, so a NaN/Inf SCG sample has poisoned it; has_noise() looks at the
+          // RHC channel only (waveform_noise.py:44-49): redo the RHC sum of squares alone, in the order of the common path
+          double t2 = 0.0;
+#pragma unroll
+          for (int k = 0; k < R; ++k) {
+            if (tid + k * NT < W) {
+              const double dy = __dsub_rn(y[k], K);
+              t2 = __fma_rn(dy, dy, t2);
+            }
+          }
+          t2 = warp_sum(t2);
+          if (lane == 0) S.zred[warp][0] = t2;
+        }
         if (cnt) atomicAdd(&S.slow_cnt, cnt);
         if (fl) atomicOr(&S.slow_flag, fl);
         __syncthreads();
         flat_cnt = S.slow_cnt;
         nonfinite = (S.slow_flag & 1) != 0;
         if (S.slow_flag & 2) { smin = qnan; smax = qnan; }
+        if (s2_bad) {
+          s2 = S.zred[0][0];
+#pragma unroll
+          for (int w = 1; w < NWARP; ++w) s2 = __dadd_rn(s2, S.zred[w][0]);
+        }
         __syncthreads();
         if (tid == 0) { S.slow_cnt = 0; S.slow_flag = 0; }
       }

@@ -7,6 +7,7 @@ from . import build as _build
 
 MAX_C = 4
 MAX_NSIG = 64
+MAX_SUBSETS = 8
 
 OK = 0
 ERR_BAD_ARG, ERR_MISSING_CHANNEL, ERR_NONFINITE_RHC, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6
@@ -33,6 +34,10 @@ class Outputs(C.Structure):
               ('reason', C.c_void_p), ('cand_win', C.c_void_p), ('cand_rec', C.c_void_p)]
 
 
+class Subset(C.Structure):
+  _fields_ = [('scg_out', C.c_void_p), ('minmax', C.c_void_p), ('C', C.c_int32), ('member', C.c_int32 * MAX_C)]
+
+
 class Compact(C.Structure):
   _fields_ = [('kept_idx', C.c_void_p), ('start_idx', C.c_void_p), ('stop_idx', C.c_void_p),
               ('rec_id', C.c_void_p), ('n_kept', C.c_void_p), ('stride', C.c_int32), ('reserved', C.c_int32)]
@@ -50,7 +55,7 @@ _lib = None
 # every symbol include/scgrhc.h declares (tests check the library exports all of them)
 SYMBOLS = ['scgrhc_abi_version', 'scgrhc_ctx_create', 'scgrhc_ctx_destroy', 'scgrhc_last_error',
            'scgrhc_ctx_set_tuning', 'scgrhc_ctx_sm_count', 'scgrhc_plan_record', 'scgrhc_process_windows',
-           'scgrhc_compact_kept', 'scgrhc_global_minmax', 'scgrhc_check_errors', 'scgrhc_gather_windows',
+           'scgrhc_compact_kept', 'scgrhc_normalize_subsets', 'scgrhc_global_minmax', 'scgrhc_check_errors', 'scgrhc_gather_windows',
            'scgrhc_window_metrics', 'scgrhc_sosfiltfilt', 'scgrhc_sosfiltfilt_scan', 'scgrhc_resample_poly', 'scgrhc_gather_windows_noise', 'scgrhc_philox_words', 'scgrhc_rolling_range_lt', 'scgrhc_decode_fmt16', 'scgrhc_waveform_stats', 'scgrhc_synth_records', 'scgrhc_selftest_div']
 
 
@@ -77,6 +82,7 @@ def lib():
                                    C.POINTER(Interval), C.c_int, C.POINTER(C.c_int), C.POINTER(i64),
                                    C.POINTER(i64), C.c_int, C.POINTER(C.c_int)]
   L.scgrhc_process_windows.argtypes = [vp, C.POINTER(Job), C.POINTER(Outputs), vp]
+  L.scgrhc_normalize_subsets.argtypes = [vp, C.POINTER(Job), C.POINTER(Subset), i32, vp, vp]
   L.scgrhc_compact_kept.argtypes = [vp, vp, vp, vp, i64, i32, C.POINTER(Compact), vp]
   L.scgrhc_global_minmax.argtypes = [vp, vp, vp, i64, vp, vp]
   L.scgrhc_check_errors.argtypes = [vp, vp, C.POINTER(i64)]

@@ -122,6 +122,7 @@ class WindowStore:
   n_cand: int
   dense: bool
   global_minmax: Optional[torch.Tensor] = None   # (4,) fp64 when use_global_min_max
+  minmax_dense: bool = False                     # minmax rows are in list order (sweep fan-out), not per candidate
 
   def slots(self):
     return torch.arange(self.n_kept, device=self.kept_idx.device) if self.dense else self.kept_idx
@@ -129,6 +130,8 @@ class WindowStore:
   def kept_minmax(self):
     if self.global_minmax is not None:
       return self.global_minmax.unsqueeze(0).expand(self.n_kept, 4)
+    if self.minmax_dense:
+      return self.minmax[:self.n_kept]
     return self.minmax[self.kept_idx]
 
   def gather(self, positions):
@@ -226,6 +229,45 @@ def prepare_windows(arena, plan, scg_cols, rhc_col, min_rhc, use_global_min_max=
     dense = True
   return WindowStore(scg, rhc, minmax, keep, reason, kept_idx[:n_kept], start_idx[:n_kept], stop_idx[:n_kept],
                      rec_id[:n_kept], n_kept, n, dense, gmm)
+
+
+def prepare_subsets(arena, plan, sup_cols, rhc_col, min_rhc, subsets, out_dtype=torch.float32,
+                    flat_threshold=FLAT_THRESHOLD, check=True):
+  """Sweep fan-out: several channel subsets of one cohort / chamber in two passes instead of one fused
+  pass per subset.  ``sup_cols``: the superset of SCG columns (<= 4, arena column indices); ``subsets``: lists of arena
+  column indices, each a subsequence of ``sup_cols`` (channel order = that order).  has_noise() looks at the RHC
+  channel only (waveform_noise.py:44-49), so ONE predicate pass serves every subset; then every kept window is read
+  once and written per subset (`scgrhc_normalize_subsets`).  Returns one dense WindowStore per subset; they share the
+  RHC tensor, the keep flags and the kept list.  Outputs are bit-identical to ``prepare_windows`` per subset."""
+  if not arena.is_cuda:
+    raise RuntimeError('prepare_subsets needs a CUDA arena (no CPU fallback)')
+  sup = list(sup_cols)
+  members, counts = [], []
+  for sub in subsets:
+    idx = [sup.index(c) for c in sub]
+    if idx != sorted(idx) or len(set(idx)) != len(idx) or not idx:
+      raise ValueError('subset %r is not a subsequence of the superset %r' % (list(sub), sup))
+    members += idx
+    counts.append(len(idx))
+  dev = arena.device
+  pred = prepare_windows(arena, plan, sup[:1], rhc_col, min_rhc, predicates_only=True, flat_threshold=flat_threshold,
+                         check=check)
+  n_kept, W = pred.n_kept, plan.W
+  rhc = torch.empty((n_kept, 1, W), dtype=out_dtype, device=dev)
+  scgs = [torch.empty((n_kept, c, W), dtype=out_dtype, device=dev) for c in counts]
+  mms = [torch.empty((n_kept, 4), dtype=torch.float64, device=dev) for _ in counts]
+  stores = []
+  for g0 in range(0, len(counts), N.MAX_SUBSETS):
+    g1 = min(len(counts), g0 + N.MAX_SUBSETS)
+    if n_kept:
+      m0 = sum(counts[:g0])
+      ops.normalize_subsets(arena, plan.device_intervals(dev), W, plan.stride, sup, rhc_col, pred.kept_idx, n_kept,
+                            members[m0:m0 + sum(counts[g0:g1])], counts[g0:g1], out_dtype == torch.float64,
+                            scgs[g0:g1], mms[g0:g1], rhc)
+  for scg, mm in zip(scgs, mms):
+    stores.append(WindowStore(scg, rhc, mm, pred.keep, pred.reason, pred.kept_idx, pred.start_idx, pred.stop_idx,
+                              pred.rec_id, n_kept, pred.n_cand, True, None, True))
+  return stores
 
 
 def _norm_flag(normalisation, use_global_min_max):

@@ -4,7 +4,7 @@ Only CUDA implementations are registered: calling an op on CPU tensors raises, t
 fallback.  torch supplies device memory and the current stream; all arithmetic is in the library.
 """
 import ctypes as C
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 from torch import Tensor
@@ -123,6 +123,53 @@ def compact_kept(keep: Tensor, cand_win: Tensor, cand_rec: Tensor, n_cand: int, 
   co = N.Compact(_ptr(kept_idx), _ptr(start_idx), _ptr(stop_idx), _ptr(rec_id), _ptr(n_kept), stride, 0)
   c = ctx(dev)
   N.check(c, N.lib().scgrhc_compact_kept(c, _ptr(keep), _ptr(cand_win), _ptr(cand_rec), n_cand, W, C.byref(co), _stream(dev)))
+
+
+@torch.library.custom_op('scgrhc::normalize_subsets', mutates_args=('scg_outs', 'minmaxes', 'rhc_out'), device_types='cuda')
+def normalize_subsets(arena: Tensor, intervals: Tensor, W: int, stride: int, sup_cols: Sequence[int], rhc_col: int,
+                      kept_list: Tensor, n_items: int, members: Sequence[int], member_counts: Sequence[int], out_f64: bool,
+                      scg_outs: List[Tensor], minmaxes: List[Tensor], rhc_out: Tensor) -> None:
+  """Sweep fan-out: SCGDataset.init_segments (recordutil.py:55-66) for several channel subsets of one superset over the
+  kept windows of one predicate pass; subset k = members[sum(counts[:k]) : sum(counts[:k+1])] (ascending indices into
+  ``sup_cols``).  Dense outputs in list order; bit-identical to process_windows run per subset."""
+  dev = _dev(arena)
+  _contig(arena, torch.float64, 'arena'); _contig(intervals, torch.int64, 'intervals'); _contig(kept_list, torch.int64, 'kept_list')
+  out_dtype = torch.float64 if out_f64 else torch.float32
+  _contig(rhc_out, out_dtype, 'rhc_out')
+  if len(member_counts) != len(scg_outs) or len(scg_outs) != len(minmaxes) or not 1 <= len(scg_outs) <= N.MAX_SUBSETS:
+    raise ValueError('1..%d subsets, one scg_out and one minmax each' % N.MAX_SUBSETS)
+  if len(sup_cols) > N.MAX_C:
+    raise N.ScgrhcError(N.ERR_UNSUPPORTED, 'at most %d superset channels' % N.MAX_C)
+  j = N.Job()
+  j.arena = arena.data_ptr()
+  j.arena_rows = arena.shape[0]
+  j.arena_capacity_bytes = arena.numel() * 8
+  j.nsig = arena.shape[1]
+  j.W = W
+  j.stride = stride
+  j.C = len(sup_cols)
+  for i, c in enumerate(sup_cols):
+    j.scg_cols[i] = c
+  j.rhc_col = rhc_col
+  j.flags = N.OUT_F64 if out_f64 else 0
+  j.intervals = intervals.data_ptr()
+  j.n_intervals = intervals.shape[0]
+  j.kept_list = kept_list.data_ptr()
+  j.n_items = n_items
+  if kept_list.numel() < n_items or rhc_out.numel() < n_items * W:
+    raise ValueError('kept_list / rhc_out too small for %d windows' % n_items)
+  subs = (N.Subset * len(scg_outs))()
+  at = 0
+  for k, cnt in enumerate(member_counts):
+    _contig(scg_outs[k], out_dtype, 'scg_out'); _contig(minmaxes[k], torch.float64, 'minmax')
+    if scg_outs[k].numel() < n_items * cnt * W or minmaxes[k].numel() < n_items * 4:
+      raise ValueError('subset %d outputs too small' % k)
+    subs[k].scg_out = scg_outs[k].data_ptr(); subs[k].minmax = minmaxes[k].data_ptr(); subs[k].C = cnt
+    for i in range(cnt):
+      subs[k].member[i] = members[at + i]
+    at += cnt
+  c = ctx(dev)
+  N.check(c, N.lib().scgrhc_normalize_subsets(c, C.byref(j), subs, len(scg_outs), _ptr(rhc_out), _stream(dev)))
 
 
 @torch.library.custom_op('scgrhc::global_minmax', mutates_args=('mm_out',), device_types='cuda')

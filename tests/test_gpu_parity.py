@@ -92,8 +92,10 @@ def test_record_small_golden_bit_exact(cfg):
   assert rhc.cpu().numpy().tobytes() == g[cfg + '.rhc'].tobytes()
 
 
-def test_records_full_golden_all_configs():
-  """All 36 runnable configs as ONE sweep job over a device-resident cohort (BASELINE configs[4])."""
+@pytest.mark.parametrize('fan_out', [True, False])
+def test_records_full_golden_all_configs(fan_out):
+  """All 36 runnable configs as ONE sweep job over a device-resident cohort (BASELINE configs[4]): with the fan-out pass
+  (one predicate pass + one normalisation pass per chamber for its 8 channel subsets) and with one fused pass per config."""
   import types
   from scgrhc import sweep
   full = H.load_json('records_full.json')
@@ -105,8 +107,10 @@ def test_records_full_golden_all_configs():
   configs = {cfg: types.SimpleNamespace(**H.effective_config(cfg, table)) for cfg in full['configs']}
   assert len(configs) == 36
   seen = 0
-  for cfg, st in sweep.iter_sweep(arena, sig, metas, [300000, 300000], configs, buffers={}):
+  dense = 0
+  for cfg, st in sweep.iter_sweep(arena, sig, metas, [300000, 300000], configs, buffers={}, fan_out=fan_out):
     entry, c = full['configs'][cfg], configs[cfg]
+    dense += bool(st.minmax_dense)
     if c.use_global_min_max:
       assert [float(v).hex() for v in st.global_minmax.cpu().tolist()] == entry['global_minmax_hex']
     scg, rhc = st.materialise()
@@ -124,6 +128,9 @@ def test_records_full_golden_all_configs():
       assert H.sha(rhc[m]) == want['rhc_sha'], (cfg, name)
     seen += 1
   assert seen == 36
+  # 4 chambers x 8 channel subsets + the legacy 02/03/05 (same channels, no pressure floor) went through the fan-out pass;
+  # waveform_04 (dataset-level min/max) takes its own two passes
+  assert dense == (35 if fan_out else 0)
 
 
 @pytest.mark.parametrize('nsig,out_dtype', [(4, torch.float32), (4, torch.float64), (5, torch.float32), (7, torch.float64)])
@@ -372,3 +379,67 @@ def test_host_ingest_chunked_equals_resident(tmp_path):
   assert st.n_kept == ref2.n_kept > 0 and torch.equal(st.kept_idx, ref2.kept_idx)
   a, b = st.materialise(), ref2.materialise()
   assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+@pytest.mark.parametrize('nsig,out_dtype,W', [(5, torch.float32, 750), (4, torch.float64, 750), (7, torch.float32, 333), (5, torch.float32, 1024)])
+def test_subset_fan_out_equals_one_pass_per_subset(nsig, out_dtype, W):
+  """scgrhc_normalize_subsets (the window read once, written for every channel subset) against scgrhc_process_windows per
+  subset, bit for bit — NaN and Inf planted in SCG columns (np.min/np.max poisoning per subset), a constant column
+  (IEEE-division tier), 9 subsets (two launches)."""
+  import scgrhc
+  sig = (synth_ref.SIG_NAMES_5 + ['x5', 'x6'])[:nsig] if nsig != 4 else synth_ref.DEFAULT_SIG_NAMES
+  kinds = synth_ref.kinds_for(sig)
+  T, n_rec = 40000, 3
+  meta = synth_ref.record_meta(80, events={'RA_1': 0, 'PA_1': 3.3, 'RV_1': 71})
+  recs = [synth_ref.gen_record(H.SEED, 300 + r, T, kinds=kinds) for r in range(n_rec)]
+  recs[0][5000, 1] = np.nan
+  recs[1][9000:9010, 0] = np.inf
+  recs[2][12000:16000, 2] = 0.0
+  arena = torch.from_numpy(np.concatenate(recs)).to(DEV)
+  plan = scgrhc.plan_cohort([meta] * n_rec, 'PA', [T] * n_rec, W)
+  rcol = sig.index('RHC_pressure')
+  sup = [c for c in range(nsig) if c != rcol][:4]
+  subsets = [sup, sup[:2], sup[1:3], [sup[0], sup[2]], [sup[0]], [sup[1]], [sup[2]], sup[:3], [sup[-1]]]
+  stores = scgrhc.prepare_subsets(arena, plan, sup, rcol, -50.0, subsets, out_dtype=out_dtype)
+  assert len(stores) == len(subsets)
+  for sub, st in zip(subsets, stores):
+    ref = scgrhc.prepare_windows(arena, plan, sub, rcol, -50.0, out_dtype=out_dtype)
+    assert st.n_kept == ref.n_kept and 0 < st.n_kept < plan.n_cand
+    assert torch.equal(st.kept_idx, ref.kept_idx) and torch.equal(st.start_idx, ref.start_idx)
+    a, b = st.materialise(), ref.materialise()
+    assert a[0].cpu().numpy().tobytes() == b[0].cpu().numpy().tobytes(), sub
+    assert a[1].cpu().numpy().tobytes() == b[1].cpu().numpy().tobytes(), sub
+    assert st.kept_minmax().cpu().numpy().tobytes() == ref.kept_minmax().cpu().numpy().tobytes(), sub
+  assert stores[0].rhc.data_ptr() == stores[-1].rhc.data_ptr()            # one RHC tensor for every subset
+  with pytest.raises(ValueError):
+    scgrhc.prepare_subsets(arena, plan, sup, rcol, -50.0, [[sup[1], sup[0]]])
+
+
+def test_nonfinite_scg_does_not_change_the_rhc_predicates():
+  """has_noise() looks at the RHC channel only (waveform_noise.py:44-49): NaN / Inf in an SCG column must leave keep and
+  reason untouched (a straight-line window stays rejected), and only poison that window's joint min/max as np.min does."""
+  import scgrhc
+  from scgrhc import _native as N
+  sig = synth_ref.DEFAULT_SIG_NAMES
+  T = 60000
+  p = synth_ref.gen_record(H.SEED, 411, T, kinds=synth_ref.kinds_for(sig))
+  meta = synth_ref.record_meta(120, events={'PA_1': 0.0})
+  plan = scgrhc.plan_cohort([meta], 'PA', [T], 750)
+  base = scgrhc.prepare_windows(torch.from_numpy(p).to(DEV), plan, [0, 1, 2], 3, -50.0)
+  reason = base.reason.cpu().numpy()
+  straight = np.nonzero(reason == N.REASON_STRAIGHT)[0]
+  kept = np.nonzero(reason == 0)[0]
+  assert len(straight) >= 2 and len(kept) >= 2
+  q = p.copy()
+  q[straight[0] * 750 + 10, 1] = np.nan
+  q[straight[1] * 750 + 700, 0] = np.inf
+  q[kept[0] * 750 + 5, 2] = np.nan
+  q[kept[1] * 750 + 5, 2] = -np.inf
+  for cols in ([0, 1, 2], [2, 0], [1]):
+    st = scgrhc.prepare_windows(torch.from_numpy(q).to(DEV), plan, cols, 3, -50.0)
+    assert st.reason.cpu().numpy().tolist() == reason.tolist(), cols
+    assert torch.equal(st.keep, base.keep)
+  st = scgrhc.prepare_windows(torch.from_numpy(q).to(DEV), plan, [0, 1, 2], 3, -50.0)
+  mm = st.minmax.cpu().numpy()
+  assert np.isnan(mm[kept[0], :2]).all() and mm[kept[1], 0] == -np.inf and np.isfinite(mm[kept[1], 1])
+  assert (mm[:, 2:] == base.minmax.cpu().numpy()[:, 2:]).all()
