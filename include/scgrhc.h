@@ -139,6 +139,12 @@ int scgrhc_plan_record(const double* event_time, const uint8_t* event_match, int
                        scgrhc_interval* out, int out_cap, int* n_out, int64_t* n_cand,
                        int64_t* bounds, int bounds_cap, int* n_bounds);
 
+/* The same for a whole cohort in one call (the per-record loop of get_segments, recordutil.py:131-132): record r owns
+ * events ev_off[r] .. ev_off[r+1] and T_rows[r] arena rows, records back to back, rec_id = rec0 + r. */
+int scgrhc_plan_cohort(const double* event_time, const uint8_t* event_match, const int64_t* ev_off, const int64_t* T_rows,
+                       int64_t n_rec, int32_t W, int32_t stride, double fs, int32_t rec0, scgrhc_interval* out,
+                       int64_t out_cap, int64_t* n_out, int64_t* n_cand);
+
 /* ---- the hot path: has_noise + SCGDataset.init_segments fused (recordutil.py:141-148,55-66;
  *      waveform_noise.py:6-49).  Asynchronous. */
 int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, const scgrhc_outputs* out, void* stream);

@@ -163,6 +163,28 @@ extern "C" int scgrhc_plan_record(const double* event_time, const uint8_t* event
   return SCGRHC_OK;
 }
 
+// The same for a whole cohort in one call: record r owns events ev_off[r] .. ev_off[r+1] and T_rows[r] arena rows, records
+// back to back; rec_id = rec0 + r.  out_cap must hold one interval per matching event.
+extern "C" int scgrhc_plan_cohort(const double* event_time, const uint8_t* event_match, const int64_t* ev_off, const int64_t* T_rows,
+                                  int64_t n_rec, int32_t W, int32_t stride, double fs, int32_t rec0, scgrhc_interval* out,
+                                  int64_t out_cap, int64_t* n_out, int64_t* n_cand) {
+  if (!n_out || !n_cand || n_rec < 0 || (n_rec && (!ev_off || !T_rows))) return SCGRHC_ERR_BAD_ARG;
+  int64_t k = 0, cand = 0, base = 0;
+  for (int64_t r = 0; r < n_rec; ++r) {
+    const int64_t e0 = ev_off[r], ne = ev_off[r + 1] - e0;
+    if (ne < 0 || ne > INT32_MAX || out_cap - k > INT32_MAX) return SCGRHC_ERR_BAD_ARG;
+    int nk = 0;
+    int64_t nc = 0;
+    const int rc = scgrhc_plan_record(event_time + e0, event_match + e0, (int)ne, T_rows[r], W, stride, fs, base, (int32_t)(rec0 + r), cand,
+                                      out ? out + k : nullptr, (int)(out_cap - k), &nk, &nc, nullptr, 0, nullptr);
+    if (rc != SCGRHC_OK) return rc;
+    k += nk; cand += nc; base += T_rows[r];
+  }
+  *n_out = k;
+  *n_cand = cand;
+  return SCGRHC_OK;
+}
+
 // ---- hot path launcher -------------------------------------------------------------------------------
 template <int C, bool NSIG4, bool IDENT, typename OutT, int WCT>
 static int launch_window(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
@@ -301,8 +323,12 @@ extern "C" int scgrhc_normalize_subsets(scgrhc_ctx* ctx, const scgrhc_job* job, 
     CUDA_TRY(ctx, cudaGetLastError());
     return SCGRHC_OK;
   };
-  if (J.flags & SCGRHC_OUT_F64) return launch(subset_norm_kernel<double>);
-  return launch(subset_norm_kernel<float>);
+  if (J.W <= 6 * NT) {                                       // 750-sample windows: 6 rows per thread
+    if (J.flags & SCGRHC_OUT_F64) return launch(subset_norm_kernel<double, 6>);
+    return launch(subset_norm_kernel<float, 6>);
+  }
+  if (J.flags & SCGRHC_OUT_F64) return launch(subset_norm_kernel<double, RMAX>);
+  return launch(subset_norm_kernel<float, RMAX>);
 }
 
 extern "C" int scgrhc_check_errors(scgrhc_ctx* ctx, void* stream, int64_t* first_bad_cand) {

@@ -44,12 +44,31 @@ struct SubsetScratch {
 template <typename OutT, int R>
 __device__ __forceinline__ void norm_store(const Normaliser& nz, const double (&v)[R], OutT* base, int tid, int W) {
   if (!nz.slow) {
+    // the window kernel's tiers: fp32 outputs first take RN(a * RN(1/d)) with an integer check of the distance to a float
+    // rounding boundary; a thread that saw a risky element (p ~ 3e-8) rewrites its elements with the exact quotient
+    bool redo = true;
+    if constexpr (sizeof(OutT) == 4) {
+      if (nz.quick) {
+        uint32_t acc = 0xffffffffu;
 #pragma unroll
-    for (int k = 0; k < R; ++k) {
-      if (tid + k * NT < W) {
-        OutT o;
-        cvt_out(o, nz.fast(v[k]));
-        st_cs(base + k * NT, o);
+        for (int k = 0; k < R; ++k) {
+          if (tid + k * NT < W) {
+            const double q0 = __dmul_rn(__dsub_rn(v[k], nz.mn), nz.inv);
+            acc = min(acc, ((uint32_t)__double2loint(q0) + 0x10000008u) & 0x1fffffffu);
+            st_cs(base + k * NT, __double2float_rn(q0));
+          }
+        }
+        redo = acc <= 16u;
+      }
+    }
+    if (redo) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        if (tid + k * NT < W) {
+          OutT o;
+          cvt_out(o, nz.fast(v[k]));
+          st_cs(base + k * NT, o);
+        }
       }
     }
   } else {
@@ -67,9 +86,10 @@ __device__ __forceinline__ void norm_store(const Normaliser& nz, const double (&
   }
 }
 
-template <typename OutT>
+// R: rows per thread (windows of up to R * NT samples)
+template <typename OutT, int R>
 __global__ void __launch_bounds__(NT, 4) subset_norm_kernel(const __grid_constant__ SubsetParams P) {
-  constexpr int R = RMAX, CS = SCGRHC_MAX_C;
+  constexpr int CS = SCGRHC_MAX_C;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SubsetScratch& S = *reinterpret_cast<SubsetScratch*>(smem_raw);
   double* stage_base = reinterpret_cast<double*>(smem_raw + ((sizeof(SubsetScratch) + 127) & ~size_t(127)));

@@ -54,7 +54,7 @@ _lib = None
 
 # every symbol include/scgrhc.h declares (tests check the library exports all of them)
 SYMBOLS = ['scgrhc_abi_version', 'scgrhc_ctx_create', 'scgrhc_ctx_destroy', 'scgrhc_last_error',
-           'scgrhc_ctx_set_tuning', 'scgrhc_ctx_sm_count', 'scgrhc_plan_record', 'scgrhc_process_windows',
+           'scgrhc_ctx_set_tuning', 'scgrhc_ctx_sm_count', 'scgrhc_plan_record', 'scgrhc_plan_cohort', 'scgrhc_process_windows',
            'scgrhc_compact_kept', 'scgrhc_normalize_subsets', 'scgrhc_global_minmax', 'scgrhc_check_errors', 'scgrhc_gather_windows',
            'scgrhc_window_metrics', 'scgrhc_sosfiltfilt', 'scgrhc_sosfiltfilt_scan', 'scgrhc_resample_poly', 'scgrhc_gather_windows_noise', 'scgrhc_philox_words', 'scgrhc_rolling_range_lt', 'scgrhc_decode_fmt16', 'scgrhc_waveform_stats', 'scgrhc_synth_records', 'scgrhc_selftest_div']
 
@@ -81,6 +81,8 @@ def lib():
   L.scgrhc_plan_record.argtypes = [C.POINTER(dbl), C.POINTER(C.c_uint8), C.c_int, i64, i32, i32, dbl, i64, i32, i64,
                                    C.POINTER(Interval), C.c_int, C.POINTER(C.c_int), C.POINTER(i64),
                                    C.POINTER(i64), C.c_int, C.POINTER(C.c_int)]
+  L.scgrhc_plan_cohort.argtypes = [C.POINTER(dbl), C.POINTER(C.c_uint8), C.POINTER(i64), C.POINTER(i64), i64, i32, i32, dbl, i32,
+                                   C.POINTER(Interval), i64, C.POINTER(i64), C.POINTER(i64)]
   L.scgrhc_process_windows.argtypes = [vp, C.POINTER(Job), C.POINTER(Outputs), vp]
   L.scgrhc_normalize_subsets.argtypes = [vp, C.POINTER(Job), C.POINTER(Subset), i32, vp, vp]
   L.scgrhc_compact_kept.argtypes = [vp, vp, vp, vp, i64, i32, C.POINTER(Compact), vp]

@@ -23,19 +23,45 @@ RHC_NAME = 'RHC_pressure'
 INTERVAL_DTYPE = np.dtype([('row0', '<i8'), ('cand0', '<i8'), ('n_win', '<i4'), ('rec_id', '<i4')])
 
 
-def event_table(meta, chamber):
-  """Event times in dict order with 'END' appended (recordutil.py:100-104) and the per-event
-  chamber match ``key.split('_')[0] == chamber`` (:108).  None when ChamEvents_in_s is not a dict
-  (:103 -> no intervals)."""
-  t0 = datetime.strptime(meta['MacStTime'].split()[1], '%H:%M:%S')
-  t1 = datetime.strptime(meta['MacEndTime'].split()[1], '%H:%M:%S')
+_duration_cache = {}
+
+
+def _record_seconds(start, end):
+  """(MacEndTime - MacStTime).total_seconds() with the date ignored (recordutil.py:100-101,104); strptime is the slow
+  part of planning a large cohort, so the result is cached by the two strings."""
+  key = (start, end)
+  v = _duration_cache.get(key)
+  if v is None:
+    t0 = datetime.strptime(start.split()[1], '%H:%M:%S')
+    t1 = datetime.strptime(end.split()[1], '%H:%M:%S')
+    v = (t1 - t0).total_seconds()
+    if len(_duration_cache) > 100000:
+      _duration_cache.clear()
+    _duration_cache[key] = v
+  return v
+
+
+def event_times(meta):
+  """(keys, times) of a side-car: event times in dict order with 'END' appended (recordutil.py:100-104); None when
+  ChamEvents_in_s is not a dict (:103 -> no intervals)."""
+  end = _record_seconds(meta['MacStTime'], meta['MacEndTime'])
   events = meta['ChamEvents_in_s']
   if not isinstance(events, dict):
     return None
   events = dict(events)
-  events['END'] = (t1 - t0).total_seconds()
+  events['END'] = end
   keys = list(events.keys())
-  times = np.array([float(events[k]) for k in keys], dtype=np.float64)
+  return keys, np.array([float(events[k]) for k in keys], dtype=np.float64)
+
+
+def event_table(meta, chamber):
+  """Event times in dict order with 'END' appended (recordutil.py:100-104) and the per-event
+  chamber match ``key.split('_')[0] == chamber`` (:108).  None when ChamEvents_in_s is not a dict
+  (:103 -> no intervals)."""
+  kt = event_times(meta)
+  if kt is None:
+    return None
+  keys, times = kt
   # '*' (extension, waveform_01 legacy default): every chamber event, i.e. no chamber segmentation
   match = np.array([(k != 'END') if chamber == '*' else (k.split('_')[0] == chamber) for k in keys], dtype=np.uint8)
   return times, match
@@ -81,15 +107,34 @@ class Plan:
 
 
 def plan_cohort(metas, chamber, T_rows, W, record_names=None, stride=0, fs=0.0):
-  """Plan for records stored back to back in the arena; ``T_rows[r]`` rows each."""
-  ivs, base, cand = [], 0, 0
-  for r, meta in enumerate(metas):
-    iv, n, _ = plan_record(meta, chamber, T_rows[r], W, base, r, cand, stride, fs)
-    ivs.append(iv)
-    base += int(T_rows[r])
-    cand += n
-  iv = np.concatenate(ivs) if ivs else np.zeros(0, dtype=INTERVAL_DTYPE)
-  return Plan(iv, cand, W, list(record_names) if record_names is not None else [], stride)
+  """Plan for records stored back to back in the arena; ``T_rows[r]`` rows each.  One C call for the whole cohort
+  (`scgrhc_plan_cohort`)."""
+  times, match, off = [], [], [0]
+  for meta in metas:
+    tab = event_table(meta, chamber)
+    if tab is not None and len(tab[0]) >= 2:
+      times.append(tab[0]); match.append(tab[1])
+      off.append(off[-1] + len(tab[0]))
+    else:
+      off.append(off[-1])
+  n_rec = len(metas)
+  names = list(record_names) if record_names is not None else []
+  if off[-1] == 0:
+    return Plan(np.zeros(0, dtype=INTERVAL_DTYPE), 0, W, names, stride)
+  t = np.ascontiguousarray(np.concatenate(times), dtype=np.float64)
+  m = np.ascontiguousarray(np.concatenate(match), dtype=np.uint8)
+  o = np.asarray(off, dtype=np.int64)
+  rows = np.ascontiguousarray(np.asarray([int(v) for v in T_rows[:n_rec]], dtype=np.int64))
+  cap = int(m.sum())
+  out = np.zeros(max(cap, 1), dtype=INTERVAL_DTYPE)
+  n_out, n_cand = C.c_int64(0), C.c_int64(0)
+  rc = N.lib().scgrhc_plan_cohort(t.ctypes.data_as(C.POINTER(C.c_double)), m.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                  o.ctypes.data_as(C.POINTER(C.c_int64)), rows.ctypes.data_as(C.POINTER(C.c_int64)), n_rec,
+                                  int(W), int(stride), float(fs), 0, out.ctypes.data_as(C.POINTER(N.Interval)), cap,
+                                  C.byref(n_out), C.byref(n_cand))
+  if rc != N.OK:
+    raise N.ScgrhcError(rc, 'scgrhc_plan_cohort failed')
+  return Plan(out[:n_out.value].copy(), n_cand.value, W, names, stride)
 
 
 def plan_uniform(meta, chamber, T, W, n_rec, rec0=0, stride=0):
