@@ -69,6 +69,24 @@ def test_plan_uniform_equals_plan_cohort():
   assert (a.intervals['rec_id'] == b.intervals['rec_id'] + 3).all()
 
 
+def test_plan_cohort_one_call_equals_the_per_record_planner():
+  """scgrhc_plan_cohort (one C call per cohort) == scgrhc_plan_record record by record, on a ragged cohort: the golden
+  side-cars (unsorted events, duplicate chambers, a non-dict ChamEvents_in_s -> no intervals), records of different
+  lengths, strides and sampling rates, chamber '*'."""
+  cases = H.load_json('intervals.json')
+  metas = [c['meta'] for c in cases.values()] * 2
+  rows = [1000 + 37111 * (i % 9) for i in range(len(metas))]
+  for chamber, W, stride, fs in (('PA', 750, 0, 0.0), ('RV', 375, 187, 250.0), ('*', 500, 0, 0.0), ('PCW', 100, 250, 0.0)):
+    plan = scgrhc.plan_cohort(metas, chamber, rows, W, stride=stride, fs=fs)
+    ivs, base, cand = [], 0, 0
+    for r, meta in enumerate(metas):
+      iv, n, _ = scgrhc.plan_record(meta, chamber, rows[r], W, base, r, cand, stride, fs)
+      ivs.append(iv); base += rows[r]; cand += n
+    want = np.concatenate(ivs)
+    assert plan.n_cand == cand and plan.intervals.tobytes() == want.tobytes(), (chamber, W)
+  assert scgrhc.plan_cohort([], 'PA', [], 750).n_cand == 0
+
+
 def test_params_loads_all_37_configs(tmp_path):
   from paramutil import Params
   table = H.configs()
