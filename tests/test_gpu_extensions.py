@@ -81,18 +81,25 @@ def test_sosfiltfilt_rejects_short_records_like_scipy():
     filters.sosfiltfilt(arena, [20], sos, [0])
 
 
-@pytest.mark.parametrize('up,down', [(1, 2), (250, 500), (2, 5), (3, 2), (125, 500), (500, 500)])
-def test_resample_poly_matches_scipy(up, down):
-  sig = synth_ref.DEFAULT_SIG_NAMES
-  rows = [5000, 1234, 777]
-  recs = [synth_ref.gen_record(H.SEED, 70 + r, T, kinds=synth_ref.kinds_for(sig)) for r, T in enumerate(rows)]
+@pytest.mark.parametrize('ncols', [4, 5, 3, 1, 2, 7])
+@pytest.mark.parametrize('up,down', [(1, 2), (250, 500), (2, 5), (3, 2), (125, 500), (500, 500), (100, 500)])
+def test_resample_poly_matches_scipy(up, down, ncols):
+  """Bit-identical to scipy for integer decimation (register-blocked kernel: every column count it is instantiated for,
+  even and odd, and > 5 columns -> the general kernel) and for other ratios (general polyphase kernel)."""
+  if ncols not in (4, 5) and (up, down) not in ((1, 2), (125, 500), (2, 5)):
+    pytest.skip('column-count sweep only on a few ratios')
+  sig = (synth_ref.SIG_NAMES_5 + ['x5', 'x6'])[:ncols] if ncols != 4 else synth_ref.DEFAULT_SIG_NAMES
+  if ncols < 4:
+    sig = synth_ref.DEFAULT_SIG_NAMES
+  rows = [5000, 1234, 777, 12345]
+  recs = [synth_ref.gen_record(H.SEED, 70 + r, T, kinds=synth_ref.kinds_for(sig))[:, :ncols].copy() for r, T in enumerate(rows)]
   arena = torch.from_numpy(np.concatenate(recs)).to(DEV)
   out, out_rows = filters.resample_poly(arena, rows, up, down)
   out = out.cpu().numpy()
   at = 0
   for p, n in zip(recs, out_rows):
     want = signal.resample_poly(p, up, down, axis=0)
-    assert want.shape == (n, 4)
+    assert want.shape == (n, ncols)
     got = out[at:at + n]
     assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
     assert got.tobytes() == want.tobytes()                # in fact bit-identical: same taps, same summation order
