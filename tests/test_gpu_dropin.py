@@ -217,6 +217,30 @@ def test_device_decode_matches_host_dac_and_digital_ingest(tmp_path, monkeypatch
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
 
 
+@pytest.mark.parametrize('nsig_in,sel', [(4, [0, 1, 2, 3]), (4, [3, 1]), (5, [4, 0, 3]), (5, [0, 1, 2, 3, 4]), (3, [1]), (8, [7, 2, 5, 0])])
+def test_device_decode_every_shape_is_bit_exact(nsig_in, sel):
+  """scgrhc_decode_fmt16 == numpy's (d - baseline) / gain bit for bit: every output column count, 4-sample frames (8-byte
+  loads) and others, awkward gains (reciprocal + two FMA corrections must give the IEEE quotient), every int16 code
+  incl. the invalid-sample code; a fractional baseline and a subnormal gain take the full-division kernel."""
+  from scgrhc import ops
+  rng = np.random.default_rng(nsig_in * 31 + len(sel))
+  T = 70001
+  d = rng.integers(-32768, 32768, size=(T, nsig_in), dtype=np.int64).astype(np.int16)
+  d[:65536, sel[0]] = np.arange(-32768, 32768, dtype=np.int64).astype(np.int16)     # every code once
+  for gains, bases in (([200000.0, 3.0, 0.1, 1e-3 / 3, 497.3][:len(sel)], [0.0, -7.0, 1024.0, 32767.0, -32768.0][:len(sel)]),
+                       ([1e5 / 7.0] * len(sel), [0.5] * len(sel)),
+                       ([5e-324 * 4] + [2.0] * (len(sel) - 1), [0.0] * len(sel))):
+    out = torch.empty((T, len(sel)), dtype=torch.float64, device='cuda')
+    ops.decode_fmt16(torch.from_numpy(d).cuda(), sel, gains, bases, out)
+    x = d[:, sel].astype(np.float64)
+    with np.errstate(over='ignore'):
+      want = (x - np.asarray(bases)) / np.asarray(gains)
+    want[d[:, sel] == -32768] = np.nan
+    got = out.cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert got[~np.isnan(got)].tobytes() == want[~np.isnan(want)].tobytes(), (gains, bases)
+
+
 def test_noise_injection_extension_philox():
   """Extension (absent from the reference): seed-exact Philox4x32-10 stream, Box-Muller within fp32 tolerance,
   distribution checks, and the loader wiring (SCG inputs only, a fresh stream per batch, off by default)."""
