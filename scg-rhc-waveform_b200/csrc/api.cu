@@ -631,7 +631,7 @@ extern "C" int scgrhc_sosfiltfilt_scan(scgrhc_ctx* ctx, const double* x, double*
 
 extern "C" int scgrhc_resample_poly(scgrhc_ctx* ctx, const double* x, double* y, const double* taps_dev, const int64_t* in0_dev,
                                     const int64_t* out0_dev, int32_t n_rec, int64_t max_out_rows, int32_t ncols, int32_t up, int32_t down,
-                                    int32_t per_phase, int32_t n_pre_remove, void* stream) {
+                                    int32_t per_phase, int32_t n_pre_remove, int32_t fused, void* stream) {
   NvtxRange nvtx_range("scgrhc_resample_poly");
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
   if (n_rec < 0 || ncols < 1 || up < 1 || down < 1 || per_phase < 1 || n_pre_remove < 0 || max_out_rows < 0 ||
@@ -658,12 +658,22 @@ extern "C" int scgrhc_resample_poly(scgrhc_ctx* ctx, const double* x, double* y,
         kern<<<grid, kDecNT, dsmem, st>>>(P, magic);
         return cudaSuccess;
       };
-      switch (ncols) {
-        case 1: CUDA_TRY(ctx, launch(resample_decim_kernel<1>)); break;
-        case 2: CUDA_TRY(ctx, launch(resample_decim_kernel<2>)); break;
-        case 3: CUDA_TRY(ctx, launch(resample_decim_kernel<3>)); break;
-        case 4: CUDA_TRY(ctx, launch(resample_decim_kernel<4>)); break;
-        default: CUDA_TRY(ctx, launch(resample_decim_kernel<5>)); break;
+      if (fused) {
+        switch (ncols) {
+          case 1: CUDA_TRY(ctx, launch(resample_decim_kernel<1, true>)); break;
+          case 2: CUDA_TRY(ctx, launch(resample_decim_kernel<2, true>)); break;
+          case 3: CUDA_TRY(ctx, launch(resample_decim_kernel<3, true>)); break;
+          case 4: CUDA_TRY(ctx, launch(resample_decim_kernel<4, true>)); break;
+          default: CUDA_TRY(ctx, launch(resample_decim_kernel<5, true>)); break;
+        }
+      } else {
+        switch (ncols) {
+          case 1: CUDA_TRY(ctx, launch(resample_decim_kernel<1, false>)); break;
+          case 2: CUDA_TRY(ctx, launch(resample_decim_kernel<2, false>)); break;
+          case 3: CUDA_TRY(ctx, launch(resample_decim_kernel<3, false>)); break;
+          case 4: CUDA_TRY(ctx, launch(resample_decim_kernel<4, false>)); break;
+          default: CUDA_TRY(ctx, launch(resample_decim_kernel<5, false>)); break;
+        }
       }
       CUDA_TRY(ctx, cudaGetLastError());
       return SCGRHC_OK;

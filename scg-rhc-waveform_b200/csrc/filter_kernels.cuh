@@ -225,7 +225,8 @@ namespace scgrhc {
 constexpr int kDecR = 4;      // outputs per thread
 constexpr int kDecNT = 128;   // threads per CTA: a tile is 512 outputs
 
-template <int NC>
+// FUSED: multiply-add in one rounding (faster: half the fp64 instructions; within ~1e-15 of scipy instead of bit-identical)
+template <int NC, bool FUSED>
 __global__ void __launch_bounds__(kDecNT) resample_decim_kernel(const __grid_constant__ ResampleParams P, unsigned pb_magic) {
   extern __shared__ __align__(16) double s_dec[];
   double* s_taps = s_dec;
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(kDecNT) resample_decim_kernel(const __grid_con
             for (int r = 0; r < kDecR; ++r) {
               const double hk = s_taps[j - r * down];
 #pragma unroll
-              for (int c = 0; c < NC; ++c) acc[r][c] = __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
+              for (int c = 0; c < NC; ++c) acc[r][c] = FUSED ? __fma_rn(xv[c], hk, acc[r][c]) : __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
             }
           } else {                                            // ramp-up / ramp-down: output r takes rows r*down .. r*down + pp - 1
 #pragma unroll
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(kDecNT) resample_decim_kernel(const __grid_con
               if (k >= 0 && k < pp) {
                 const double hk = s_taps[k];
 #pragma unroll
-                for (int c = 0; c < NC; ++c) acc[r][c] = __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
+                for (int c = 0; c < NC; ++c) acc[r][c] = FUSED ? __fma_rn(xv[c], hk, acc[r][c]) : __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
               }
             }
           }

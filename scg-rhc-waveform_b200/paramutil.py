@@ -61,6 +61,7 @@ class Params:
     self.bandpass_sos = self.data.get('bandpass_sos')      # or explicit second-order sections
     self.bandpass_mode = self.data.get('bandpass_mode')    # 'exact' (default, bit-identical to scipy) | 'scan' (time-parallel)
     self.resample_rate = self.data.get('resample_rate')    # model sampling rate in Hz (native: 500)
+    self.resample_mode = self.data.get('resample_mode')    # 'exact' (default, bit-identical to scipy) | 'fused' (one FMA per tap)
     self.normalisation = self.data.get('normalisation')    # 'minmax' (default = the reference) | 'zscore' (per-window mean/std)
 
   def _get(self, key):

@@ -444,7 +444,7 @@ def prepare_cohort(params, record_names=None, chunk_records=32):
     scan = getattr(params, 'bandpass_mode', None) == 'scan'      # time-parallel kernel: filters the staged cohort in place
     arena = filters.sosfiltfilt(arena, rows, sos, list(range(C)), exact=not scan, inplace=scan and len(sos) <= 4)
   if rate and int(rate) != SAMPLE_FREQ:    # extension: every channel to the model rate (scipy resample_poly semantics)
-    arena, rows = filters.resample_poly(arena, rows, int(rate), SAMPLE_FREQ)
+    arena, rows = filters.resample_poly(arena, rows, int(rate), SAMPLE_FREQ, exact=getattr(params, 'resample_mode', None) != 'fused')
     W = int(params.segment_size * int(rate))
     plan = engine.plan_cohort(metas, params.chamber, rows, W, names, stride=int(stride_s * int(rate)) if stride_s else 0,
                               fs=float(int(rate)))

@@ -95,7 +95,7 @@ def lib():
   L.scgrhc_sosfiltfilt.argtypes = [vp, vp, vp, vp, vp, C.POINTER(i64), i32, i32, C.POINTER(i32), i32, C.POINTER(dbl), C.POINTER(dbl), i32, i32, vp]
   L.scgrhc_sosfiltfilt_scan.argtypes = [vp, vp, vp, vp, C.POINTER(i64), i32, i32, C.POINTER(i32), i32, C.POINTER(dbl), C.POINTER(dbl),
                                         i32, i32, i32, i32, vp]
-  L.scgrhc_resample_poly.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, vp]
+  L.scgrhc_resample_poly.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, vp]
   L.scgrhc_rolling_range_lt.argtypes = [vp, vp, i64, i32, dbl, vp, vp]
   L.scgrhc_decode_fmt16.argtypes = [vp, vp, i64, i32, C.POINTER(i32), i32, C.POINTER(dbl), C.POINTER(dbl), vp, vp]
   L.scgrhc_waveform_stats.argtypes = [vp, vp, i64, i64, dbl, vp, vp]

@@ -130,9 +130,10 @@ def resample_design(n_in, up, down, window=('kaiser', 5.0)):
   return up, down, n_out, taps, padlen // up, n_pre_remove, n_post_pad
 
 
-def resample_poly(arena, record_rows, up, down, window=('kaiser', 5.0)):
+def resample_poly(arena, record_rows, up, down, window=('kaiser', 5.0), exact=True):
   """Resample every record of ``arena`` ((rows, ncols) fp64 CUDA) by up/down; returns (new_arena, new_record_rows).
-  ``up == down`` after reduction returns a copy, as scipy does."""
+  ``up == down`` after reduction returns a copy, as scipy does.  ``exact=True``: bit-identical to scipy; ``exact=False``
+  (integer decimation only): one FMA per tap, ~1.7x faster, within 1e-14 of scipy."""
   import math
   if not arena.is_cuda:
     raise RuntimeError('resample_poly needs a CUDA arena (no CPU fallback)')
@@ -159,5 +160,5 @@ def resample_poly(arena, record_rows, up, down, window=('kaiser', 5.0)):
     n = min(65535, len(rows) - lo)
     N.check(c, N.lib().scgrhc_resample_poly(c, ops._ptr(arena), ops._ptr(out), ops._ptr(taps), ops._ptr(in0[lo:]), ops._ptr(out0[lo:]),
                                             n, max(out_rows[lo:lo + n]), arena.shape[1], first[0], first[1], first[4], first[5],
-                                            ops._stream(dev.index)))
+                                            0 if exact else 1, ops._stream(dev.index)))
   return out, out_rows

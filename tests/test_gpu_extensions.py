@@ -105,6 +105,9 @@ def test_resample_poly_matches_scipy(up, down, ncols):
     assert got.tobytes() == want.tobytes()                # in fact bit-identical: same taps, same summation order
     at += n
   assert at == out.shape[0]
+  fast, _ = filters.resample_poly(arena, rows, up, down, exact=False)      # one FMA per tap (integer decimation only)
+  scale = np.abs(out).max(axis=0)
+  assert (np.abs(fast.cpu().numpy() - out) / scale).max() <= 1e-14
 
 
 def test_filter_resample_window_pipeline_against_scipy_plus_oracle():

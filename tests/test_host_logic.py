@@ -181,7 +181,7 @@ def test_params_optional_extension_keys_default_off(tmp_path):
   p.write_text(json.dumps(base))
   q = Params(str(p), strict=True)
   for k in ('split_seed', 'segment_stride', 'noise_std', 'noise_seed', 'bandpass', 'bandpass_order', 'bandpass_sos',
-            'bandpass_mode', 'resample_rate', 'normalisation'):
+            'bandpass_mode', 'resample_rate', 'resample_mode', 'normalisation'):
     assert getattr(q, k) is None
   p.write_text(json.dumps(dict(base, bandpass=[1, 40], resample_rate=250, segment_stride=0.5, noise_std=0.01)))
   q = Params(str(p))
