@@ -425,32 +425,27 @@ def prepare_cohort(params, record_names=None, chunk_records=32):
   sos = _bandpass_sos(params)
   rate = getattr(params, 'resample_rate', None)
   extensions = sos is not None or (rate and int(rate) != SAMPLE_FREQ)
-  if not extensions:
-    ing = engine.HostIngest(plan, rows, C + 1, dev, chunk_records=chunk_records, digital_nsig=(C + 1) if digital else None)
-    store = ing.run(host, list(range(C)), C, params.min_RHC, decode=(list(range(C + 1)), gains, bases) if digital else None,
-                    use_global_min_max=bool(params.use_global_min_max), normalisation=getattr(params, 'normalisation', None))
-    return store, names
-  # the optional filter / resample stages work on a resident cohort
-  if digital:
-    d_dev = host.to(dev, non_blocking=True)
-    arena = torch.empty((total, C + 1), dtype=torch.float64, device=dev)
-    at = 0
-    for r, n in enumerate(rows):
-      ops.decode_fmt16(d_dev[at:at + n], list(range(C + 1)), gains[r], bases[r], arena[at:at + n])
-      at += n
-  else:
-    arena = host.to(dev, non_blocking=True)
-  if sos is not None:                      # extension: zero-phase band-pass of the SCG channels (scipy sosfiltfilt semantics)
-    scan = getattr(params, 'bandpass_mode', None) == 'scan'      # time-parallel kernel: filters the staged cohort in place
-    arena = filters.sosfiltfilt(arena, rows, sos, list(range(C)), exact=not scan, inplace=scan and len(sos) <= 4)
-  if rate and int(rate) != SAMPLE_FREQ:    # extension: every channel to the model rate (scipy resample_poly semantics)
-    arena, rows = filters.resample_poly(arena, rows, int(rate), SAMPLE_FREQ, exact=getattr(params, 'resample_mode', None) != 'fused')
-    W = int(params.segment_size * int(rate))
-    plan = engine.plan_cohort(metas, params.chamber, rows, W, names, stride=int(stride_s * int(rate)) if stride_s else 0,
-                              fs=float(int(rate)))
-  store = engine.prepare_windows(arena, plan, list(range(C)), C, params.min_RHC,
-                                 use_global_min_max=bool(params.use_global_min_max),
-                                 normalisation=getattr(params, 'normalisation', None))
+  stages = None
+  if extensions:
+    # the optional stages (absent from the reference) run per chunk inside the same streamed ingest: copy of chunk k+1
+    # overlaps decode / band-pass / resample / window kernel of chunk k, and the cohort never has to be resident
+    stages = {}
+    if sos is not None:                    # zero-phase band-pass of the SCG channels (scipy sosfiltfilt semantics)
+      stages.update(sos=sos, filter_cols=list(range(C)), filter_exact=getattr(params, 'bandpass_mode', None) != 'scan')
+    if rate and int(rate) != SAMPLE_FREQ:  # every channel to the model rate (scipy resample_poly semantics)
+      import math
+      g = math.gcd(int(rate), SAMPLE_FREQ)
+      up, down = int(rate) // g, SAMPLE_FREQ // g
+      out_rows = [-(-int(n) * up // down) for n in rows]
+      stages.update(resample=(int(rate), SAMPLE_FREQ), out_rows=out_rows,
+                    resample_exact=getattr(params, 'resample_mode', None) != 'fused')
+      W = int(params.segment_size * int(rate))
+      plan = engine.plan_cohort(metas, params.chamber, out_rows, W, names, stride=int(stride_s * int(rate)) if stride_s else 0,
+                                fs=float(int(rate)))
+  ing = engine.HostIngest(plan, rows, C + 1, dev, chunk_records=chunk_records, digital_nsig=(C + 1) if digital else None,
+                          stages=stages)
+  store = ing.run(host, list(range(C)), C, params.min_RHC, decode=(list(range(C + 1)), gains, bases) if digital else None,
+                  use_global_min_max=bool(params.use_global_min_max), normalisation=getattr(params, 'normalisation', None))
   return store, names
 
 

@@ -351,26 +351,36 @@ class HostIngest:
   (compute stream).  This is the end-to-end path a caller with records in host memory uses
   (the reference reads each record from disk into host numpy arrays, recordutil.py:137)."""
 
-  def __init__(self, plan, record_rows, nsig, device, chunk_records=64, digital_nsig=None):
+  def __init__(self, plan, record_rows, nsig, device, chunk_records=64, digital_nsig=None, stages=None):
     """``nsig``: columns of the fp64 arena the window kernel reads.  ``digital_nsig``: the host cohort is WFDB
     format-16 int16 frames with that many signals per frame; they are copied as int16 (4x fewer PCIe bytes than
-    fp64 physical samples) and converted on the device (scgrhc_decode_fmt16)."""
+    fp64 physical samples) and converted on the device (scgrhc_decode_fmt16).
+
+    ``stages`` (extension, default off): the optional per-record stages run on every chunk between the copy and the
+    window kernel, so they overlap the next chunk's copy and the cohort never has to be resident:
+    ``{'sos': (n, 6) sections, 'filter_cols': [...], 'filter_exact': bool, 'resample': (up, down), 'out_rows': [...]}``;
+    with ``resample`` the plan's rows are rows AFTER resampling (``out_rows`` per record)."""
     self.plan, self.nsig, self.device = plan, nsig, torch.device(device)
+    self.stages = stages or None
     rows = np.asarray(record_rows, dtype=np.int64)
+    self.record_rows = rows
     base = np.concatenate([[0], np.cumsum(rows)])
     self.record_base = base
     self.total_rows = int(base[-1])
+    plan_base = base
+    if self.stages and self.stages.get('resample'):
+      plan_base = np.concatenate([[0], np.cumsum(np.asarray(self.stages['out_rows'], dtype=np.int64))])
     iv = plan.intervals
     self.chunks = []
     max_rows = 0
     for r0 in range(0, len(rows), chunk_records):
       r1 = min(len(rows), r0 + chunk_records)
       lo, hi = int(base[r0]), int(base[r1])
-      a, b = np.searchsorted(iv['row0'], [lo, hi], side='left')
+      a, b = np.searchsorted(iv['row0'], [int(plan_base[r0]), int(plan_base[r1])], side='left')
       sub = iv[a:b].copy()
       cand_lo = int(sub['cand0'][0]) if len(sub) else 0
       n = int(sub['n_win'].sum())
-      sub['row0'] -= lo
+      sub['row0'] -= int(plan_base[r0])
       sub['cand0'] -= cand_lo
       t = torch.from_numpy(sub.view(np.int64).reshape(-1, 3).copy()).to(self.device) if len(sub) else None
       self.chunks.append((lo, hi, cand_lo, n, t, r0, r1))
@@ -412,9 +422,24 @@ class HostIngest:
         else:
           ops.decode_fmt16(stage, list(cols), [float(v) for v in gain], [float(v) for v in baseline], dst)
       if nc:
-        body(dst, chunk)
+        body(self._run_stages(dst, r0, r1), chunk)
       done[k & 1] = torch.cuda.Event()
       done[k & 1].record(compute)
+
+  def _run_stages(self, dst, r0, r1):
+    """Optional per-record stages on one resident chunk (records r0..r1): zero-phase band-pass, then resampling."""
+    st = self.stages
+    if not st:
+      return dst
+    from . import filters
+    rows = [int(v) for v in self.record_rows[r0:r1]]
+    if st.get('sos') is not None:
+      exact = bool(st.get('filter_exact', True)) or len(st['sos']) > 4
+      dst = filters.sosfiltfilt(dst, rows, st['sos'], list(st['filter_cols']), exact=exact, inplace=not exact)
+    if st.get('resample'):
+      up, down = st['resample']
+      dst, _ = filters.resample_poly(dst, rows, up, down, exact=bool(st.get('resample_exact', True)))
+    return dst
 
   def run(self, host_arena, scg_cols, rhc_col, min_rhc, out_dtype=torch.float32, flat_threshold=FLAT_THRESHOLD,
           buffers=None, decode=None, use_global_min_max=False, group=None, normalisation='minmax'):

@@ -211,3 +211,36 @@ def test_zscore_normalisation_matches_numpy(sig, chans, out_dtype, W):
   assert abs(float(scg.mean())) < 1e-2 and abs(float(scg.reshape(len(scg), -1).std(axis=1).mean()) - 1.0) < 5e-2
   with pytest.raises(ValueError):
     scgrhc.prepare_windows(arena, plan, chans, rcol, -50.0, use_global_min_max=True, normalisation='zscore')
+
+
+def test_extension_stages_stream_per_chunk(tmp_path, monkeypatch):
+  """The optional stages run per chunk inside the streamed host ingest: a cohort of ragged records gives the same windows
+  whatever the chunking (one record per chunk vs the whole cohort in one chunk), for physical and digital host records,
+  local and dataset-global min-max — and equals scipy + the oracle arithmetic on one record."""
+  import json
+  import types
+  import recordutil
+  from scgrhc import wfdbio
+  root = tmp_path / 'data'; root.mkdir()
+  monkeypatch.setattr(recordutil, 'PROCESSED_DATA_PATH', str(root))
+  monkeypatch.setattr(recordutil, 'wfdb', wfdbio)
+  sig = synth_ref.DEFAULT_SIG_NAMES
+  names = []
+  for r, T in enumerate((40000, 23456, 31001, 9000)):
+    meta = synth_ref.record_meta(T // 500, events={'PA_1': 1.0 + r, 'RV_1': T // 500 - 3})
+    p = synth_ref.gen_record(H.SEED, 120 + r, T, kinds=synth_ref.kinds_for(sig))
+    wfdbio.wrsamp('rec%d' % r, 500, ['g', 'g', 'g', 'mmHg'], sig, p, write_dir=str(root))
+    (root / ('rec%d.json' % r)).write_text(json.dumps(meta))
+    names.append('rec%d' % r)
+  base = dict(in_channels=sig[:3], chamber='PA', segment_size=1.5, min_RHC=-50)
+  for extra in (dict(bandpass=[1.0, 40.0], bandpass_mode='scan', resample_rate=250, use_global_min_max=False),
+                dict(bandpass=[0.8, 30.0], resample_rate=125, segment_stride=0.5, use_global_min_max=True),
+                dict(resample_rate=250, resample_mode='fused', normalisation='zscore', use_global_min_max=False)):
+    params = types.SimpleNamespace(**base, **extra)
+    one, _ = recordutil.prepare_cohort(params, names, chunk_records=1)
+    whole, _ = recordutil.prepare_cohort(params, names, chunk_records=32)
+    assert one.n_kept == whole.n_kept > 0 and one.n_cand == whole.n_cand
+    assert torch.equal(one.kept_idx, whole.kept_idx) and torch.equal(one.rec_id, whole.rec_id)
+    a, b = one.materialise(), whole.materialise()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert torch.equal(one.kept_minmax(), whole.kept_minmax())
