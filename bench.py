@@ -498,6 +498,37 @@ def run_b200(args):
            'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e, 'steps': k_e2e,
            'api': 'scgrhc.engine.HostIngest.run (pinned host fp64 records, %d-record chunks, copy/compute overlap)' % args.chunk_records,
            'h2d_gbs': ing.h2d_bytes / (ms_e2e * 1e-3) / 1e9}
+    # ---- the brief's full pipeline end to end: the same pinned host records, every optional stage ON per chunk
+    #      (band-pass -> 500->250 Hz -> z-score windows) between the copy and the window kernel ----
+    if not args.no_pipeline:
+      try:
+        from scipy import signal as _sig
+        sos = _sig.butter(4, (1.0, 40.0), btype='bandpass', fs=500, output='sos')
+        out_rows = [T_ROWS // 2] * n_rec
+        plan2 = scgrhc.plan_uniform(meta(), 'PA', T_ROWS // 2, 375, n_rec, rec0=lo)
+        ingp = HostIngest(plan2, [T_ROWS] * n_rec, len(SIG), dev, chunk_records=200,   # one filter CTA per record: big chunks
+                          stages=dict(sos=sos, filter_cols=cols, filter_exact=False, resample=(250, 500), out_rows=out_rows,
+                                      resample_exact=False))
+        bufp = {}
+        for _ in range(2):
+          stp = ingp.run(host, cols, rcol, MIN_RHC, buffers=bufp, normalisation='zscore')
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k_e2e):
+          stp = ingp.run(host, cols, rcol, MIN_RHC, buffers=bufp, normalisation='zscore')
+          meta_host = (stp.kept_idx.cpu(), stp.start_idx.cpu(), stp.rec_id.cpu())
+        b.record()
+        barrier()
+        ms_p = a.elapsed_time(b) / k_e2e
+        e2e['north_star_pipeline'] = {'value': stp.n_kept / (ms_p * 1e-3), 'unit': UNIT, 'ms_per_step': ms_p,
+                                      'h2d_bytes_per_step': ingp.h2d_bytes, 'h2d_gbs': ingp.h2d_bytes / (ms_p * 1e-3) / 1e9,
+                                      'kept_windows_per_step': stp.n_kept, 'scope': 'this rank',
+                                      'note': 'every optional stage ON (band-pass, resample, z-score) per 200-record chunk, '
+                                              'overlapping the PCIe copy of the next chunk'}
+        del bufp, stp
+      except Exception as exc:
+        e2e['north_star_pipeline'] = {'error': str(exc)[:300]}
     del host
     # ---- the same, from WFDB format-16 digital frames (what is on disk): int16 over PCIe, decode on the device ----
     if not args.no_fmt16:

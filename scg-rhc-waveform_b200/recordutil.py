@@ -385,7 +385,7 @@ def train_valid_test_split(n, seed=None):
   return train, valid, test
 
 
-def prepare_cohort(params, record_names=None, chunk_records=32):
+def prepare_cohort(params, record_names=None, chunk_records=None):
   """Records -> HBM -> fused window kernel.  Returns (WindowStore, record_names): every kept window of the
   cohort, device resident, in the reference's order (records in ``record_names`` order).
 
@@ -442,6 +442,9 @@ def prepare_cohort(params, record_names=None, chunk_records=32):
       W = int(params.segment_size * int(rate))
       plan = engine.plan_cohort(metas, params.chamber, out_rows, W, names, stride=int(stride_s * int(rate)) if stride_s else 0,
                                 fs=float(int(rate)))
+  if chunk_records is None:
+    # the time-parallel band-pass runs one CTA per record (8 per SM): a chunk of a few hundred records costs what 32 do
+    chunk_records = 256 if (stages and stages.get('sos') is not None) else 32
   ing = engine.HostIngest(plan, rows, C + 1, dev, chunk_records=chunk_records, digital_nsig=(C + 1) if digital else None,
                           stages=stages)
   store = ing.run(host, list(range(C)), C, params.min_RHC, decode=(list(range(C + 1)), gains, bases) if digital else None,
