@@ -500,7 +500,7 @@ def run_b200(args):
            'h2d_gbs': ing.h2d_bytes / (ms_e2e * 1e-3) / 1e9}
     # ---- the brief's full pipeline end to end: the same pinned host records, every optional stage ON per chunk
     #      (band-pass -> 500->250 Hz -> z-score windows) between the copy and the window kernel ----
-    if not args.no_pipeline:
+    if world == 1 and not args.no_pipeline:
       try:
         from scipy import signal as _sig
         sos = _sig.butter(4, (1.0, 40.0), btype='bandpass', fs=500, output='sos')
