@@ -483,16 +483,18 @@ extern "C" int scgrhc_sosfiltfilt(scgrhc_ctx* ctx, const double* x, double* y, d
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  // The recurrence is latency bound, so prefer many warps: as few columns per warp as still fills the GPU
-  int cpw = 32 / nsec;
-  while (cpw > 1 && (long long)n_rec * ((ncf + cpw - 2) / (cpw - 1)) <= (long long)ctx->sm_count * 48) --cpw;
+  // A warp's recurrence needs ~45 cycles per sample (4 dependent fp64 ops) and occupies the fp64 pipe for 18 whatever
+  // the number of live lanes: beyond ~2.5 warps per sub-partition more warps only queue on the pipe.  So: as few
+  // columns per warp as keeps the warp count under 10 per SM.
+  int cpw = std::min(32 / nsec, (int)ncf);
+  while (cpw > 1 && (long long)n_rec * ((ncf + cpw - 2) / (cpw - 1)) <= (long long)ctx->sm_count * 10) --cpw;
   P.cpw = cpw;
   for (int r = 0; r < n_rec; ++r)
     if (row0_host[r + 1] - row0_host[r] + 2LL * edge >= INT32_MAX) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "sosfiltfilt: record too long");
   const int groups = (ncf + cpw - 1) / cpw;
   const long long warps = (long long)n_rec * groups;
   const unsigned grid = (unsigned)((warps + 3) / 4);
-  const size_t smem = (size_t)4 * kRing * kTileRows * cpw * sizeof(double);   // 4 warps per CTA
+  const size_t smem = (size_t)4 * (kPrefetch + nsec + 1) * cpw * (kBlock + 1) * sizeof(double);   // 4 warps per CTA
   CUDA_TRY(ctx, cudaFuncSetAttribute(sosfilt_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_TRY(ctx, cudaFuncSetAttribute(sosfilt_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sosfilt_pass_kernel<0><<<grid, 128, smem, st>>>(P);

@@ -4,11 +4,12 @@
 //
 // Every (record, column) is an independent sequence.  The recurrence is serial in time, so parallelism comes from
 //   * sequences: one warp per (record, group of columns),
-//   * sections: a systolic pipeline across lanes — lane (column c, section s) handles sample it-s at iteration `it`
-//     and hands its output to lane s+1 with one shuffle,
+//   * sections: a block pipeline across lanes — lane (column c, section s) filters block t - s (kBlock samples) at step t,
+//     in place in a shared-memory ring, and the next section picks the block up one step later (one __syncwarp per
+//     block instead of one shuffle per sample),
 // and every operation is rounded exactly as scipy's compiled loop does (separate multiply/add, no FMA), which makes the
-// result bit-identical to scipy instead of merely close.  A chunked parallel scan over time would be faster but changes
-// the rounding order.
+// result bit-identical to scipy instead of merely close.  The time-parallel kernel (filter_scan_kernel.cuh) is an order
+// of magnitude faster but changes the rounding order.
 #pragma once
 #include "common.cuh"
 
@@ -16,8 +17,8 @@ namespace scgrhc {
 
 constexpr int kMaxSections = 8;
 constexpr int kMaxFilterCols = 8;
-constexpr int kTileRows = 32;   // samples per staged tile
-constexpr int kRing = 8;        // tiles in flight per warp (256 samples ahead)
+constexpr int kBlock = 32;      // samples per block
+constexpr int kPrefetch = 6;    // blocks loaded ahead of the first section
 
 struct SosParams {
   const double* x;        // (rows, ncols) arena
@@ -34,12 +35,12 @@ struct SosParams {
 template <int PASS>  // 0: forward over the odd extension, x -> tmp; 1: backward over reversed tmp -> y (trimmed)
 __global__ void __launch_bounds__(128) sosfilt_pass_kernel(const __grid_constant__ SosParams P) {
   const int lane = threadIdx.x & 31;
-  const int cpw = P.cpw;
+  const int cpw = P.cpw, nsec = P.nsec;
   const int groups = (P.ncf + cpw - 1) / cpw;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= (long long)P.n_rec * groups) return;
   const int rec = (int)(warp / groups), grp = (int)(warp % groups);
-  const int ci = lane / P.nsec, s = lane - ci * P.nsec;
+  const int ci = lane / nsec, s = lane - ci * nsec;
   const int j = grp * cpw + ci;                             // filtered-column slot
   const bool live = ci < cpw && j < P.ncf;
   const int col = live ? P.fcols[j] : 0;
@@ -65,61 +66,65 @@ __global__ void __launch_bounds__(128) sosfilt_pass_kernel(const __grid_constant
     z0 = __dmul_rn(P.zi[s][0], first);
     z1 = __dmul_rn(P.zi[s][1], first);
   }
-  // Input staging: the whole warp loads tiles of kTileRows samples x (this warp's columns) into a shared-memory ring,
-  // kRing tiles ahead of the sample being filtered, so the serial recurrence never waits on a global load.
+  // Ring of D = prefetch + sections + 1 blocks per column, pitch kBlock + 1 doubles (lanes of different sections /
+  // columns then fall into different banks).  Step t: the block that left the last section one step ago is stored,
+  // block t + prefetch is loaded, lane (c, s) filters block t - s in place.
   extern __shared__ double s_ring[];
   const int wcols = min(cpw, P.ncf - grp * cpw);            // filtered columns handled by this warp
-  double* ring = s_ring + (size_t)(threadIdx.x >> 5) * kRing * kTileRows * cpw;
-  auto load_tile = [&](int tile) {
-    double* dst = ring + (size_t)(tile % kRing) * kTileRows * cpw;
-    double v[4];
+  const int D = kPrefetch + nsec + 1;
+  constexpr int pitch = kBlock + 1;
+  double* ring = s_ring + (size_t)(threadIdx.x >> 5) * D * cpw * pitch;
+  const int nblocks = (Lext + kBlock - 1) / kBlock;
+  auto load_block = [&](int b) {
+    double* dst = ring + (size_t)(b % D) * cpw * pitch;
+    for (int q0 = 0; q0 < kBlock * wcols; q0 += 128) {       // loads first, then the stores
+      double v[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {                            // issue the loads first, then the stores
-      const int q = lane + 32 * i;
-      const int row = q / wcols, jj = q - row * wcols, e = tile * kTileRows + row;
-      v[i] = (q < kTileRows * wcols && e < Lext) ? input(e, grp * cpw + jj, P.fcols[grp * cpw + jj]) : 0.0;
-    }
+      for (int i = 0; i < 4; ++i) {
+        const int q = q0 + lane + 32 * i;
+        const int u = q / wcols, jj = q - u * wcols, e = b * kBlock + u;
+        v[i] = (q < kBlock * wcols && e < Lext) ? input(e, grp * cpw + jj, P.fcols[grp * cpw + jj]) : 0.0;
+      }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int q = lane + 32 * i;
-      const int row = q / wcols, jj = q - row * wcols;
-      if (q < kTileRows * wcols) dst[row * cpw + jj] = v[i];
-    }
-    for (int q = lane + 128; q < kTileRows * wcols; q += 32) {   // more than 4 columns per warp: plain loop
-      const int row = q / wcols, jj = q - row * wcols, e = tile * kTileRows + row;
-      dst[row * cpw + jj] = e < Lext ? input(e, grp * cpw + jj, P.fcols[grp * cpw + jj]) : 0.0;
+      for (int i = 0; i < 4; ++i) {
+        const int q = q0 + lane + 32 * i;
+        const int u = q / wcols, jj = q - u * wcols;
+        if (q < kBlock * wcols) dst[jj * pitch + u] = v[i];
+      }
     }
   };
-  const int ntiles = (Lext + kTileRows - 1) / kTileRows;
-  for (int tl = 0; tl < kRing - 1 && tl < ntiles; ++tl) load_tile(tl);
+  auto store_block = [&](int b) {
+    const double* src = ring + (size_t)(b % D) * cpw * pitch;
+    for (int q = lane; q < kBlock * wcols; q += 32) {
+      const int u = q / wcols, jj = q - u * wcols, n = b * kBlock + u;
+      if (n >= Lext) continue;
+      const double v = src[jj * pitch + u];
+      if (PASS == 0) {
+        P.tmp[tbase + (long long)n * P.ncf + grp * cpw + jj] = v;
+      } else if (n >= P.edge && n < P.edge + T) {            // reverse + trim
+        P.y[(r0 + (long long)(Lext - 1 - P.edge - n)) * P.ncols + P.fcols[grp * cpw + jj]] = v;
+      }
+    }
+  };
+  for (int b = 0; b < kPrefetch && b < nblocks; ++b) load_block(b);
   __syncwarp();
-  double x_new = 0.0;
-  const int iters = Lext + P.nsec - 1;
-  const bool last = live && s == P.nsec - 1;
-  // output cursor of the last section: forward -> tmp row n; backward -> y row Lext-1-edge-n (reverse + trim)
-  double* outp = PASS == 0 ? P.tmp + tbase + j - (long long)s * P.ncf
-                           : P.y + (r0 + (long long)(Lext - 1 - P.edge + s)) * P.ncols + col;
-  const long long ostep = PASS == 0 ? (long long)P.ncf : -(long long)P.ncols;
-  for (int tile = 0; tile * kTileRows < iters; ++tile) {
-    if (tile + kRing - 1 < ntiles) load_tile(tile + kRing - 1);   // slot (tile-1) % kRing: its reads finished last round
-    const double* src = ring + (size_t)(tile % kRing) * kTileRows * cpw + (live ? ci : 0);   // idle lanes stay in bounds
-#pragma unroll 8
-    for (int u = 0; u < kTileRows; ++u) {
-      const int n = tile * kTileRows + u - s;
-      const double from_prev = __shfl_up_sync(kFull, x_new, 1);
-      const double x_cur = s == 0 ? src[u * cpw] : from_prev;
-      if (live && (unsigned)n < (unsigned)Lext) {
-        x_new = __dadd_rn(__dmul_rn(b0, x_cur), z0);
+  for (int t = 0; t < nblocks + nsec; ++t) {
+    if (t - nsec >= 0) store_block(t - nsec);               // left the last section at step t - 1
+    if (t + kPrefetch < nblocks) load_block(t + kPrefetch); // its slot held block t - nsec - 1, stored at step t - 1
+    const int b = t - s;
+    if (live && b >= 0 && b < nblocks) {
+      double* buf = ring + ((size_t)(b % D) * cpw + ci) * pitch;
+      const int cnt = min(kBlock, Lext - b * kBlock);
+#pragma unroll 4
+      for (int u = 0; u < cnt; ++u) {
+        const double x_cur = buf[u];
+        const double x_new = __dadd_rn(__dmul_rn(b0, x_cur), z0);
         z0 = __dadd_rn(__dsub_rn(__dmul_rn(b1, x_cur), __dmul_rn(a1, x_new)), z1);
         z1 = __dsub_rn(__dmul_rn(b2, x_cur), __dmul_rn(a2, x_new));
-        if (last) {
-          if (PASS == 0) *outp = x_new;
-          else if (n >= P.edge && n < P.edge + T) *outp = x_new;
-        }
+        buf[u] = x_new;
       }
-      outp += ostep;
     }
-    __syncwarp();                                            // the tile just consumed may be overwritten next round
+    __syncwarp();
   }
 }
 
