@@ -244,3 +244,75 @@ def test_extension_stages_stream_per_chunk(tmp_path, monkeypatch):
     a, b = one.materialise(), whole.materialise()
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     assert torch.equal(one.kept_minmax(), whole.kept_minmax())
+
+
+def _guarded(shape, dtype, pad=4096):
+  """A tensor carved out of the middle of a larger buffer whose margins hold a sentinel: (view, check) — check() asserts
+  that no kernel wrote outside the view (compute-sanitizer is closed on this GPU pool)."""
+  n = int(np.prod(shape))
+  sentinel = {torch.float64: 1.2345e300, torch.float32: 1.2345e30, torch.int16: 12345, torch.uint8: 123,
+              torch.int32: 123456789, torch.int64: 1234567890123}[dtype]
+  buf = torch.full((n + 2 * pad,), sentinel, dtype=dtype, device=DEV)
+  view = buf[pad:pad + n].view(*shape)
+  def check():
+    assert bool((buf[:pad] == sentinel).all()) and bool((buf[pad + n:] == sentinel).all()), 'write outside the output buffer'
+  return view, check
+
+
+def test_no_kernel_writes_outside_its_outputs():
+  """Every kernel added for the optional stages / the sweep writes only inside its output buffers: outputs are carved
+  out of sentinel-filled buffers, ragged shapes chosen to end mid-tile / mid-span / mid-chunk."""
+  import scgrhc
+  from scgrhc import ops
+  sig = synth_ref.SIG_NAMES_5
+  rows = [777 + 32 * 24, 5001, 311, 32 * 24 * 3]
+  recs = [synth_ref.gen_record(H.SEED, 500 + r, T, kinds=synth_ref.kinds_for(sig)) for r, T in enumerate(rows)]
+  for ncols in (4, 5):
+    src = torch.from_numpy(np.concatenate([p[:, :ncols] for p in recs])).to(DEV)
+    sos = signal.butter(4, (1.0, 40.0), btype='bandpass', fs=500, output='sos')
+    # band-pass, time-parallel: in place on a guarded arena
+    arena, chk = _guarded(tuple(src.shape), torch.float64)
+    arena.copy_(src)
+    got = filters.sosfiltfilt(arena, rows, sos, [0, 1, 2], exact=False, inplace=True)
+    chk()
+    want = filters.sosfiltfilt(src, rows, sos, [0, 1, 2], exact=False)
+    assert torch.equal(got, want)
+    # decimation by 2 and by 5 and a general ratio into guarded outputs (through the C ABI: the wrapper allocates its own)
+    for up, down in ((1, 2), (1, 5), (2, 3)):
+      ref, out_rows = filters.resample_poly(src, rows, up, down)
+      import ctypes as C
+      from scgrhc import _native as N
+      d = filters.resample_design(rows[0], up, down)
+      designs = [filters.resample_design(n, up, down) for n in rows]
+      out, chk = _guarded((sum(out_rows), ncols), torch.float64)
+      in0 = torch.from_numpy(np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)).to(DEV)
+      out0 = torch.from_numpy(np.concatenate([[0], np.cumsum(out_rows)]).astype(np.int64)).to(DEV)
+      taps = torch.from_numpy(d[3]).to(DEV)
+      c = ops.ctx(0)
+      N.check(c, N.lib().scgrhc_resample_poly(c, ops._ptr(src), ops._ptr(out), ops._ptr(taps), ops._ptr(in0), ops._ptr(out0), len(rows),
+                                              max(out_rows), ncols, d[0], d[1], d[4], d[5], 0, ops._stream(0)))
+      chk()
+      assert torch.equal(out, ref)
+  # sweep fan-out: every output of every subset guarded
+  src = torch.from_numpy(np.concatenate(recs)).to(DEV)
+  metas = [synth_ref.record_meta(max(2, T // 500), events={'PA_1': 0.2}) for T in rows]
+  plan = scgrhc.plan_cohort(metas, 'PA', rows, 333)
+  pred = scgrhc.prepare_windows(src, plan, [0], 3, -50.0, predicates_only=True)
+  n = pred.n_kept
+  assert n > 3
+  subsets, members, counts = [[0, 1, 2, 4], [1], [0, 4]], [0, 1, 2, 3, 1, 0, 3], [4, 1, 2]
+  scgs, mms, checks = [], [], []
+  for cnt in counts:
+    t, chk = _guarded((n, cnt, 333), torch.float32); scgs.append(t); checks.append(chk)
+    t, chk = _guarded((n, 4), torch.float64); mms.append(t); checks.append(chk)
+  rhc, chk = _guarded((n, 1, 333), torch.float32); checks.append(chk)
+  ops.normalize_subsets(src, plan.device_intervals(src.device), 333, 0, [0, 1, 2, 4], 3, pred.kept_idx, n, members, counts, False, scgs, mms, rhc)
+  for chk in checks:
+    chk()
+  ref = scgrhc.prepare_windows(src, plan, [0, 4], 3, -50.0)
+  assert torch.equal(scgs[2], ref.materialise()[0]) and torch.equal(rhc, ref.materialise()[1])
+  # format-16 decode, 3 of 5 columns
+  d16 = torch.randint(-32768, 32767, (4099, 5), dtype=torch.int16, device=DEV)
+  out, chk = _guarded((4099, 3), torch.float64)
+  ops.decode_fmt16(d16, [4, 0, 2], [200.0, 3.0, 0.5], [0.0, 1.0, -2.0], out)
+  chk()
