@@ -468,6 +468,13 @@ def save_dataloaders(params):
   """
   Get training and test segments, then save as loader objects (recordutil.py:172-216).
   """
+  _check_no_loaders(params)
+  store, names = prepare_cohort(params)
+  _write_loaders(params, store, names)
+
+
+def _check_no_loaders(params):
+  """The reference's guards, same messages (recordutil.py:176-181; waveform_pipeline.py:12-15 relies on them)."""
   if os.path.exists(params.train_path):
     raise Exception('Train file already exists!')
   elif os.path.exists(params.valid_path):
@@ -475,7 +482,9 @@ def save_dataloaders(params):
   elif os.path.exists(params.test_path):
     raise Exception('Test file already exists!')
 
-  store, names = prepare_cohort(params)
+
+def _write_loaders(params, store, names):
+  """Split 90/5/5, build the three loaders, pickle them and write record_log.txt (recordutil.py:191-216)."""
   n_all = store.n_kept
   train_idx, valid_idx, test_idx = train_valid_test_split(n_all, getattr(params, 'split_seed', None))
 
@@ -513,6 +522,64 @@ def save_dataloaders(params):
     f.write(f'Valid segments: {len(valid_idx)}\n')
     f.write(f'Train segments: {len(train_idx)}\n')
     f.write(f'Test segments: {len(test_idx)}\n')
+
+
+def save_dataloaders_sweep(params_list, record_names=None):
+  """Extension (BASELINE configs[4]; the reference runs its `all` sweep as independent jobs, waveform_pipeline.py:33-37):
+  data preparation for SEVERAL experiment configs over one cohort.  Every record is read and uploaded once (the union
+  of the configs' channels + RHC); configs that differ only in their channel subset share one predicate pass and one
+  fan-out pass (scgrhc.sweep.iter_sweep); each config then gets its three pickled loaders and record_log.txt exactly as
+  save_dataloaders writes them.  Configs whose loaders already exist are reported and skipped, like the reference's
+  guard; configs with optional-stage keys (band-pass, resample, stride, z-score) take the single-config path.
+  Returns {dir_path: n_kept}."""
+  from scgrhc import sweep
+  todo, single, out = [], [], {}
+  for params in params_list:
+    try:
+      _check_no_loaders(params)
+    except Exception as e:
+      print(e)
+      continue
+    ext = any(getattr(params, k, None) for k in ('bandpass', 'bandpass_sos', 'resample_rate', 'segment_stride')) or \
+        getattr(params, 'normalisation', None) not in (None, 'minmax')
+    (single if ext else todo).append(params)
+  for params in single:
+    save_dataloaders(params)
+    out[params.dir_path] = None
+  if not todo:
+    return out
+  names = list(record_names) if record_names is not None else get_record_names()
+  wanted = []
+  for params in todo:
+    for ch in params.in_channels:
+      if ch not in wanted:
+        wanted.append(ch)
+  records, metas, rows, sig = [], [], [], None
+  for name in names:
+    record = wfdb.rdrecord(os.path.join(PROCESSED_DATA_PATH, name))
+    order = sorted(wanted, key=record.sig_name.index)          # ValueError for a missing channel, as list.index does
+    cols, rcol = engine.resolve_columns(record.sig_name, order)
+    this_sig = order + [engine.RHC_NAME]
+    if sig is None:
+      sig = this_sig
+    elif sig != this_sig:
+      raise ValueError('records of one sweep must list the selected signals in the same order (%s vs %s)' % (sig, this_sig))
+    records.append(np.ascontiguousarray(record.p_signal[:, cols + [rcol]], dtype=np.float64))
+    metas.append(_read_meta(name))
+    rows.append(records[-1].shape[0])
+  dev = _device()
+  host = torch.empty((int(sum(rows)), len(sig)), dtype=torch.float64, pin_memory=True)
+  at = 0
+  for block in records:
+    host[at:at + len(block)] = torch.from_numpy(block)
+    at += len(block)
+  arena = host.to(dev, non_blocking=True)
+  configs = {str(i): p for i, p in enumerate(todo)}
+  for key, store in sweep.iter_sweep(arena, sig, metas, rows, configs, buffers={}):
+    params = configs[key]
+    _write_loaders(params, store, names)
+    out[params.dir_path] = store.n_kept
+  return out
 
 
 def load_dataloader(path):

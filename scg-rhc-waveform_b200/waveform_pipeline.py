@@ -43,14 +43,11 @@ def run(params):
 
 
 def prepare_all(dir_names):
-  """Extension: data preparation only, for several experiment directories (the 37-config sweep of
-  BASELINE.json configs[4]).  Each config is one fused pass over the cohort."""
-  for dir_name in dir_names:
-    params = Params(os.path.join(dir_name, 'params.json'))
-    try:
-      recordutil(params)
-    except Exception as e:
-      print(e)
+  """Extension: data preparation only, for several experiment directories (the 37-config sweep of BASELINE.json
+  configs[4]).  The cohort is read and uploaded once; configs that differ only in their channel subset share one
+  predicate pass and one fan-out pass (recordutil.save_dataloaders_sweep)."""
+  from recordutil import save_dataloaders_sweep
+  return save_dataloaders_sweep([Params(os.path.join(d, 'params.json')) for d in dir_names])
 
 
 if __name__ == '__main__':

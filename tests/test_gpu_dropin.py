@@ -174,6 +174,55 @@ def test_save_dataloaders_end_to_end(tmp_path, monkeypatch):
   assert seen == set(want)                                  # every kept window lands in exactly one split
 
 
+def test_save_dataloaders_sweep_equals_one_job_per_config(tmp_path, monkeypatch):
+  """`waveform_pipeline.py prepare d1 d2 ...`: one read + one upload of the cohort, one predicate pass and one fan-out pass
+  per chamber — and every config directory ends up with the loaders a separate save_dataloaders job writes."""
+  import waveform_pipeline
+  root = tmp_path / 'data'; root.mkdir()
+  monkeypatch.setattr(recordutil, 'PROCESSED_DATA_PATH', str(root))
+  monkeypatch.setattr(recordutil, 'wfdb', wfdbio)
+  sig = synth_ref.SIG_NAMES_5
+  for r in range(3):
+    meta = synth_ref.record_meta(120, events={'RA_1': 0, 'PA_1': 20 + r, 'RV_1': 100, 'PCW_1': 110})
+    p = synth_ref.gen_record(H.SEED, 140 + r, 60000 + 500 * r, kinds=synth_ref.kinds_for(sig))
+    wfdbio.wrsamp('rec%d' % r, 500, ['g', 'g', 'g', 'mmHg', 'mV'], sig, p, write_dir=str(root))
+    (root / ('rec%d.json' % r)).write_text(json.dumps(meta))
+  table = H.configs()
+  cfgs = ['waveform_06', 'waveform_07', 'waveform_09', 'waveform_10', 'waveform_25', 'waveform_11', 'waveform_04']
+  dirs = {}
+  for tag in ('sweep', 'single'):
+    for cfg in cfgs:
+      d = tmp_path / tag / cfg; d.mkdir(parents=True)
+      e = H.effective_config(cfg, table)
+      c = dict(in_channels=e['in_channels'], chamber=e['chamber'], segment_size=e['segment_size'], batch_size=e['batch_size'],
+               min_RHC=e['min_RHC'], use_global_min_max=e['use_global_min_max'],
+               dir_path=str(d), train_path='loader_train.pickle', valid_path='loader_valid.pickle', test_path='loader_test.pickle',
+               split_seed=11, comparison_dir_path='comparisons', checkpoint_dir_path='checkpoints',
+               pred_top_dir_path='pred_top', pred_rand_dir_path='pred_rand', alpha=1e-4, beta1=0.5, beta2=0.999, n_critic=2,
+               lambda_gp=10, lambda_aux=1, total_epochs=1)
+      (d / 'params.json').write_text(json.dumps(c))
+      dirs[(tag, cfg)] = d
+  names = sorted(recordutil.get_record_names())
+  monkeypatch.setattr(recordutil, 'get_record_names', lambda: names)     # the reference's order is hash-random (list(set))
+  counts = waveform_pipeline.prepare_all([str(dirs[('sweep', c)]) for c in cfgs])
+  assert all(v for v in counts.values()) and len(counts) == len(cfgs)
+  from paramutil import Params
+  for cfg in cfgs:
+    recordutil.run(Params(str(dirs[('single', cfg)] / 'params.json')))
+    for which in ('train', 'valid', 'test'):
+      a = recordutil.load_dataloader(str(dirs[('sweep', cfg)] / ('loader_%s.pickle' % which))).dataset
+      b = recordutil.load_dataloader(str(dirs[('single', cfg)] / ('loader_%s.pickle' % which))).dataset
+      assert len(a) == len(b) > 0, (cfg, which)
+      for x, y in zip(a, b):
+        assert torch.equal(x[0].cpu(), y[0].cpu()) and torch.equal(x[1].cpu(), y[1].cpu()), (cfg, which)
+        assert (x[2], int(x[3]), int(x[4])) == (y[2], int(y[3]), int(y[4]))
+        assert tuple(x[5]) == tuple(y[5]) and tuple(x[6]) == tuple(y[6])
+    la = (dirs[('sweep', cfg)] / 'record_log.txt').read_text().splitlines()[1:]
+    assert la == (dirs[('single', cfg)] / 'record_log.txt').read_text().splitlines()[1:]
+  # a second run reports the existing loaders and touches nothing, like the reference's guard
+  assert waveform_pipeline.prepare_all([str(dirs[('sweep', c)]) for c in cfgs[:2]]) == {}
+
+
 def test_device_decode_matches_host_dac_and_digital_ingest(tmp_path, monkeypatch):
   """Format-16 frames decoded on the device == wfdb's host-side (d - baseline) / gain, bit for bit; the digital
   ingest path (int16 over PCIe) gives the same windows as the physical one, also with dataset-global pairs."""
