@@ -84,6 +84,12 @@ __device__ __forceinline__ double div_by_recip(double a, double d, double inv) {
   return q;
 }
 
+// Tier 1 of the fp32 normalisation (window_kernel.cuh): q0 = RN(a * RN(1/d)) rounds to the same float as the exact
+// quotient unless the low 29 bits of its mantissa lie within [0x0ffffff8, 0x10000008] (8 ulp64 around a float rounding
+// boundary).  key = 8 * (distance of those bits from 0x0ffffff8), wrapping: risky <=> key <= kTier1Risky.  One shift-add.
+constexpr uint32_t kTier1Risky = 128u;
+__device__ __forceinline__ uint32_t tier1_key(double q0) { return ((uint32_t)__double2loint(q0) << 3) - 0x7fffffc0u; }
+
 // streaming stores (outputs are written once and not re-read by this kernel)
 __device__ __forceinline__ void st_cs(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_cs(double* p, double v) { __stcs(p, v); }

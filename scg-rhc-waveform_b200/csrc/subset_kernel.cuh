@@ -54,11 +54,11 @@ __device__ __forceinline__ void norm_store(const Normaliser& nz, const double (&
         for (int k = 0; k < R; ++k) {
           if (tid + k * NT < W) {
             const double q0 = __dmul_rn(__dsub_rn(v[k], nz.mn), nz.inv);
-            acc = min(acc, ((uint32_t)__double2loint(q0) + 0x10000008u) & 0x1fffffffu);
+            acc = min(acc, tier1_key(q0));
             st_cs(base + k * NT, __double2float_rn(q0));
           }
         }
-        redo = acc <= 16u;
+        redo = acc <= kTier1Risky;
       }
     }
     if (redo) {

@@ -153,8 +153,7 @@ __global__ void __launch_bounds__(256) selftest_div_kernel(unsigned long long se
     if (mode == 2) {
       if (nz.quick) {
         const double q0 = __dmul_rn(__dsub_rn(x, nz.mn), nz.inv);
-        const uint32_t dist = ((uint32_t)__double2loint(q0) + 0x10000008u) & 0x1fffffffu;
-        if (dist <= 16u) ++cnt;      // risky: the kernel recomputes these exactly
+        if (tier1_key(q0) <= kTier1Risky) ++cnt;      // risky: the kernel recomputes these exactly
         else bad32 += (__float_as_int(__double2float_rn(q0)) != __float_as_int(__double2float_rn(ref)));
       } else {
         ++bad64;                     // operands of this mode must all qualify for tier 1
@@ -358,22 +357,29 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
       s1 = warp_sum(s1); s2 = warp_sum(__dadd_rn(s2, nanacc)); sxy = warp_sum(sxy);
       if (lane == 0) {
         double* r = S.red[par2][warp];
-        r[0] = a_smin; r[1] = a_smax; r[2] = a_ymin; r[3] = a_ymax; r[4] = s1; r[5] = s2; r[6] = sxy;
-        r[7] = dense_word ? 1.0 : 0.0;
+        r[0] = -a_smin; r[1] = a_smax; r[2] = -a_ymin; r[3] = a_ymax; r[4] = s1; r[5] = s2; r[6] = sxy;   // minima negated:
+        r[7] = dense_word ? 1.0 : 0.0;                                                                  // slots 0..3 all take a max
       }
       __syncthreads();  // the only block barrier of the common path; every thread is also done with the stage
 
+      // block combine, lane parallel: lane v & 7 folds slot v over the warps (same order as a serial fold: ties keep the
+      // earlier warp, sums add warp 0 + 1 + 2 + 3), then the eight results are broadcast — ~40 instructions per thread
+      // instead of ~90 for every thread folding all eight slots itself
       double dense;
       {
-        const double* r = S.red[par2][0];
-        smin = r[0]; smax = r[1]; ymin = r[2]; ymax = r[3]; s1 = r[4]; s2 = r[5]; sxy = r[6]; dense = r[7];
+        const int v = lane & 7;
+        double a = S.red[par2][0][v];
 #pragma unroll
         for (int w = 1; w < NWARP; ++w) {
-          r = S.red[par2][w];
-          smin = r[0] < smin ? r[0] : smin; smax = r[1] > smax ? r[1] : smax;
-          ymin = r[2] < ymin ? r[2] : ymin; ymax = r[3] > ymax ? r[3] : ymax;
-          s1 = __dadd_rn(s1, r[4]); s2 = __dadd_rn(s2, r[5]); sxy = __dadd_rn(sxy, r[6]); dense = __dadd_rn(dense, r[7]);
+          const double b = S.red[par2][w][v];
+          const double mx = b > a ? b : a;
+          const double sm = __dadd_rn(a, b);
+          a = v < 4 ? mx : sm;
         }
+        smin = -__shfl_sync(kFull, a, 0); smax = __shfl_sync(kFull, a, 1);
+        ymin = -__shfl_sync(kFull, a, 2); ymax = __shfl_sync(kFull, a, 3);
+        s1 = __shfl_sync(kFull, a, 4); s2 = __shfl_sync(kFull, a, 5); sxy = __shfl_sync(kFull, a, 6);
+        dense = __shfl_sync(kFull, a, 7);
       }
       // `dense` counts the warps that saw a dense mask word; only then scan the small-step mask for
       // >= 49 consecutive ones (every warp does, on the same shared words: no second barrier)
@@ -583,15 +589,15 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
 #pragma unroll
               for (int c = 0; c < C; ++c) {
                 const double q0 = __dmul_rn(__dsub_rn(x[k][c], ns.mn), ns.inv);
-                acc = min(acc, ((uint32_t)__double2loint(q0) + 0x10000008u) & 0x1fffffffu);
+                acc = min(acc, tier1_key(q0));
                 st_cs(so + (size_t)c * W + k * NT, __double2float_rn(q0));
               }
               const double q0 = __dmul_rn(__dsub_rn(y[k], nr.mn), nr.inv);
-              acc = min(acc, ((uint32_t)__double2loint(q0) + 0x10000008u) & 0x1fffffffu);
+              acc = min(acc, tier1_key(q0));
               st_cs(ro + k * NT, __double2float_rn(q0));
             }
           }
-          redo = acc <= 16u;
+          redo = acc <= kTier1Risky;
         }
       }
       if (!redo) {
