@@ -42,7 +42,8 @@ def test_sosfiltfilt_matches_scipy(order, band, btype):
 
 @pytest.mark.parametrize('order,band,btype,chunk,nbuf,tol', [(4, (1.0, 40.0), 'bandpass', 0, 0, 1e-10), (2, (0.5, 20.0), 'bandpass', 24, 1, 1e-10),
                                                              (4, 30.0, 'low', 7, 2, 1e-10), (3, 2.0, 'high', 32, 1, 1e-10),
-                                                             (1, 5.0, 'low', 3, 2, 1e-10), (4, (1.0, 40.0), 'bandpass', 12, 2, 1e-10)])
+                                                             (1, 5.0, 'low', 3, 2, 1e-10), (4, (1.0, 40.0), 'bandpass', 12, 2, 1e-10),
+                                                             (3, (2.0, 35.0), 'bandpass', 0, 0, 1e-10), (6, 45.0, 'low', 24, 1, 1e-10)])
 def test_sosfiltfilt_time_parallel_scan_within_1e_10(order, band, btype, chunk, nbuf, tol):
   """The time-parallel variant (BASELINE north_star: fp64 device mode within 1e-10) against scipy and the exact kernel:
   5 signals per row (40-byte rows: plain warp copies, two column groups, the second in place) and 4 signals per row
