@@ -140,8 +140,22 @@ def test_filter_resample_window_pipeline_against_scipy_plus_oracle():
   assert plan.n_cand == n and st.keep.cpu().numpy().astype(bool).tolist() == keep.tolist() and 0 < keep.sum() < n
   scg = q[:, :3][idx][keep]
   mm = scg.min(axis=(1, 2)), scg.max(axis=(1, 2))
-  want = ((scg - mm[0][:, None, None]) / (mm[1] - mm[0] + 0.0001)[:, None, None]).transpose(0, 2, 1).astype(np.float32)
+  want64 = ((scg - mm[0][:, None, None]) / (mm[1] - mm[0] + 0.0001)[:, None, None]).transpose(0, 2, 1)
+  want = want64.astype(np.float32)
   assert st.materialise()[0].cpu().numpy().tobytes() == np.ascontiguousarray(want).tobytes()
+  # BASELINE configs[1]: fp32 vs fp64 tolerance check of the whole chain — the fp64 device mode against the fp64 host chain
+  # within 1e-10 (here: equal), the fp32 mode against it within rel 1e-5; and the fast modes of every stage (time-parallel
+  # band-pass, fused-multiply-add decimator) within 1e-10 of full scale before the cast
+  st64 = scgrhc.prepare_windows(r, plan, [0, 1, 2], 3, -50.0, out_dtype=torch.float64)
+  got64 = st64.materialise()[0].cpu().numpy()
+  assert np.abs(got64 - want64).max() <= 1e-10 and got64.tobytes() == np.ascontiguousarray(want64).tobytes()
+  assert np.abs(st.materialise()[0].cpu().numpy().astype(np.float64) - want64).max() <= 1e-5
+  ff = filters.sosfiltfilt(arena, [T], sos, [0, 1, 2], exact=False)
+  rf, _ = filters.resample_poly(ff, [T], 250, 500, exact=False)
+  assert (np.abs(rf.cpu().numpy() - q) / np.abs(q).max(axis=0)).max() <= 1e-10
+  stf = scgrhc.prepare_windows(rf, plan, [0, 1, 2], 3, -50.0, out_dtype=torch.float64)
+  assert torch.equal(stf.keep, st64.keep)
+  assert np.abs(stf.materialise()[0].cpu().numpy() - want64).max() <= 1e-9     # normalised samples in [0, 1]; 1e-10 x window scale
 
 
 def test_recordutil_optional_keys_drive_the_extension_stages(tmp_path, monkeypatch):
