@@ -284,41 +284,59 @@ __global__ void __launch_bounds__(kDecNT) resample_decim_kernel(const __grid_con
       // accumulators in that order; the columns are put back once, at the store.
       const double* base = s_x + (size_t)tid * (PB + 1) * NC;
       const int J = pp + (kDecR - 1) * down, ramp = (kDecR - 1) * down;
-      int j = 0;
-      for (int blk = 0; j < J; ++blk) {
-        const double* pb = base + ((size_t)blk * (PB + 1) - (size_t)blk * PB) * NC;   // row j of this block: pb + j * NC
-        const int jend = min(J, (blk + 1) * PB);
-#pragma unroll 4
-        for (; j < jend; ++j) {
-          double xv[NC];
-          const double* p = pb + (size_t)j * NC;
-          if constexpr (NC == 4) {
-            const double2 a = *reinterpret_cast<const double2*>(p + (swap ? 2 : 0));
-            const double2 b = *reinterpret_cast<const double2*>(p + (swap ? 0 : 2));
-            xv[0] = a.x; xv[1] = a.y; xv[2] = b.x; xv[3] = b.y;
-          } else {
+      auto load_row = [&](const double* p, double (&xv)[NC]) {
+        if constexpr (NC == 4) {
+          const double2 a = *reinterpret_cast<const double2*>(p + (swap ? 2 : 0));
+          const double2 b = *reinterpret_cast<const double2*>(p + (swap ? 0 : 2));
+          xv[0] = a.x; xv[1] = a.y; xv[2] = b.x; xv[3] = b.y;
+        } else {
 #pragma unroll
-            for (int c = 0; c < NC; ++c) xv[c] = p[c];
-          }
-          if (j >= ramp && j < pp) {                          // steady state: every output takes this row
+          for (int c = 0; c < NC; ++c) xv[c] = p[c];
+        }
+      };
+      auto some = [&](int j, const double (&xv)[NC]) {        // ramp-up / ramp-down: output r takes rows r*down .. r*down + pp - 1
 #pragma unroll
-            for (int r = 0; r < kDecR; ++r) {
-              const double hk = s_taps[j - r * down];
+        for (int r = 0; r < kDecR; ++r) {
+          const int k = j - r * down;
+          if (k >= 0 && k < pp) {
+            const double hk = s_taps[k];
 #pragma unroll
-              for (int c = 0; c < NC; ++c) acc[r][c] = FUSED ? __fma_rn(xv[c], hk, acc[r][c]) : __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
-            }
-          } else {                                            // ramp-up / ramp-down: output r takes rows r*down .. r*down + pp - 1
-#pragma unroll
-            for (int r = 0; r < kDecR; ++r) {
-              const int k = j - r * down;
-              if (k >= 0 && k < pp) {
-                const double hk = s_taps[k];
-#pragma unroll
-                for (int c = 0; c < NC; ++c) acc[r][c] = FUSED ? __fma_rn(xv[c], hk, acc[r][c]) : __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
-              }
-            }
+            for (int c = 0; c < NC; ++c) acc[r][c] = FUSED ? __fma_rn(xv[c], hk, acc[r][c]) : __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
           }
         }
+      };
+      // Row j sits at pb + j * NC while it belongs to the current block of PB rows (one pad row per block).  Three
+      // loops, so that the steady one is branch-free and the compiler can run the loads of the next rows ahead.
+      const double* pb = base;
+      int j = 0, bend = PB;
+      for (; j < ramp; ++j) {                                 // ramp < PB: all in block 0
+        double xv[NC];
+        load_row(pb + (size_t)j * NC, xv);
+        some(j, xv);
+      }
+      while (j < pp) {                                        // steady state: every output takes the row
+        const int je = min(pp, bend);
+#pragma unroll 4
+        for (; j < je; ++j) {
+          double xv[NC];
+          load_row(pb + (size_t)j * NC, xv);
+#pragma unroll
+          for (int r = 0; r < kDecR; ++r) {
+            const double hk = s_taps[j - r * down];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) acc[r][c] = FUSED ? __fma_rn(xv[c], hk, acc[r][c]) : __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
+          }
+        }
+        if (j == bend) { bend += PB; pb += NC; }
+      }
+      while (j < J) {
+        const int je = min(J, bend);
+        for (; j < je; ++j) {
+          double xv[NC];
+          load_row(pb + (size_t)j * NC, xv);
+          some(j, xv);
+        }
+        if (j == bend) { bend += PB; pb += NC; }
       }
       if constexpr (NC == 4) {
 #pragma unroll
