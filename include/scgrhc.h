@@ -47,7 +47,8 @@ typedef enum {
 #define SCGRHC_REASON_STRAIGHT  2u  /* R^2 > 0.8                 (waveform_noise.py:34) */
 #define SCGRHC_REASON_FLOOR     4u  /* a sample < min_RHC        (waveform_noise.py:38-40) */
 #define SCGRHC_REASON_NONFINITE 8u  /* NaN/Inf reached the regression -> reference raises */
-#define SCGRHC_REASON_AMBIGUOUS 16u /* |R^2 - 0.8| < 1e-12: closed form vs lstsq could disagree */
+#define SCGRHC_REASON_AMBIGUOUS 16u /* |R^2 - 0.8| < 1e-9 * R^2-scale (relative): closed form vs sklearn's lstsq could disagree in
+                                       the last bits; decided by the closed form, counted by scgrhc_ambiguous_count */
 
 /* job flags */
 #define SCGRHC_OUT_F64        1u  /* write fp64 windows instead of fp32 (torch.float32 at recordutil.py:53) */
@@ -179,6 +180,10 @@ int scgrhc_global_minmax(scgrhc_ctx* ctx, const double* minmax, const uint8_t* k
 /* ---- error word of the last process call: synchronises `stream`; returns SCGRHC_ERR_NONFINITE_RHC
  *      and the first offending candidate when a non-finite RHC sample reached the regression. */
 int scgrhc_check_errors(scgrhc_ctx* ctx, void* stream, int64_t* first_bad_cand);
+/* Candidate windows flagged SCGRHC_REASON_AMBIGUOUS by the process calls the last scgrhc_check_errors covered (no
+ * synchronisation of its own; -1 for a NULL context).  SURVEY.md §7: the closed-form R^2 and the reference's
+ * sklearn/LAPACK score agree to ~6e-16, so only these windows could be decided differently; callers warn when > 0. */
+int64_t scgrhc_ambiguous_count(const scgrhc_ctx* ctx);
 
 /* ---- batch collate (default_collate of recordutil.py:198): out[b] = store[slot[b]] ---------- */
 int scgrhc_gather_windows(scgrhc_ctx* ctx, const void* store, const int64_t* slots, int64_t n,
@@ -243,6 +248,15 @@ int scgrhc_rolling_range_lt(scgrhc_ctx* ctx, const double* y, int64_t n, int32_t
  *      (d - baseline) / gain, the invalid code -32768 -> NaN.  gain/baseline/cols are host arrays of ncols entries. */
 int scgrhc_decode_fmt16(scgrhc_ctx* ctx, const int16_t* d, int64_t T, int32_t nsig_in, const int32_t* cols,
                         int32_t ncols, const double* gain, const double* baseline, double* out, void* stream);
+
+/* The same for a chunk of n_rec records back to back, each with its own calibration (one launch per chunk instead of one
+ * per record): rec_row0 (n_rec+1, device) = first frame of every record inside d / out; gain, baseline (n_rec, ncols)
+ * device tables; max_rec_rows = the longest record of the chunk; recip != 0 selects the reciprocal-based quotient
+ * (bit-identical to IEEE division; the caller has checked 2^-40 <= |gain| <= 2^60 and integer |baseline| < 2^16 for the
+ * whole table), 0 = IEEE division. */
+int scgrhc_decode_fmt16_records(scgrhc_ctx* ctx, const int16_t* d, const int64_t* rec_row0_dev, int32_t n_rec,
+                                int64_t max_rec_rows, int32_t nsig_in, const int32_t* cols, int32_t ncols,
+                                const double* gain_dev, const double* baseline_dev, int32_t recip, double* out, void* stream);
 
 /* ---- is_straight_line / in_rhc_range on waveforms of any length (waveform_noise.py:29-41), one
  *      waveform per row of y (n_wave, L); stats (n_wave, 6) = {R^2, min, max, below_floor, nonfinite, sum} */

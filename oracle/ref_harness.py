@@ -20,10 +20,15 @@ import tempfile
 import types
 
 REFERENCE_PATH = os.environ.get('SCGRHC_REFERENCE_PATH', '/root/reference')
+STAGED_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')   # oracle/make_ref.py: byte copies for the GPU box
 
 
 def reference_available():
   return os.path.isfile(os.path.join(REFERENCE_PATH, 'recordutil.py'))
+
+
+def staged_available():
+  return os.path.isfile(os.path.join(STAGED_PATH, 'recordutil.py'))
 
 
 class FakeRecord:
@@ -36,8 +41,11 @@ class FakeRecord:
 
 
 class ReferenceHarness:
-  def __init__(self):
-    if not reference_available():
+  def __init__(self, path=None):
+    """``path``: where the reference's modules live (default: /root/reference; the GPU box passes STAGED_PATH)."""
+    REFERENCE_PATH = path or globals()['REFERENCE_PATH']
+    self.path = REFERENCE_PATH
+    if not os.path.isfile(os.path.join(REFERENCE_PATH, 'recordutil.py')):
       raise RuntimeError('reference not present at %s' % REFERENCE_PATH)
     self.tmp = tempfile.TemporaryDirectory(prefix='scgrhc_ref_')
     self.records = {}
@@ -92,7 +100,7 @@ class ReferenceHarness:
   def params(self, config_dir, **overrides):
     """Reference ``Params`` for ``waveform_NN``; for the 5 legacy configs that the reference's
     own loader rejects the missing keys come from ``overrides``."""
-    path = os.path.join(REFERENCE_PATH, config_dir, 'params.json')
+    path = os.path.join(self.path, config_dir, 'params.json')
     try:
       p = self.paramutil.Params(path)
     except KeyError:

@@ -23,7 +23,8 @@ struct scgrhc_ctx {
   int sm_count = 0;
   int ctas_per_sm = 0;  // 0 = from occupancy
   int stages = 0;       // 0 = default
-  unsigned long long* err_dev = nullptr;  // 2 words
+  unsigned long long* err_dev = nullptr;  // 3 words: flags, first bad candidate, ambiguous windows
+  long long last_ambiguous = 0;           // word 2 as read by the last scgrhc_check_errors
   int* block_counts = nullptr;
   long long* block_offsets = nullptr;
   long long scan_cap = 0;
@@ -80,7 +81,7 @@ extern "C" int scgrhc_ctx_create(int device, scgrhc_ctx** out) {
     return fail(nullptr, SCGRHC_ERR_UNSUPPORTED, "device %d is sm_%d%d; libscgrhc is built for sm_100a only", device, prop.major, prop.minor);
   }
   ctx->sm_count = prop.multiProcessorCount;
-  CUDA_TRY(nullptr, cudaMalloc(&ctx->err_dev, 2 * sizeof(unsigned long long)));
+  CUDA_TRY(nullptr, cudaMalloc(&ctx->err_dev, 4 * sizeof(unsigned long long)));
   CUDA_TRY(nullptr, cudaMalloc(&ctx->mm_partial, GMM_BLOCKS * 4 * sizeof(double)));
   *out = ctx;
   return SCGRHC_OK;
@@ -257,6 +258,7 @@ extern "C" int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, co
   if (!(J.flags & SCGRHC_KEEP_ERRORS)) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->err_dev, 0, sizeof(unsigned long long), st));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->err_dev + 1, 0xFF, sizeof(unsigned long long), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->err_dev + 2, 0, sizeof(unsigned long long), st));
   }
   if (items == 0) return SCGRHC_OK;
   if (!J.intervals || J.n_intervals == 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "candidates without intervals");
@@ -334,15 +336,18 @@ extern "C" int scgrhc_normalize_subsets(scgrhc_ctx* ctx, const scgrhc_job* job, 
 extern "C" int scgrhc_check_errors(scgrhc_ctx* ctx, void* stream, int64_t* first_bad_cand) {
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  unsigned long long h[2] = {0, 0};
+  unsigned long long h[3] = {0, 0, 0};
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->err_dev, sizeof h, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  ctx->last_ambiguous = (long long)h[2];
   if (first_bad_cand) *first_bad_cand = (h[0] & 1ull) ? (int64_t)h[1] : -1;
   if (h[0] & 1ull)
     return fail(ctx, SCGRHC_ERR_NONFINITE_RHC, "Input y contains NaN. (candidate window %lld; waveform_noise.py:32)", (long long)h[1]);
   return SCGRHC_OK;
 }
+
+extern "C" int64_t scgrhc_ambiguous_count(const scgrhc_ctx* ctx) { return ctx ? ctx->last_ambiguous : -1; }
 
 // ---- ordered compaction ----------------------------------------------------------------------------
 static int ensure_scan(scgrhc_ctx* ctx, long long nblocks) {
@@ -756,6 +761,40 @@ extern "C" int scgrhc_decode_fmt16(scgrhc_ctx* ctx, const int16_t* d, int64_t T,
     const long long total = T * ncols;
     const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16);
     decode_fmt16_kernel<<<grid, 256, 0, st>>>(P);
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_decode_fmt16_records(scgrhc_ctx* ctx, const int16_t* d, const int64_t* rec_row0_dev, int32_t n_rec,
+                                           int64_t max_rec_rows, int32_t nsig_in, const int32_t* cols, int32_t ncols,
+                                           const double* gain_dev, const double* baseline_dev, int32_t recip, double* out,
+                                           void* stream) {
+  NvtxRange nvtx_range("scgrhc_decode_fmt16_records");
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (n_rec < 0 || max_rec_rows < 0 || nsig_in < 1 || ncols < 1 || ncols > SCGRHC_MAX_C + 1 || !cols ||
+      (n_rec && (!d || !out || !rec_row0_dev || !gain_dev || !baseline_dev)))
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "decode_fmt16_records: bad arguments (1..%d output columns)", SCGRHC_MAX_C + 1);
+  if (n_rec > 65535) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "decode_fmt16_records: at most 65535 records per call");
+  DecodeRecParams P;
+  P.d = d; P.out = out; P.rec_row0 = reinterpret_cast<const long long*>(rec_row0_dev); P.gain = gain_dev; P.baseline = baseline_dev;
+  P.n_rec = n_rec; P.nsig_in = nsig_in; P.ncols = ncols; P.recip = recip ? 1 : 0;
+  for (int j = 0; j < ncols; ++j) {
+    if (cols[j] < 0 || cols[j] >= nsig_in) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "decode_fmt16_records: column %d outside 0..%d", cols[j], nsig_in - 1);
+    P.cols[j] = cols[j];
+  }
+  if (n_rec == 0 || max_rec_rows == 0) return SCGRHC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  // enough CTAs per record to fill the GPU when the chunk holds few records, no more than the record has frames for
+  const long long per_rec = std::max<long long>(1, ((long long)ctx->sm_count * 16 + n_rec - 1) / n_rec);
+  dim3 grid((unsigned)std::min<long long>((max_rec_rows + 255) / 256, per_rec), (unsigned)n_rec);
+  switch (ncols) {
+    case 1: decode_fmt16_records_kernel<1><<<grid, 256, 0, st>>>(P); break;
+    case 2: decode_fmt16_records_kernel<2><<<grid, 256, 0, st>>>(P); break;
+    case 3: decode_fmt16_records_kernel<3><<<grid, 256, 0, st>>>(P); break;
+    case 4: decode_fmt16_records_kernel<4><<<grid, 256, 0, st>>>(P); break;
+    default: decode_fmt16_records_kernel<5><<<grid, 256, 0, st>>>(P); break;
   }
   CUDA_TRY(ctx, cudaGetLastError());
   return SCGRHC_OK;

@@ -234,6 +234,65 @@ __global__ void __launch_bounds__(256) decode_fmt16_rows_kernel(const __grid_con
   }
 }
 
+// The same for a CHUNK of records with per-record calibration (every WFDB header carries its own gain/baseline): one
+// launch per chunk instead of one per record.  blockIdx.y = record of the chunk; rec_row0[r] .. rec_row0[r+1] = its
+// frames inside d / out; gain / baseline are (n_rec, NC) device tables.  `recip` != 0: the host has checked that every
+// gain of the table satisfies the conditions of the reciprocal path above; else IEEE division.
+struct DecodeRecParams {
+  const short* d;            // (T_chunk, nsig_in) interleaved frames, records back to back
+  double* out;               // (T_chunk, ncols)
+  const long long* rec_row0; // device (n_rec + 1)
+  const double* gain;        // device (n_rec, ncols)
+  const double* baseline;    // device (n_rec, ncols)
+  int n_rec, nsig_in, ncols, recip;
+  int cols[SCGRHC_MAX_C + 1];
+};
+template <int NC>
+__global__ void __launch_bounds__(256) decode_fmt16_records_kernel(const __grid_constant__ DecodeRecParams P) {
+  const int r = blockIdx.y;
+  const long long t0 = P.rec_row0[r], t1 = P.rec_row0[r + 1];
+  double g[NC], b[NC], inv[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    g[j] = P.gain[(size_t)r * NC + j];
+    b[j] = P.baseline[(size_t)r * NC + j];
+    inv[j] = __drcp_rn(g[j]);
+  }
+  const bool frame4 = P.nsig_in == 4 && (reinterpret_cast<uintptr_t>(P.d) & 7) == 0;
+  const bool out16 = (reinterpret_cast<uintptr_t>(P.out) & 15) == 0;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  for (long long t = t0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < t1; t += (long long)gridDim.x * blockDim.x) {
+    short dv[NC];
+    if (frame4) {
+      const short4 f = __ldcs(reinterpret_cast<const short4*>(P.d) + t);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int c = P.cols[j];
+        dv[j] = c == 0 ? f.x : (c == 1 ? f.y : (c == 2 ? f.z : f.w));
+      }
+    } else {
+      const short* row = P.d + t * P.nsig_in;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) dv[j] = row[P.cols[j]];
+    }
+    double v[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const double a = __dsub_rn((double)dv[j], b[j]);
+      const double q = P.recip ? div_by_recip(a, g[j], inv[j]) : __ddiv_rn(a, g[j]);
+      v[j] = dv[j] == -32768 ? qnan : q;
+    }
+    double* o = P.out + t * NC;
+    if (NC % 2 == 0 && out16) {
+#pragma unroll
+      for (int j = 0; j + 1 < NC; j += 2) __stcs(reinterpret_cast<double2*>(o + j), make_double2(v[j], v[j + 1]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) __stcs(o + j, v[j]);
+    }
+  }
+}
+
 // ---- extension (north star, absent from the reference): train-time noise injection fused into the batch gather.
 // Counter-based Philox4x32-10 (Salmon et al., Random123; the cuRAND-style 4x32 variant, NOT numpy's 4x64):
 // key = seed, counter = (block index of the element quad, stream offset).  Element j of the batch takes word j&3

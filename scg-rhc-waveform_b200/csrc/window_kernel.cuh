@@ -50,7 +50,7 @@ struct StageMeta {
 struct KParams {
   scgrhc_job job;
   scgrhc_outputs out;
-  unsigned long long* err;  // [0] error flags, [1] first offending candidate (atomicMin)
+  unsigned long long* err;  // [0] error flags, [1] first offending candidate (atomicMin), [2] windows flagged AMBIGUOUS
   int stages;
   int stage_elems;          // doubles per stage buffer (even, >= W*nsig + nsig + 2)
   long long arena_elems_cap;
@@ -97,6 +97,33 @@ struct Normaliser {
 
 __device__ __forceinline__ void cvt_out(float& o, double q) { o = __double2float_rn(q); }
 __device__ __forceinline__ void cvt_out(double& o, double q) { o = q; }
+
+// np.add.reduce over n copies of v in numpy's pairwise order (numpy/_core/src/umath/loops_utils.h.src, *_pairwise_sum:
+// < 8 elements serial from 0; <= 128 eight strided accumulators combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) then the
+// tail; else split at n/2 rounded down to a multiple of 8).  For a constant vector the eight accumulators are equal.
+// Used for exactly constant RHC windows only: sklearn's R^2 of a constant y is rounding noise, 1.0 iff np.mean(y) is
+// exact (oracle/scgrhc_oracle.py: r_squared).  D bounds the recursion statically: n <= 128 * 2^D.
+template <int D>
+__device__ __forceinline__ double np_sum_const(double v, int n) {
+  if (n < 8) {
+    double r = 0.0;
+    for (int i = 0; i < n; ++i) r = __dadd_rn(r, v);
+    return r;
+  }
+  if (n <= 128 || D == 0) {
+    double r = v;
+    for (int i = 8; i < n - (n % 8); i += 8) r = __dadd_rn(r, v);
+    r = __dadd_rn(r, r); r = __dadd_rn(r, r); r = __dadd_rn(r, r);
+    for (int i = n - (n % 8); i < n; ++i) r = __dadd_rn(r, v);
+    return r;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return __dadd_rn(np_sum_const<(D > 0 ? D - 1 : 0)>(v, n2), np_sum_const<(D > 0 ? D - 1 : 0)>(v, n - n2));
+}
+__device__ __noinline__ bool np_mean_of_const_is_exact(double v, int n) {
+  return __ddiv_rn(np_sum_const<3>(v, n), (double)n) == v;      // W <= RMAX * NT = 1024 = 128 * 2^3
+}
 
 __device__ __forceinline__ double sel4(int col, double v0, double v1, double v2, double v3) {
   double lo = (col & 1) ? v1 : v0;
@@ -472,6 +499,9 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
       if (flat_cnt >= 2) reason |= SCGRHC_REASON_FLAT;
       if (syy > 0.0 && lhs > __dmul_rn(0.8, den)) reason |= SCGRHC_REASON_STRAIGHT;
       if (syy > 0.0 && fabs(__fma_rn(-0.8, den, lhs)) < __dmul_rn(1e-9, den)) reason |= SCGRHC_REASON_AMBIGUOUS;
+      // exactly constant window (CTA-uniform, rare): the reference's R^2 is rounding noise — is_straight_line() is True
+      // iff np.mean(y) == y[0] exactly.  Only decides windows shorter than 51 samples (longer ones are flat lines).
+      if (ymin == ymax && !nonfinite && np_mean_of_const_is_exact(ymin, W)) reason |= SCGRHC_REASON_STRAIGHT;
       if (ymin < min_rhc) reason |= SCGRHC_REASON_FLOOR;  // some sample < floor <=> the minimum is
       if (nonfinite) reason |= SCGRHC_REASON_NONFINITE;
       keep = keep_all ||
@@ -489,6 +519,7 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
           atomicOr(P.err, 1ull);
           atomicMin(P.err + 1, (unsigned long long)M.cand);
         }
+        if (reason & SCGRHC_REASON_AMBIGUOUS) atomicAdd(P.err + 2, 1ull);   // surfaced by scgrhc_ambiguous_count
       }
       if (zscore && keep && !pred_only) {
         // extension: joint mean / population std of the SCG block (as the reference takes its min/max jointly) and of

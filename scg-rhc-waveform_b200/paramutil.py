@@ -62,6 +62,7 @@ class Params:
     self.bandpass_mode = self.data.get('bandpass_mode')    # 'exact' (default, bit-identical to scipy) | 'scan' (time-parallel)
     self.resample_rate = self.data.get('resample_rate')    # model sampling rate in Hz (native: 500)
     self.resample_mode = self.data.get('resample_mode')    # 'exact' (default, bit-identical to scipy) | 'fused' (one FMA per tap)
+    self.train_layout = self.data.get('train_layout')      # multi-GPU jobs: 'gathered' (rank 0 holds the train loader) | 'sharded'
     self.normalisation = self.data.get('normalisation')    # 'minmax' (default = the reference) | 'zscore' (per-window mean/std)
 
   def _get(self, key):

@@ -374,7 +374,7 @@ def train_valid_test_split(n, seed=None):
     m = len(idx)
     n_train = int(np.floor(frac * m))
     n_test = m - n_train
-    if m and n_train == 0:
+    if n_train == 0:                  # sklearn raises for an empty cohort too: the reference then writes no loaders
       raise ValueError('With n_samples=%d, test_size=None and train_size=%s, the resulting train set will be empty. '
                        'Adjust any of the aforementioned parameters.' % (m, frac))
     perm = rng.permutation(m)
@@ -385,50 +385,18 @@ def train_valid_test_split(n, seed=None):
   return train, valid, test
 
 
-def prepare_cohort(params, record_names=None, chunk_records=None):
-  """Records -> HBM -> fused window kernel.  Returns (WindowStore, record_names): every kept window of the
-  cohort, device resident, in the reference's order (records in ``record_names`` order).
-
-  Ingest: when the reader exposes the digital frames (``d_signal``/``adc_gain``/``baseline``, as scgrhc.wfdbio
-  does for format-16 records) the selected columns travel to the GPU as int16 and are converted there
-  ((d - baseline) / gain in fp64, what wfdb.rdrecord does on the host at recordutil.py:137); otherwise the fp64
-  ``p_signal`` columns are uploaded.  Only the C SCG columns + RHC are uploaded, so the arena always has the
-  identity column layout."""
-  names = list(record_names) if record_names is not None else get_record_names()
+def _stage_spec(params, C, rows, metas, names, rec0):
+  """Optional per-record stages (band-pass, resample; absent from the reference, default off) as HostIngest's ``stages``
+  dict, plus the plan of the cohort AFTER them."""
   W = int(params.segment_size * SAMPLE_FREQ)
-  C = len(params.in_channels)
-  blocks, metas, rows, gains, bases = [], [], [], [], []
-  digital = True
-  for name in names:
-    record = wfdb.rdrecord(os.path.join(PROCESSED_DATA_PATH, name))
-    cols, rcol = engine.resolve_columns(record.sig_name, params.in_channels)
-    sel = cols + [rcol]
-    digital = digital and getattr(record, 'd_signal', None) is not None and getattr(record, 'adc_gain', None) is not None \
-        and getattr(record, 'baseline', None) is not None and record.d_signal.dtype == np.int16
-    blocks.append((record, sel))
-    metas.append(_read_meta(name))
-    rows.append(record.d_signal.shape[0] if digital else record.p_signal.shape[0])
   stride_s = getattr(params, 'segment_stride', None)
-  plan = engine.plan_cohort(metas, params.chamber, rows, W, names, stride=int(stride_s * SAMPLE_FREQ) if stride_s else 0)
-  dev = _device()
-  total = int(sum(rows))
-  host = torch.empty((total, C + 1), dtype=torch.int16 if digital else torch.float64, pin_memory=True)
-  at = 0
-  for (record, sel), n in zip(blocks, rows):
-    if digital:
-      host[at:at + n] = torch.from_numpy(np.ascontiguousarray(record.d_signal[:, sel]))
-      gains.append([float(record.adc_gain[j]) for j in sel])
-      bases.append([float(record.baseline[j]) for j in sel])
-    else:
-      host[at:at + n] = torch.from_numpy(np.ascontiguousarray(record.p_signal[:, sel], dtype=np.float64))
-    at += n
+  plan = engine.plan_cohort(metas, params.chamber, rows, W, names, stride=int(stride_s * SAMPLE_FREQ) if stride_s else 0, rec0=rec0)
   sos = _bandpass_sos(params)
   rate = getattr(params, 'resample_rate', None)
-  extensions = sos is not None or (rate and int(rate) != SAMPLE_FREQ)
   stages = None
-  if extensions:
-    # the optional stages (absent from the reference) run per chunk inside the same streamed ingest: copy of chunk k+1
-    # overlaps decode / band-pass / resample / window kernel of chunk k, and the cohort never has to be resident
+  if sos is not None or (rate and int(rate) != SAMPLE_FREQ):
+    # they run per chunk inside the same streamed ingest: copy of chunk k+1 overlaps decode / band-pass / resample /
+    # window kernel of chunk k, and the cohort never has to be resident
     stages = {}
     if sos is not None:                    # zero-phase band-pass of the SCG channels (scipy sosfiltfilt semantics)
       stages.update(sos=sos, filter_cols=list(range(C)), filter_exact=getattr(params, 'bandpass_mode', None) != 'scan')
@@ -441,15 +409,80 @@ def prepare_cohort(params, record_names=None, chunk_records=None):
                     resample_exact=getattr(params, 'resample_mode', None) != 'fused')
       W = int(params.segment_size * int(rate))
       plan = engine.plan_cohort(metas, params.chamber, out_rows, W, names, stride=int(stride_s * int(rate)) if stride_s else 0,
-                                fs=float(int(rate)))
+                                fs=float(int(rate)), rec0=rec0)
+  return plan, stages
+
+
+def prepare_cohort(params, record_names=None, chunk_records=None, group=None):
+  """Records -> HBM -> fused window kernel.  Returns (WindowStore, record_names): every kept window of this rank's
+  records, device resident, in the reference's order (records in ``record_names`` order).
+
+  Multi-GPU (one process per GPU under torchrun): the per-record loop of get_segments
+  (recordutil.py:131-132) shards by contiguous blocks of ``record_names`` (``engine.shard_records``); every rank runs
+  the same pipeline on its block, ``use_global_min_max`` (recordutil.py:152-169,185-189) goes through ONE MIN all-reduce
+  of {min, -max}, and one all-gather of the kept counts gives ``store.shard`` (this rank's offset in the cohort-wide
+  ordered list), so the concatenation of the ranks' stores in rank order IS the single-GPU store.  ``rec_id`` indexes
+  the full ``record_names`` list on every rank.
+
+  Ingest: format-16 records (scgrhc.wfdbio) are STREAMED — headers only are parsed up front, a reader pool fills a ring
+  of pinned chunk buffers straight from the ``.dat`` files (``engine.DiskSource``), the int16 frames cross PCIe as
+  they are (4x fewer bytes than fp64) and ``(d - baseline) / gain`` runs on the device with the per-record calibration
+  in a device table (what wfdb.rdrecord does on the host at recordutil.py:137); host memory holds a few chunks whatever
+  the cohort size.  Other readers (the real ``wfdb`` package, other formats) take the resident path: ``p_signal`` of
+  every record of the shard in one pinned buffer."""
+  from scgrhc import dist as sdist
+  names_all = list(record_names) if record_names is not None else get_record_names()
+  rank, world = sdist.current(group)
+  lo, hi = engine.shard_records(len(names_all), rank, world)
+  names = names_all[lo:hi]
+  C = len(params.in_channels)
+  dev = _device()
+  metas = [_read_meta(name) for name in names]
+  plan = stages = source = decode = host = None
+  rows = []
+  if hasattr(wfdb, 'read_header'):
+    try:
+      heads = [wfdb.read_header(os.path.join(PROCESSED_DATA_PATH, name)) for name in names]
+      sels = [engine.resolve_columns(h[0], params.in_channels) for h in heads]
+      if heads and all(len(h[0]) == len(heads[0][0]) and s == sels[0] for h, s in zip(heads, sels)):
+        rows = [h[2] for h in heads]
+        sel = sels[0][0] + [sels[0][1]]
+        source = engine.DiskSource([h[5] for h in heads], rows, len(heads[0][0]))
+        decode = (sel, [[float(h[3][j]) for j in sel] for h in heads], [[float(h[4][j]) for j in sel] for h in heads])
+    except NotImplementedError:
+      source = None
+  if source is None:
+    blocks, digital = [], True
+    for name in names:
+      record = wfdb.rdrecord(os.path.join(PROCESSED_DATA_PATH, name))
+      cols, rcol = engine.resolve_columns(record.sig_name, params.in_channels)
+      digital = digital and getattr(record, 'd_signal', None) is not None and getattr(record, 'adc_gain', None) is not None \
+          and getattr(record, 'baseline', None) is not None and record.d_signal.dtype == np.int16
+      blocks.append((record, cols + [rcol]))
+      rows.append(record.d_signal.shape[0] if digital else record.p_signal.shape[0])
+    host = torch.empty((int(sum(rows)), C + 1), dtype=torch.int16 if digital else torch.float64, pin_memory=True)
+    at, gains, bases = 0, [], []
+    for (record, sel), n in zip(blocks, rows):
+      if digital:
+        host[at:at + n] = torch.from_numpy(np.ascontiguousarray(record.d_signal[:, sel]))
+        gains.append([float(record.adc_gain[j]) for j in sel])
+        bases.append([float(record.baseline[j]) for j in sel])
+      else:
+        host[at:at + n] = torch.from_numpy(np.ascontiguousarray(record.p_signal[:, sel], dtype=np.float64))
+      at += n
+    source, digital_nsig = host, (C + 1) if digital else None
+    decode = (list(range(C + 1)), gains, bases) if digital else None
+  else:
+    digital_nsig = source.nsig
+  plan, stages = _stage_spec(params, C, rows, metas, names_all, lo)
   if chunk_records is None:
     # the time-parallel band-pass runs one CTA per record (8 per SM): a chunk of a few hundred records costs what 32 do
     chunk_records = 256 if (stages and stages.get('sos') is not None) else 32
-  ing = engine.HostIngest(plan, rows, C + 1, dev, chunk_records=chunk_records, digital_nsig=(C + 1) if digital else None,
-                          stages=stages)
-  store = ing.run(host, list(range(C)), C, params.min_RHC, decode=(list(range(C + 1)), gains, bases) if digital else None,
-                  use_global_min_max=bool(params.use_global_min_max), normalisation=getattr(params, 'normalisation', None))
-  return store, names
+  ing = engine.HostIngest(plan, rows, C + 1, dev, chunk_records=chunk_records, digital_nsig=digital_nsig, stages=stages)
+  store = ing.run(source, list(range(C)), C, params.min_RHC, decode=decode, use_global_min_max=bool(params.use_global_min_max),
+                  group=group, normalisation=getattr(params, 'normalisation', None))
+  store.shard = sdist.exchange_counts(store.n_kept, dev, group)
+  return store, names_all
 
 
 def _bandpass_sos(params):
@@ -466,9 +499,12 @@ def _bandpass_sos(params):
 
 def save_dataloaders(params):
   """
-  Get training and test segments, then save as loader objects (recordutil.py:172-216).
+  Get training and test segments, then save as loader objects (recordutil.py:172-216).  Under torchrun every rank
+  prepares its block of records and rank 0 writes the reference's three pickles (see ``_write_loaders``).
   """
+  from scgrhc import dist as sdist
   _check_no_loaders(params)
+  sdist.barrier()                        # every rank has looked before any rank writes
   store, names = prepare_cohort(params)
   _write_loaders(params, store, names)
 
@@ -483,55 +519,146 @@ def _check_no_loaders(params):
     raise Exception('Test file already exists!')
 
 
-def _write_loaders(params, store, names):
-  """Split 90/5/5, build the three loaders, pickle them and write record_log.txt (recordutil.py:191-216)."""
-  n_all = store.n_kept
-  train_idx, valid_idx, test_idx = train_valid_test_split(n_all, getattr(params, 'split_seed', None))
+class ShardedTrainLoader:
+  """What ``train_path`` holds when the train windows of a multi-GPU job stay on their ranks (``train_layout: "sharded"``,
+  or automatically when they exceed ``SCGRHC_GATHER_LIMIT_GB``): rank r's ``WindowLoader`` is pickled next to it as
+  ``<train_path>.rank<r>-of-<N>``.  ``load_dataloader(train_path)`` resolves it: under torchrun with the same world size
+  every rank gets its own shard (data-parallel training); a single process gets all shards concatenated."""
+
+  def __init__(self, world, counts, batch_size):
+    self.world, self.counts, self.batch_size = int(world), list(counts), int(batch_size)
+
+  @staticmethod
+  def shard_path(train_path, rank, world):
+    return '%s.rank%d-of-%d' % (train_path, rank, world)
+
+  def resolve(self, train_path):
+    from scgrhc import dist as sdist
+    rank, world = sdist.current()
+    if world == self.world and world > 1:
+      with open(self.shard_path(train_path, rank, world), 'rb') as f:
+        return pickle.load(f)
+    parts = []
+    for r in range(self.world):
+      with open(self.shard_path(train_path, r, self.world), 'rb') as f:
+        parts.append(pickle.load(f))
+    ds = [p.dataset for p in parts]
+    dev = ds[0].scg.device
+    merged = SCGDataset.from_arrays(torch.cat([d.scg.to(dev) for d in ds]), torch.cat([d.rhc.to(dev) for d in ds]),
+                                    sum((d._names for d in ds), []), np.concatenate([d._start for d in ds]),
+                                    np.concatenate([d._stop for d in ds]), np.concatenate([d._mm for d in ds]), 1.0)
+    merged.segment_size = ds[0].segment_size
+    first = parts[0]
+    return WindowLoader(merged, batch_size=first.batch_size, shuffle=first.shuffle, noise_std=first.noise_std,
+                        noise_seed=first.noise_seed)
+
+
+def _write_loaders(params, store, names, shard=None):
+  """Split 90/5/5, build the three loaders, pickle them and write record_log.txt (recordutil.py:191-216).
+
+  Multi-GPU: ``store`` holds this rank's kept windows, ``shard`` (default ``store.shard``) its place in the cohort-wide
+  ordered list.  The split is ONE draw over the global list (the same on every rank); each rank gathers its members of
+  the three subsets on its own GPU; valid / test windows (5 % each) travel to rank 0, which writes the reference's
+  pickles — identical to a single-GPU run with the same ``split_seed``.  Train windows are gathered to rank 0 as well
+  (``train_layout: "gathered"``, the drop-in default: the reference's trainer is one process) unless they exceed
+  ``SCGRHC_GATHER_LIMIT_GB`` (default 16) or ``train_layout: "sharded"`` asks for per-rank loaders (``ShardedTrainLoader``)."""
+  from scgrhc import dist as sdist
+  sh = shard if shard is not None else getattr(store, 'shard', None)
+  if sh is None:
+    sh = sdist.Shard(0, 1, None, 0, store.n_kept, (store.n_kept,))
+  dev = store.kept_idx.device
+  n_all = sh.total
+  n_amb = store.n_ambiguous
+  if n_amb:
+    import warnings
+    warnings.warn('%d candidate window(s) have an R^2 within 1e-9 of the 0.8 straight-line threshold (waveform_noise.py:34); '
+                  'they were decided by the closed-form R^2, which sklearn\'s lstsq-based score could round the other way'
+                  % n_amb)
+  seed = getattr(params, 'split_seed', None)
+  if sh.active and seed is None:        # unseeded like the reference, but one draw for the whole job: rank 0's
+    seed = int(sdist.broadcast_index(torch.tensor([np.random.randint(0, 2 ** 31 - 1)]), dev, sh.group)[0])
+  train_idx, valid_idx, test_idx = train_valid_test_split(n_all, seed)
 
   rec_id = store.rec_id.cpu().numpy()
   start, stop = store.start_idx.cpu().numpy(), store.stop_idx.cpu().numpy()
   mm = store.kept_minmax().cpu().numpy()
+  C, W = (store.scg.shape[1], store.scg.shape[2]) if store.scg is not None else (len(params.in_channels), int(params.segment_size * SAMPLE_FREQ))
+  bounds = np.concatenate([[0], np.cumsum(sh.counts)])
 
-  def make(idx, device):
-    pos = torch.as_tensor(idx, dtype=torch.int64, device=store.kept_idx.device)
-    scg, rhc = store.gather(pos)
-    return SCGDataset.from_arrays(scg.to(device), rhc.to(device), [names[r] for r in rec_id[idx]], start[idx], stop[idx],
-                                  mm[idx], params.segment_size)
+  def make(idx, device, gather=True):
+    """SCGDataset over the global list positions ``idx`` (in that order).  Single GPU: a device gather.  Multi-GPU: every
+    rank gathers its members; with ``gather`` they are sent to rank 0 (None elsewhere), else each rank keeps its own."""
+    owner = np.searchsorted(bounds, idx, side='right') - 1            # rank holding each member
+    mine = owner == sh.rank
+    local = (idx[mine] - sh.offset).astype(np.int64)
+    pos = torch.as_tensor(local, dtype=torch.int64, device=dev)
+    scg, rhc = store.gather(pos) if store.scg is not None else (torch.empty((0, C, W), device=dev), torch.empty((0, 1, W), device=dev))
+    meta = np.concatenate([rec_id[local, None].astype(np.float64), start[local, None].astype(np.float64),
+                           stop[local, None].astype(np.float64), mm[local].reshape(-1, 4)], axis=1)
+    if sh.active and gather:
+      counts = [int((owner == r).sum()) for r in range(sh.world)]
+      scg = sdist.gather_rows(scg, counts, sh.group)
+      rhc = sdist.gather_rows(rhc, counts, sh.group)
+      meta_t = sdist.gather_rows(torch.from_numpy(meta).to(dev), counts, sh.group)
+      if sh.rank != 0:
+        return None
+      # rows arrived rank by rank; put them back in the order of ``idx``
+      back = torch.as_tensor(np.argsort(np.argsort(owner, kind='stable'), kind='stable'), dtype=torch.int64, device=dev)
+      scg, rhc, meta = scg[back], rhc[back], meta_t[back].cpu().numpy()
+    return SCGDataset.from_arrays(scg.to(device), rhc.to(device), [names[int(r)] for r in meta[:, 0]], meta[:, 1].astype(np.int64),
+                                  meta[:, 2].astype(np.int64), meta[:, 3:7], params.segment_size)
 
-  train_set = make(train_idx, store.kept_idx.device)     # stays in HBM for waveform_train
+  layout = getattr(params, 'train_layout', None)
+  if sh.active and layout is None:
+    limit = float(os.environ.get('SCGRHC_GATHER_LIMIT_GB', '16')) * 1e9
+    layout = 'sharded' if len(train_idx) * (C + 1) * W * 4 > limit else 'gathered'
+  sharded = sh.active and layout == 'sharded'
+
+  noise = dict(noise_std=getattr(params, 'noise_std', None) or 0.0, noise_seed=getattr(params, 'noise_seed', None) or 0)
+  train_set = make(train_idx, dev, gather=not sharded)   # stays in HBM for waveform_train
   valid_set = make(valid_idx, 'cpu')                     # waveform_test calls .numpy() on items
   test_set = make(test_idx, 'cpu')
 
-  train_loader = WindowLoader(train_set, batch_size=params.batch_size, shuffle=True,
-                              noise_std=getattr(params, 'noise_std', None) or 0.0, noise_seed=getattr(params, 'noise_seed', None) or 0)
-  valid_loader = WindowLoader(valid_set, batch_size=1, shuffle=True)
-  test_loader = WindowLoader(test_set, batch_size=1, shuffle=True)
+  if sharded:
+    with open(ShardedTrainLoader.shard_path(params.train_path, sh.rank, sh.world), 'wb') as f:
+      pickle.dump(WindowLoader(train_set, batch_size=params.batch_size, shuffle=True, **noise), f)
+  if sh.rank == 0:
+    if sharded:
+      owner = np.searchsorted(bounds, train_idx, side='right') - 1
+      train_loader = ShardedTrainLoader(sh.world, [int((owner == r).sum()) for r in range(sh.world)], params.batch_size)
+    else:
+      train_loader = WindowLoader(train_set, batch_size=params.batch_size, shuffle=True, **noise)
+    valid_loader = WindowLoader(valid_set, batch_size=1, shuffle=True)
+    test_loader = WindowLoader(test_set, batch_size=1, shuffle=True)
 
-  with open(params.train_path, 'wb') as f:
-    pickle.dump(train_loader, f)
+    with open(params.train_path, 'wb') as f:
+      pickle.dump(train_loader, f)
 
-  with open(params.valid_path, 'wb') as f:
-    pickle.dump(valid_loader, f)
+    with open(params.valid_path, 'wb') as f:
+      pickle.dump(valid_loader, f)
 
-  with open(params.test_path, 'wb') as f:
-    pickle.dump(test_loader, f)
+    with open(params.test_path, 'wb') as f:
+      pickle.dump(test_loader, f)
 
-  with open(os.path.join(params.dir_path, 'record_log.txt'), 'w') as f:
-    f.write(f'Dataset created: {datetime.now()}\n')
-    f.write(f'All segments: {n_all}\n')
-    f.write(f'Valid segments: {len(valid_idx)}\n')
-    f.write(f'Train segments: {len(train_idx)}\n')
-    f.write(f'Test segments: {len(test_idx)}\n')
+    with open(os.path.join(params.dir_path, 'record_log.txt'), 'w') as f:
+      f.write(f'Dataset created: {datetime.now()}\n')
+      f.write(f'All segments: {n_all}\n')
+      f.write(f'Valid segments: {len(valid_idx)}\n')
+      f.write(f'Train segments: {len(train_idx)}\n')
+      f.write(f'Test segments: {len(test_idx)}\n')
+  sdist.barrier(sh.group)                # the files exist when any rank returns
 
 
-def save_dataloaders_sweep(params_list, record_names=None):
+def save_dataloaders_sweep(params_list, record_names=None, group=None):
   """Extension (BASELINE configs[4]; the reference runs its `all` sweep as independent jobs, waveform_pipeline.py:33-37):
   data preparation for SEVERAL experiment configs over one cohort.  Every record is read and uploaded once (the union
   of the configs' channels + RHC); configs that differ only in their channel subset share one predicate pass and one
   fan-out pass (scgrhc.sweep.iter_sweep); each config then gets its three pickled loaders and record_log.txt exactly as
   save_dataloaders writes them.  Configs whose loaders already exist are reported and skipped, like the reference's
   guard; configs with optional-stage keys (band-pass, resample, stride, z-score) take the single-config path.
-  Returns {dir_path: n_kept}."""
+  Under torchrun the records shard across the ranks exactly as for one config (``prepare_cohort``); every config's
+  loaders are assembled on rank 0.  Returns {dir_path: n_kept}."""
+  from scgrhc import dist as sdist
   from scgrhc import sweep
   todo, single, out = [], [], {}
   for params in params_list:
@@ -543,19 +670,22 @@ def save_dataloaders_sweep(params_list, record_names=None):
     ext = any(getattr(params, k, None) for k in ('bandpass', 'bandpass_sos', 'resample_rate', 'segment_stride')) or \
         getattr(params, 'normalisation', None) not in (None, 'minmax')
     (single if ext else todo).append(params)
+  sdist.barrier(group)                   # every rank has looked before any rank writes
   for params in single:
     save_dataloaders(params)
     out[params.dir_path] = None
   if not todo:
     return out
-  names = list(record_names) if record_names is not None else get_record_names()
+  names_all = list(record_names) if record_names is not None else get_record_names()
+  rank, world = sdist.current(group)
+  lo, hi = engine.shard_records(len(names_all), rank, world)
   wanted = []
   for params in todo:
     for ch in params.in_channels:
       if ch not in wanted:
         wanted.append(ch)
   records, metas, rows, sig = [], [], [], None
-  for name in names:
+  for name in names_all[lo:hi]:
     record = wfdb.rdrecord(os.path.join(PROCESSED_DATA_PATH, name))
     order = sorted(wanted, key=record.sig_name.index)          # ValueError for a missing channel, as list.index does
     cols, rcol = engine.resolve_columns(record.sig_name, order)
@@ -567,6 +697,8 @@ def save_dataloaders_sweep(params_list, record_names=None):
     records.append(np.ascontiguousarray(record.p_signal[:, cols + [rcol]], dtype=np.float64))
     metas.append(_read_meta(name))
     rows.append(records[-1].shape[0])
+  if sig is None:                        # a rank without records still takes part in every collective
+    sig = list(wanted) + [engine.RHC_NAME]
   dev = _device()
   host = torch.empty((int(sum(rows)), len(sig)), dtype=torch.float64, pin_memory=True)
   at = 0
@@ -575,10 +707,11 @@ def save_dataloaders_sweep(params_list, record_names=None):
     at += len(block)
   arena = host.to(dev, non_blocking=True)
   configs = {str(i): p for i, p in enumerate(todo)}
-  for key, store in sweep.iter_sweep(arena, sig, metas, rows, configs, buffers={}):
+  for key, store in sweep.iter_sweep(arena, sig, metas, rows, configs, buffers={}, group=group, rec0=lo):
     params = configs[key]
-    _write_loaders(params, store, names)
-    out[params.dir_path] = store.n_kept
+    shard = sdist.exchange_counts(store.n_kept, dev, group)
+    _write_loaders(params, store, names_all, shard)
+    out[params.dir_path] = shard.total
   return out
 
 
@@ -587,7 +720,10 @@ def load_dataloader(path):
   Load prior loader object (recordutil.py:219-224).
   """
   with open(path, 'rb') as f:
-    return pickle.load(f)
+    loader = pickle.load(f)
+  if isinstance(loader, ShardedTrainLoader):      # a multi-GPU job left the train windows on their ranks
+    loader = loader.resolve(path)
+  return loader
 
 
 def run(params):
@@ -596,7 +732,19 @@ def run(params):
   save_dataloaders(params)
 
 
+def prepare_all(dir_names):
+  """Extension (BASELINE configs[4]): data preparation only, for several experiment directories in one job —
+  ``python recordutil.py prepare waveform_06 waveform_07 ...``.  The cohort is read and uploaded once; configs that
+  differ only in their channel subset share one predicate pass and one fan-out pass (save_dataloaders_sweep).  The
+  reference's own ``waveform_pipeline.py`` (used as is) then finds the loaders in place and goes
+  straight to training (its "already exists" branch, waveform_pipeline.py:12-15)."""
+  return save_dataloaders_sweep([Params(os.path.join(d, 'params.json')) for d in dir_names])
+
+
 if __name__ == '__main__':
-  dir_path = sys.argv[1]
-  params = Params(os.path.join(dir_path, 'params.json'))
-  run(params)
+  if sys.argv[1] == 'prepare':
+    prepare_all(sys.argv[2:])
+  else:
+    dir_path = sys.argv[1]
+    params = Params(os.path.join(dir_path, 'params.json'))
+    run(params)

@@ -55,8 +55,8 @@ _lib = None
 # every symbol include/scgrhc.h declares (tests check the library exports all of them)
 SYMBOLS = ['scgrhc_abi_version', 'scgrhc_ctx_create', 'scgrhc_ctx_destroy', 'scgrhc_last_error',
            'scgrhc_ctx_set_tuning', 'scgrhc_ctx_sm_count', 'scgrhc_plan_record', 'scgrhc_plan_cohort', 'scgrhc_process_windows',
-           'scgrhc_compact_kept', 'scgrhc_normalize_subsets', 'scgrhc_global_minmax', 'scgrhc_check_errors', 'scgrhc_gather_windows',
-           'scgrhc_window_metrics', 'scgrhc_sosfiltfilt', 'scgrhc_sosfiltfilt_scan', 'scgrhc_resample_poly', 'scgrhc_gather_windows_noise', 'scgrhc_philox_words', 'scgrhc_rolling_range_lt', 'scgrhc_decode_fmt16', 'scgrhc_waveform_stats', 'scgrhc_synth_records', 'scgrhc_selftest_div']
+           'scgrhc_compact_kept', 'scgrhc_normalize_subsets', 'scgrhc_global_minmax', 'scgrhc_check_errors', 'scgrhc_ambiguous_count', 'scgrhc_gather_windows',
+           'scgrhc_window_metrics', 'scgrhc_sosfiltfilt', 'scgrhc_sosfiltfilt_scan', 'scgrhc_resample_poly', 'scgrhc_gather_windows_noise', 'scgrhc_philox_words', 'scgrhc_rolling_range_lt', 'scgrhc_decode_fmt16', 'scgrhc_decode_fmt16_records', 'scgrhc_waveform_stats', 'scgrhc_synth_records', 'scgrhc_selftest_div']
 
 
 def lib():
@@ -88,6 +88,8 @@ def lib():
   L.scgrhc_compact_kept.argtypes = [vp, vp, vp, vp, i64, i32, C.POINTER(Compact), vp]
   L.scgrhc_global_minmax.argtypes = [vp, vp, vp, i64, vp, vp]
   L.scgrhc_check_errors.argtypes = [vp, vp, C.POINTER(i64)]
+  L.scgrhc_ambiguous_count.argtypes = [vp]
+  L.scgrhc_ambiguous_count.restype = i64
   L.scgrhc_gather_windows.argtypes = [vp, vp, vp, i64, i64, vp, vp]
   L.scgrhc_gather_windows_noise.argtypes = [vp, vp, vp, i64, i64, vp, C.c_float, u64, u64, vp]
   L.scgrhc_philox_words.argtypes = [vp, u64, u64, i64, vp, vp]
@@ -98,6 +100,7 @@ def lib():
   L.scgrhc_resample_poly.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, vp]
   L.scgrhc_rolling_range_lt.argtypes = [vp, vp, i64, i32, dbl, vp, vp]
   L.scgrhc_decode_fmt16.argtypes = [vp, vp, i64, i32, C.POINTER(i32), i32, C.POINTER(dbl), C.POINTER(dbl), vp, vp]
+  L.scgrhc_decode_fmt16_records.argtypes = [vp, vp, vp, i32, i64, i32, C.POINTER(i32), i32, vp, vp, i32, vp, vp]
   L.scgrhc_waveform_stats.argtypes = [vp, vp, i64, i64, dbl, vp, vp]
   L.scgrhc_synth_records.argtypes = [vp, u64, i64, i64, i64, i32, C.POINTER(i32), i32, i32, vp, vp]
   L.scgrhc_selftest_div.argtypes = [vp, u64, i64, i32, vp, vp]

@@ -106,9 +106,10 @@ class Plan:
     return self._dev
 
 
-def plan_cohort(metas, chamber, T_rows, W, record_names=None, stride=0, fs=0.0):
+def plan_cohort(metas, chamber, T_rows, W, record_names=None, stride=0, fs=0.0, rec0=0):
   """Plan for records stored back to back in the arena; ``T_rows[r]`` rows each.  One C call for the whole cohort
-  (`scgrhc_plan_cohort`)."""
+  (`scgrhc_plan_cohort`).  ``rec0``: record number of the first record (a rank's shard of a larger cohort reports global
+  record ids)."""
   times, match, off = [], [], [0]
   for meta in metas:
     tab = event_table(meta, chamber)
@@ -130,7 +131,7 @@ def plan_cohort(metas, chamber, T_rows, W, record_names=None, stride=0, fs=0.0):
   n_out, n_cand = C.c_int64(0), C.c_int64(0)
   rc = N.lib().scgrhc_plan_cohort(t.ctypes.data_as(C.POINTER(C.c_double)), m.ctypes.data_as(C.POINTER(C.c_uint8)),
                                   o.ctypes.data_as(C.POINTER(C.c_int64)), rows.ctypes.data_as(C.POINTER(C.c_int64)), n_rec,
-                                  int(W), int(stride), float(fs), 0, out.ctypes.data_as(C.POINTER(N.Interval)), cap,
+                                  int(W), int(stride), float(fs), int(rec0), out.ctypes.data_as(C.POINTER(N.Interval)), cap,
                                   C.byref(n_out), C.byref(n_cand))
   if rc != N.OK:
     raise N.ScgrhcError(rc, 'scgrhc_plan_cohort failed')
@@ -168,6 +169,9 @@ class WindowStore:
   dense: bool
   global_minmax: Optional[torch.Tensor] = None   # (4,) fp64 when use_global_min_max
   minmax_dense: bool = False                     # minmax rows are in list order (sweep fan-out), not per candidate
+  shard: Optional[object] = None                 # scgrhc.dist.Shard: this rank's offset / the total in the cohort-wide ordered list
+  n_ambiguous: int = 0                           # candidates whose R^2 lies within 1e-9 of 0.8 (REASON_AMBIGUOUS): the only
+                                                 # windows the closed form could decide differently from sklearn's lstsq
 
   def slots(self):
     return torch.arange(self.n_kept, device=self.kept_idx.device) if self.dense else self.kept_idx
@@ -260,8 +264,7 @@ def prepare_windows(arena, plan, scg_cols, rhc_col, min_rhc, use_global_min_max=
     gmm = buf('gmm', (4,), torch.float64)
     ops.global_minmax(minmax, keep, n, gmm)
     gmm = allreduce_minmax(gmm, group)
-  if check:
-    ops.check_errors(dev.index)
+  n_amb = ops.check_errors(dev.index) if check else 0
   n_kept = int(n_kept_t.item())
   dense = False
   if two_pass:
@@ -273,7 +276,7 @@ def prepare_windows(arena, plan, scg_cols, rhc_col, min_rhc, use_global_min_max=
                           scg, rhc, minmax, None, None, None, None)
     dense = True
   return WindowStore(scg, rhc, minmax, keep, reason, kept_idx[:n_kept], start_idx[:n_kept], stop_idx[:n_kept],
-                     rec_id[:n_kept], n_kept, n, dense, gmm)
+                     rec_id[:n_kept], n_kept, n, dense, gmm, n_ambiguous=n_amb)
 
 
 def prepare_subsets(arena, plan, sup_cols, rhc_col, min_rhc, subsets, out_dtype=torch.float32,
@@ -311,7 +314,7 @@ def prepare_subsets(arena, plan, sup_cols, rhc_col, min_rhc, subsets, out_dtype=
                             scgs[g0:g1], mms[g0:g1], rhc)
   for scg, mm in zip(scgs, mms):
     stores.append(WindowStore(scg, rhc, mm, pred.keep, pred.reason, pred.kept_idx, pred.start_idx, pred.stop_idx,
-                              pred.rec_id, n_kept, pred.n_cand, True, None, True))
+                              pred.rec_id, n_kept, pred.n_cand, True, None, True, pred.n_ambiguous))
   return stores
 
 
@@ -334,7 +337,12 @@ def allreduce_minmax(gmm, group=None):
     return gmm
   sign = torch.tensor([1.0, -1.0, 1.0, -1.0], dtype=gmm.dtype, device=gmm.device)
   v = gmm * sign
-  dist.all_reduce(v, op=dist.ReduceOp.MIN, group=group)
+  if dist.get_backend(group) != 'nccl' and v.is_cuda:     # gloo (CPU tests, 2 ranks sharing one GPU): host copy of 32 bytes
+    h = v.cpu()
+    dist.all_reduce(h, op=dist.ReduceOp.MIN, group=group)
+    v = h.to(gmm.device)
+  else:
+    dist.all_reduce(v, op=dist.ReduceOp.MIN, group=group)
   return v * sign
 
 
@@ -345,11 +353,108 @@ def shard_records(n_rec, rank, world):
   return lo, hi
 
 
+class PinnedArenaSource:
+  """Chunk source: the cohort already sits in (pinned) host memory, records back to back."""
+
+  def __init__(self, host_arena):
+    self.host = host_arena
+
+  def begin(self, ingest):
+    pass
+
+  def enqueue(self, k, chunk, stage):        # called with the copy stream current
+    stage.copy_(self.host[chunk[0]:chunk[1]], non_blocking=True)
+
+  def end(self):
+    pass
+
+
+class SynthSource:
+  """Chunk source: records generated on the device (scgrhc_synth_records) — cohorts that never exist on the host, e.g.
+  BASELINE configs[3]'s 100k records = 960 GB of fp64 ("must be generated on device in chunks")."""
+
+  def __init__(self, seed, T, kinds, defect_scale=16, grid=750, rec0=0):
+    self.seed, self.T, self.kinds, self.defect_scale, self.grid, self.rec0 = seed, int(T), list(kinds), defect_scale, grid, rec0
+
+  def begin(self, ingest):
+    pass
+
+  def enqueue(self, k, chunk, stage):
+    r0, r1 = chunk[5], chunk[6]
+    ops.synth_records(stage, self.seed, self.rec0 + r0, r1 - r0, self.T, self.kinds, self.defect_scale, self.grid)
+
+  def end(self):
+    pass
+
+
+class DiskSource:
+  """Chunk source: WFDB format-16 ``.dat`` files -> a ring of pinned chunk buffers -> HBM (the streaming replacement of the
+  reference's per-record ``wfdb.rdrecord``, recordutil.py:137).  A small pool of reader threads fills ring slot k % R with
+  the frames of chunk k (``readinto`` straight into pinned memory: no intermediate host copy, the GIL is released during
+  the read); the H2D copy of chunk k is enqueued as soon as its reads have landed, while chunks k+1 .. k+R-1 are still
+  being read and chunk k-1 is in the window kernel.  Host memory: R chunks, whatever the cohort size."""
+
+  def __init__(self, dat_paths, record_rows, nsig_file, ring=3, workers=8, byte_offsets=None):
+    self.paths, self.rows, self.nsig = list(dat_paths), [int(r) for r in record_rows], int(nsig_file)
+    self.ring, self.workers = max(2, int(ring)), max(1, int(workers))
+    self.offsets = list(byte_offsets) if byte_offsets is not None else [0] * len(self.paths)
+    self.slots = None
+    self.bytes_read = 0
+
+  def _read(self, r, view):
+    want = view.nbytes
+    with open(self.paths[r], 'rb', buffering=0) as f:
+      if self.offsets[r]:
+        f.seek(self.offsets[r])
+      got, mv = 0, memoryview(view).cast('B')
+      while got < want:
+        n = f.readinto(mv[got:])
+        if not n:
+          raise IOError('%s: %d bytes short of the %d frames its header announces' % (self.paths[r], want - got, self.rows[r]))
+        got += n
+    return want
+
+  def _submit(self, j):
+    lo, hi, r0, r1 = self.ingest.chunks[j][0], self.ingest.chunks[j][1], self.ingest.chunks[j][5], self.ingest.chunks[j][6]
+    buf = self.slots[j % self.ring]
+    base = self.ingest.record_base
+    self.futures[j] = [self.pool.submit(self._read, r, buf[int(base[r]) - lo:int(base[r + 1]) - lo]) for r in range(r0, r1)]
+
+  def begin(self, ingest):
+    from concurrent.futures import ThreadPoolExecutor
+    self.ingest = ingest
+    max_rows = max((c[1] - c[0] for c in ingest.chunks), default=0)
+    if self.slots is None or self.slots[0].shape[0] < max_rows:
+      self.slots = [torch.empty((max_rows, self.nsig), dtype=torch.int16, pin_memory=True).numpy() for _ in range(self.ring)]
+      self.pinned = [torch.from_numpy(a) for a in self.slots]
+    self.pool = ThreadPoolExecutor(self.workers)
+    self.futures, self.copied = {}, {}
+    for j in range(min(self.ring - 1, len(ingest.chunks))):
+      self._submit(j)
+
+  def enqueue(self, k, chunk, stage):
+    nxt = k + self.ring - 1
+    if nxt < len(self.ingest.chunks):
+      if k >= 1:
+        self.copied.pop(k - 1).synchronize()      # slot (k-1) % R is free once chunk k-1 has left host memory
+      self._submit(nxt)
+    for f in self.futures.pop(k):
+      self.bytes_read += f.result()
+    stage.copy_(self.pinned[k % self.ring][:chunk[1] - chunk[0]], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(stage.device))
+    self.copied[k] = ev
+
+  def end(self):
+    self.pool.shutdown(wait=True)
+    self.copied.clear()
+
+
 class HostIngest:
-  """Host-resident cohort -> HBM -> hot path, chunked at record boundaries and double buffered:
-  the pinned-host -> device copy of chunk k+1 (copy stream) overlaps the window kernel of chunk k
-  (compute stream).  This is the end-to-end path a caller with records in host memory uses
-  (the reference reads each record from disk into host numpy arrays, recordutil.py:137)."""
+  """Host-resident (or disk-resident, or device-generated) cohort -> HBM -> hot path, chunked at record boundaries and
+  double buffered: the pinned-host -> device copy of chunk k+1 (copy stream) overlaps the window kernel of chunk k
+  (compute stream).  This is the end-to-end path a caller with records outside HBM uses (the reference reads each record
+  from disk into host numpy arrays, recordutil.py:137)."""
 
   def __init__(self, plan, record_rows, nsig, device, chunk_records=64, digital_nsig=None, stages=None):
     """``nsig``: columns of the fp64 arena the window kernel reads.  ``digital_nsig``: the host cohort is WFDB
@@ -378,7 +483,9 @@ class HostIngest:
       lo, hi = int(base[r0]), int(base[r1])
       a, b = np.searchsorted(iv['row0'], [int(plan_base[r0]), int(plan_base[r1])], side='left')
       sub = iv[a:b].copy()
-      cand_lo = int(sub['cand0'][0]) if len(sub) else 0
+      # a chunk without candidate windows still needs the running candidate prefix: pass B of use_global_min_max cuts the
+      # kept list at these values, so they must be monotonic
+      cand_lo = int(iv['cand0'][a]) if a < len(iv) else int(plan.n_cand)
       n = int(sub['n_win'].sum())
       sub['row0'] -= int(plan_base[r0])
       sub['cand0'] -= cand_lo
@@ -391,40 +498,65 @@ class HostIngest:
         if digital_nsig else None
     self.copy_stream = torch.cuda.Stream(self.device)
     self.h2d_bytes = self.total_rows * (digital_nsig * 2 if digital_nsig else nsig * 8)
+    self._tables = None
 
-  def _stream(self, host_arena, decode, body):
+  def _decode_tables(self, decode):
+    """Per-record calibration as device tables (gain, baseline: (n_rec, ncols) fp64) + per-chunk record offsets, so that
+    the decode of a chunk is ONE launch whatever the number of records in it."""
+    cols, gain, baseline = decode
+    key = id(gain), id(baseline)
+    if self._tables is not None and self._tables[0] == key:
+      return self._tables[1:]
+    g = np.ascontiguousarray(np.asarray(gain, dtype=np.float64).reshape(len(self.record_rows), len(cols)))
+    b = np.ascontiguousarray(np.asarray(baseline, dtype=np.float64).reshape(len(self.record_rows), len(cols)))
+    ag = np.abs(g)
+    recip = bool(g.size and (ag >= 2.0 ** -40).all() and (ag <= 2.0 ** 60).all() and (np.abs(b) < 65536.0).all() and (b == np.floor(b)).all())
+    offs = [torch.from_numpy(np.ascontiguousarray(self.record_base[c[5]:c[6] + 1] - c[0])).to(self.device) for c in self.chunks]
+    longest = [int(self.record_rows[c[5]:c[6]].max()) if c[6] > c[5] else 0 for c in self.chunks]
+    t = (torch.from_numpy(g).to(self.device), torch.from_numpy(b).to(self.device), recip, offs, longest)
+    self._tables = (key,) + t
+    return t
+
+  def _stream(self, source, decode, body):
     """Copy (and, for digital cohorts, decode) chunk after chunk, double buffered, and hand each resident chunk to
-    ``body(dst, chunk)`` on the compute stream."""
+    ``body(dst, chunk)`` on the compute stream.  ``source``: a CPU tensor (the whole cohort in host memory) or a chunk
+    source (PinnedArenaSource / DiskSource / SynthSource)."""
     dev = self.device
+    if isinstance(source, torch.Tensor):
+      source = PinnedArenaSource(source)
     compute = torch.cuda.current_stream(dev)
     done = [None, None]
     self.copy_stream.wait_stream(compute)
     digital = self.digital_nsig is not None
     if digital and decode is None:
       raise ValueError('digital cohort: decode=(cols, gain, baseline) is required')
-    for k, chunk in enumerate(self.chunks):
-      lo, hi, cand_lo, nc, iv, r0, r1 = chunk
-      dst = self.bufs[k & 1][:hi - lo]
-      stage = self.dbufs[k & 1][:hi - lo] if digital else dst
-      with torch.cuda.stream(self.copy_stream):
-        if done[k & 1] is not None:
-          self.copy_stream.wait_event(done[k & 1])
-        stage.copy_(host_arena[lo:hi], non_blocking=True)
-        ready = torch.cuda.Event()
-        ready.record(self.copy_stream)
-      compute.wait_event(ready)
-      if digital:
-        cols, gain, baseline = decode
-        if isinstance(gain[0], (list, tuple, np.ndarray)):      # per-record calibration
-          for r in range(r0, r1):
-            a, b2 = int(self.record_base[r]) - lo, int(self.record_base[r + 1]) - lo
-            ops.decode_fmt16(stage[a:b2], list(cols), [float(v) for v in gain[r]], [float(v) for v in baseline[r]], dst[a:b2])
-        else:
-          ops.decode_fmt16(stage, list(cols), [float(v) for v in gain], [float(v) for v in baseline], dst)
-      if nc:
-        body(self._run_stages(dst, r0, r1), chunk)
-      done[k & 1] = torch.cuda.Event()
-      done[k & 1].record(compute)
+    per_record = digital and len(decode[1]) and isinstance(decode[1][0], (list, tuple, np.ndarray))
+    if per_record:
+      gain_t, base_t, recip, offs, longest = self._decode_tables(decode)
+    source.begin(self)
+    try:
+      for k, chunk in enumerate(self.chunks):
+        lo, hi, cand_lo, nc, iv, r0, r1 = chunk
+        dst = self.bufs[k & 1][:hi - lo]
+        stage = self.dbufs[k & 1][:hi - lo] if digital else dst
+        with torch.cuda.stream(self.copy_stream):
+          if done[k & 1] is not None:
+            self.copy_stream.wait_event(done[k & 1])
+          source.enqueue(k, chunk, stage)
+          ready = torch.cuda.Event()
+          ready.record(self.copy_stream)
+        compute.wait_event(ready)
+        if digital and nc:
+          if per_record:       # every record has its own gain / baseline (WFDB headers): device tables, one launch per chunk
+            ops.decode_fmt16_records(stage, offs[k], longest[k], list(decode[0]), gain_t[r0:r1], base_t[r0:r1], recip, dst)
+          else:
+            ops.decode_fmt16(stage, list(decode[0]), [float(v) for v in decode[1]], [float(v) for v in decode[2]], dst)
+        if nc:
+          body(self._run_stages(dst, r0, r1), chunk)
+        done[k & 1] = torch.cuda.Event()
+        done[k & 1].record(compute)
+    finally:
+      source.end()
 
   def _run_stages(self, dst, r0, r1):
     """Optional per-record stages on one resident chunk (records r0..r1): zero-phase band-pass, then resampling."""
@@ -442,14 +574,21 @@ class HostIngest:
     return dst
 
   def run(self, host_arena, scg_cols, rhc_col, min_rhc, out_dtype=torch.float32, flat_threshold=FLAT_THRESHOLD,
-          buffers=None, decode=None, use_global_min_max=False, group=None, normalisation='minmax'):
+          buffers=None, decode=None, use_global_min_max=False, group=None, normalisation='minmax', sink=None):
     """``host_arena``: (total_rows, nsig) fp64 CPU tensor (pinned for an asynchronous copy), or — with
     ``digital_nsig`` — (total_rows, digital_nsig) int16 frames plus ``decode = (cols, gain, baseline)`` where
-    gain/baseline are one list per selected column (all records) or one such list per record.
+    gain/baseline are one list per selected column (all records) or one such list per record; or a chunk source
+    (``DiskSource``: format-16 files streamed through a pinned ring; ``SynthSource``: generated on the device).
 
     ``use_global_min_max`` (recordutil.py:185-186) streams the cohort twice — predicates + per-window pairs, the
     dataset-level reduction (+ all-reduce over ``group``), then normalisation of the kept windows with the global pairs
-    into dense outputs — so cohorts larger than HBM (BASELINE configs[3]: 100k records) never have to be resident."""
+    into dense outputs — so cohorts larger than HBM (BASELINE configs[3]: 100k records) never have to be resident.
+
+    ``sink(k, scg, rhc, info)``: streamed OUTPUTS for cohorts whose windows do not fit in HBM either (100k records are
+    480 GB of fp32 windows): the window tensors of chunk k are written into a two-slot ring and handed to ``sink`` on
+    the compute stream right after the chunk's kernel (``info``: candidate range, and in global mode the kept-list
+    range — the tensors are then dense); the consumer must enqueue its reads on the current stream.  The returned
+    store then carries no window tensors, only the per-candidate metadata and the ordered kept list."""
     plan, dev = self.plan, self.device
     n, W, Cn = plan.n_cand, plan.W, len(scg_cols)
     b = buffers if buffers is not None else {}
@@ -466,17 +605,30 @@ class HostIngest:
     rec_id, n_kept_t = buf('rec_id', (n,), torch.int32), buf('n_kept', (1,), torch.int64)
     base_flags = (N.OUT_F64 if out_dtype == torch.float64 else 0) | _norm_flag(normalisation, use_global_min_max)
     scg = rhc = None
-    if not use_global_min_max:
+    ring = None
+    if sink is not None:
+      cmax = max((c[3] for c in self.chunks), default=0)
+      ring = [(buf('scg_ring%d' % i, (cmax, Cn, W), out_dtype), buf('rhc_ring%d' % i, (cmax, 1, W), out_dtype)) for i in range(2)]
+    elif not use_global_min_max:
       scg, rhc = buf('scg', (n, Cn, W), out_dtype), buf('rhc', (n, 1, W), out_dtype)
     launched = [0]
+    index = {id(c): i for i, c in enumerate(self.chunks)}
 
     def pass_a(dst, chunk):
       lo, hi, cand_lo, nc, iv, r0, r1 = chunk
       flags = base_flags | (N.PREDICATES_ONLY if use_global_min_max else 0) | (N.KEEP_ERRORS if launched[0] else 0)
+      k = index[id(chunk)]
+      so = ro = None
+      if ring is not None and not use_global_min_max:
+        so, ro = ring[k & 1]
+      elif scg is not None:
+        so, ro = scg[cand_lo:], rhc[cand_lo:]
       ops.process_windows(dst, iv, nc, W, plan.stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
-                          [0.0] * 4, None, 0, None if scg is None else scg[cand_lo:], None if rhc is None else rhc[cand_lo:],
+                          [0.0] * 4, None, 0, so, ro,
                           minmax[cand_lo:], keep[cand_lo:], reason[cand_lo:], cand_win[cand_lo:], cand_rec[cand_lo:])
       launched[0] += 1
+      if ring is not None and not use_global_min_max:
+        sink(k, so[:nc], ro[:nc], {'cand_lo': cand_lo, 'n_cand': nc, 'dense': False, 'keep': keep[cand_lo:cand_lo + nc]})
 
     self._stream(host_arena, decode, pass_a)
     ops.compact_kept(keep, cand_win, cand_rec, n, W, plan.stride, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
@@ -485,26 +637,31 @@ class HostIngest:
       gmm = buf('gmm', (4,), torch.float64)
       ops.global_minmax(minmax, keep, n, gmm)
       gmm = allreduce_minmax(gmm, group)
+    n_amb = 0
     if n and launched[0]:
-      ops.check_errors(dev.index)      # raises ValueError like the reference if a non-finite RHC window reached the regression
+      n_amb = ops.check_errors(dev.index)      # raises ValueError like the reference if a non-finite RHC window reached the regression
     n_kept = int(n_kept_t.item())      # device -> host read of the step's result
     if use_global_min_max:
-      scg, rhc = buf('scg', (n_kept, Cn, W), out_dtype), buf('rhc', (n_kept, 1, W), out_dtype)
+      if ring is None:
+        scg, rhc = buf('scg', (n_kept, Cn, W), out_dtype), buf('rhc', (n_kept, 1, W), out_dtype)
       kept = kept_idx[:n_kept]
       edges = torch.tensor([c[2] for c in self.chunks] + [n], dtype=torch.int64, device=dev)
       pos = torch.searchsorted(kept, edges).cpu().tolist()        # kept-list range of every chunk (plumbing, not arithmetic)
       gm = gmm.cpu().tolist()
-      order = {id(c): i for i, c in enumerate(self.chunks)}
 
       def pass_b(dst, chunk):
         lo, hi, cand_lo, nc, iv, r0, r1 = chunk
-        a, e = pos[order[id(chunk)]], pos[order[id(chunk)] + 1]
+        k = index[id(chunk)]
+        a, e = pos[k], pos[k + 1]
         if e > a:
+          so, ro = (ring[k & 1]) if ring is not None else (scg[a:], rhc[a:])
           ops.process_windows(dst, iv, nc, W, plan.stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold),
                               base_flags | N.USE_KEPT_LIST | N.NORM_GLOBAL, gm, (kept[a:e] - cand_lo).contiguous(), e - a,
-                              scg[a:], rhc[a:], None, None, None, None, None)
+                              so, ro, None, None, None, None, None)
+          if ring is not None:
+            sink(k, so[:e - a], ro[:e - a], {'cand_lo': cand_lo, 'n_cand': nc, 'dense': True, 'kept_lo': a, 'kept_hi': e})
 
       if n_kept:
         self._stream(host_arena, decode, pass_b)
     return WindowStore(scg, rhc, minmax, keep, reason, kept_idx[:n_kept], start_idx[:n_kept], stop_idx[:n_kept],
-                       rec_id[:n_kept], n_kept, n, bool(use_global_min_max), gmm)
+                       rec_id[:n_kept], n_kept, n, bool(use_global_min_max), gmm, n_ambiguous=n_amb)

@@ -3,6 +3,7 @@
 Only CUDA implementations are registered: calling an op on CPU tensors raises, there is no
 fallback.  torch supplies device memory and the current stream; all arithmetic is in the library.
 """
+import atexit
 import ctypes as C
 from typing import List, Optional, Sequence
 
@@ -25,6 +26,13 @@ def ctx(device_index):
       raise N.ScgrhcError(rc, (L.scgrhc_last_error(None) or b'').decode())
     c = _ctx[device_index] = h
   return c
+
+
+@atexit.register
+def _destroy_contexts():
+  while _ctx:
+    _, h = _ctx.popitem()
+    N.lib().scgrhc_ctx_destroy(h)
 
 
 def set_tuning(device_index, ctas_per_sm=0, stages=0):
@@ -253,6 +261,23 @@ def decode_fmt16(d: Tensor, cols: Sequence[int], gain: Sequence[float], baseline
                                          (C.c_double * n)(*gain), (C.c_double * n)(*baseline), _ptr(out), _stream(dev)))
 
 
+@torch.library.custom_op('scgrhc::decode_fmt16_records', mutates_args=('out',), device_types='cuda')
+def decode_fmt16_records(d: Tensor, rec_row0: Tensor, max_rec_rows: int, cols: Sequence[int], gain: Tensor, baseline: Tensor,
+                         recip: bool, out: Tensor) -> None:
+  """decode_fmt16 for a chunk of records with per-record calibration in ONE launch: ``rec_row0`` (n_rec+1,) int64 device,
+  ``gain`` / ``baseline`` (n_rec, len(cols)) fp64 device tables (every WFDB header carries its own pair)."""
+  dev = _dev(d)
+  _contig(d, torch.int16, 'd'); _contig(out, torch.float64, 'out'); _contig(rec_row0, torch.int64, 'rec_row0')
+  _contig(gain, torch.float64, 'gain'); _contig(baseline, torch.float64, 'baseline')
+  n, n_rec = len(cols), rec_row0.numel() - 1
+  if d.dim() != 2 or out.numel() < d.shape[0] * n or gain.numel() < n_rec * n or baseline.numel() < n_rec * n:
+    raise ValueError('decode_fmt16_records: d must be (T, nsig), out (T, len(cols)), tables (n_rec, len(cols))')
+  c = ctx(dev)
+  N.check(c, N.lib().scgrhc_decode_fmt16_records(c, _ptr(d), _ptr(rec_row0), n_rec, int(max_rec_rows), d.shape[1],
+                                                 (C.c_int32 * n)(*cols), n, _ptr(gain), _ptr(baseline), 1 if recip else 0,
+                                                 _ptr(out), _stream(dev)))
+
+
 @torch.library.custom_op('scgrhc::waveform_stats', mutates_args=('stats',), device_types='cuda')
 def waveform_stats(y: Tensor, min_rhc: float, stats: Tensor) -> None:
   """Per row of y (n_wave, L): R^2 of the OLS line, min, max, below-floor, non-finite, sum
@@ -282,13 +307,15 @@ def synth_records(out: Tensor, seed: int, rec0: int, n_rec: int, T: int, kinds: 
 
 def check_errors(device_index):
   """Synchronises the current stream; raises ValueError like the reference when a non-finite RHC
-  sample reached the regression (waveform_noise.py:32 via sklearn)."""
+  sample reached the regression (waveform_noise.py:32 via sklearn).  Returns the number of candidate windows the
+  covered process calls flagged REASON_AMBIGUOUS (R^2 within 1e-9 of 0.8)."""
   c = ctx(device_index)
   bad = C.c_int64(-1)
   rc = N.lib().scgrhc_check_errors(c, _stream(device_index), C.byref(bad))
   if rc == N.ERR_NONFINITE_RHC:
     raise ValueError('Input y contains NaN.')
   N.check(c, rc)
+  return int(N.lib().scgrhc_ambiguous_count(c))
 
 
 def selftest_div(device_index, seed, n, mode):

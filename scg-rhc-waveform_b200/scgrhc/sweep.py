@@ -14,7 +14,8 @@ from . import engine
 SAMPLE_FREQ = 500
 
 
-def iter_sweep(arena, sig_name, metas, record_rows, configs, out_dtype=torch.float32, group=None, buffers=None, fan_out=True):
+def iter_sweep(arena, sig_name, metas, record_rows, configs, out_dtype=torch.float32, group=None, buffers=None, fan_out=True,
+               rec0=0):
   """Yield ``(name, WindowStore)`` for every config in ``configs`` (name -> object with ``in_channels``, ``chamber``,
   ``segment_size``, ``min_RHC``, ``use_global_min_max``).
 
@@ -23,7 +24,9 @@ def iter_sweep(arena, sig_name, metas, record_rows, configs, out_dtype=torch.flo
   normalisation pass that reads every kept window once and writes it per subset (`engine.prepare_subsets`); their
   stores are dense and share the RHC tensor.  Everything else takes one fused pass per config; those stores reuse
   ``buffers`` (pass a dict) so that a long sweep does not hold 37 cohorts of windows in HBM: consume each store before
-  advancing."""
+  advancing.  ``rec0``: record number of the first record of ``arena`` (a rank's shard of a larger cohort); with a
+  process ``group`` every rank must iterate the same configs in the same order (they do: the order is a function of
+  ``configs`` alone), because configs with ``use_global_min_max`` all-reduce inside."""
   plans = {}
   order = sorted(configs, key=lambda k: (str(configs[k].chamber), float(configs[k].segment_size), k))
 
@@ -31,7 +34,7 @@ def iter_sweep(arena, sig_name, metas, record_rows, configs, out_dtype=torch.flo
     W = int(c.segment_size * SAMPLE_FREQ)
     key = (c.chamber, W)
     if key not in plans:
-      plans[key] = engine.plan_cohort(metas, c.chamber, record_rows, W)
+      plans[key] = engine.plan_cohort(metas, c.chamber, record_rows, W, rec0=rec0)
     return plans[key]
 
   groups = {}

@@ -74,6 +74,21 @@ def _parse_header(path):
   return name, fs, nsamp, sigs
 
 
+def read_header(path):
+  """Everything the streaming ingest needs WITHOUT touching the signal file: (sig_name, fs, n_frames, gain, baseline,
+  dat_path) of a single-file format-16 record; raises NotImplementedError for other layouts.  The frame count comes from
+  the header, else from the size of the signal file."""
+  name, fs, nsamp, sigs = _parse_header(path)
+  if not sigs:
+    raise ValueError('record %s has no signals' % path)
+  if any(s['fmt'] != '16' for s in sigs) or len({s['file'] for s in sigs}) != 1:
+    raise NotImplementedError('wfdbio reads single-file format-16 records only (install wfdb for others)')
+  dat = os.path.join(os.path.dirname(path), sigs[0]['file'])
+  on_disk = os.path.getsize(dat) // (2 * len(sigs))
+  T = on_disk if nsamp is None else min(nsamp, on_disk)
+  return [s['name'] for s in sigs], fs, T, [s['gain'] for s in sigs], [s['baseline'] for s in sigs], dat
+
+
 def read_digital(path):
   """(name, sig_name, fs, int16 frames (T, nsig), gain, baseline, units) for the record at ``path`` (no extension)."""
   name, fs, nsamp, sigs = _parse_header(path)

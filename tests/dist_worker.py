@@ -43,6 +43,23 @@ assert (part.intervals['n_win'] == full.intervals['n_win'][m]).all()
 counts = torch.tensor([part.n_cand], dtype=torch.int64)
 dist.all_reduce(counts)
 assert int(counts) == full.n_cand
+# the plumbing of the sharded drop-in (scgrhc/dist.py): kept-count exchange, one split draw for the job, rows to rank 0
+from scgrhc import dist as sdist  # noqa: E402
+n_local = 5 + 3 * rank
+sh = sdist.exchange_counts(n_local, torch.device('cpu'))
+assert sh.world == world and sh.counts == tuple(5 + 3 * r for r in range(world)) and sh.offset == sum(sh.counts[:rank])
+assert sh.total == sum(sh.counts)
+idx = sdist.broadcast_index(torch.arange(7) * (rank + 1), torch.device('cpu'))
+assert idx.tolist() == list(range(7))
+rows_t = (torch.arange(n_local * 3, dtype=torch.float32).reshape(n_local, 3) + 1000 * rank)
+got = sdist.gather_rows(rows_t, list(sh.counts))
+if rank == 0:
+  want_rows = torch.cat([torch.arange((5 + 3 * r) * 3, dtype=torch.float32).reshape(-1, 3) + 1000 * r for r in range(world)])
+  assert torch.equal(got, want_rows)
+else:
+  assert got is None
+empty = sdist.gather_rows(torch.zeros((0, 2)), [0] * world)           # nothing to send anywhere is fine
+assert empty is None or empty.shape == (0, 2)
 dist.barrier()
 if rank == 0:
   print('DIST_OK')

@@ -9,6 +9,8 @@ reproducible from code); only the reference's OUTPUTS are stored:
                       on adversarial + synthetic windows                        (waveform_noise.py:6-49)
   record_small.npz    get_segments + SCGDataset on a short record, full tensors (recordutil.py:55-66,122-149)
   configs.json        path-relevant keys of the 37 params.json + the reference loader's verdict
+  short_windows.json  is_straight_line / has_noise on windows of 2..50 samples (exact constants included)
+  ambiguity.npz       windows with R^2 = 0.8 +- 1e-13..1e-3: inputs, the reference's verdict and score
   records_full.json   the same on a 10-min record for all 37 waveform_NN configs:
                       ordered (start, stop) lists + sha256 of the fp32 tensors and min/max pairs
 """
@@ -234,6 +236,61 @@ def run_configs(h):
   print('configs: %d (%d load in the reference)' % (len(res), sum(v['reference_params_error'] is None for v in res.values())))
 
 
+def short_windows():
+  """Windows shorter than 51 samples (no flat-line test can fire): exact constants, ramps, noise."""
+  key, finc = synth_ref.record_params(SEED, 4321)
+  out = []
+  for n in (2, 3, 7, 8, 9, 16, 30, 49, 50):
+    t = np.arange(n, dtype=np.int64)
+    nz = synth_ref.noise(key, 3, t)
+    for v in (0.1, 0.3, 17.25, 1.0 / 3.0, -2.7, 1e-3, 25.123456789, -50.0, -50.000001, 0.0):
+      out.append(np.full(n, v))
+    out.append(3.0 + 0.01 * t)
+    out.append(20.0 + nz)
+    out.append(5.0 + 0.05 * t + 0.3 * nz)
+    out.append(5.0 + 0.05 * t + 1.0 * nz)
+  return out
+
+
+def run_short_windows(h):
+  """is_straight_line / has_noise of the reference on windows of 2..50 samples (segment_size < 0.102 s): exactly constant
+  windows are decided by sklearn's rounding noise there (R^2 = 1.0 iff the mean is exact), nothing else rejects them."""
+  wn = h.waveform_noise
+  p50 = h.params('waveform_06')
+  ys = short_windows()
+  res = {'inputs_sha': sha(np.concatenate(ys)), 'n': [len(y) for y in ys],
+         'straight': [bool(wn.is_straight_line(y)) for y in ys], 'has_noise': [bool(wn.has_noise(p50, y)) for y in ys]}
+  with open(os.path.join(HERE, 'short_windows.json'), 'w') as f:
+    json.dump(res, f)
+  print('short_windows: %d windows, straight=%d noisy=%d' % (len(ys), sum(res['straight']), sum(res['has_noise'])))
+
+
+def run_ambiguity(h):
+  """750-sample windows whose R^2 sits at 0.8 +- {1e-13 .. 1e-3}: the reference's own verdict (sklearn lstsq + r2_score)
+  and score, with the inputs stored (they come out of dot products, which are not bit-reproducible across BLAS builds)."""
+  from sklearn.linear_model import LinearRegression
+  wn = h.waveform_noise
+  key, _ = synth_ref.record_params(SEED, 999)
+  t = np.arange(750, dtype=np.float64)
+  x = t - t.mean()
+  xh = x / np.sqrt((x * x).sum())
+  e = synth_ref.noise(key, 3, np.arange(750, dtype=np.int64))
+  e = e - e.mean()
+  e = e - (e * xh).sum() * xh
+  eh = e / np.sqrt((e * e).sum())
+  ys, deltas = [], []
+  for d in (0.0, 1e-13, -1e-13, 1e-12, -1e-12, 1e-11, -1e-11, 1e-10, -1e-10, 3e-9, -3e-9, 1e-6, -1e-6, 1e-3, -1e-3):
+    r2 = 0.8 + d
+    ys.append(12.5 + 40.0 * (np.sqrt(r2) * xh + np.sqrt(1.0 - r2) * eh))
+    deltas.append(d)
+  ys = np.stack(ys)
+  X = np.arange(750).reshape(-1, 1)
+  np.savez_compressed(os.path.join(HERE, 'ambiguity.npz'), ys=ys, deltas=np.array(deltas),
+                      straight=np.array([bool(wn.is_straight_line(y)) for y in ys]),
+                      r2=np.array([LinearRegression().fit(X, y).score(X, y) for y in ys]))
+  print('ambiguity: %d windows' % len(ys))
+
+
 def run_reference_pickle(h):
   """A DataLoader pickled by the reference itself (recordutil.py:198-209): the drop-in's load_dataloader must read it."""
   import pickle
@@ -255,6 +312,11 @@ if __name__ == '__main__':
     with ReferenceHarness() as h:
       run_reference_pickle(h)
     sys.exit(0)
+  if len(sys.argv) > 1 and sys.argv[1] == 'short':
+    with ReferenceHarness() as h:
+      run_short_windows(h)
+      run_ambiguity(h)
+    sys.exit(0)
   with ReferenceHarness() as h:
     run_reference_pickle(h)
     run_configs(h)
@@ -262,3 +324,5 @@ if __name__ == '__main__':
     run_predicates(h)
     run_record_small(h)
     run_records_full(h)
+    run_short_windows(h)
+    run_ambiguity(h)

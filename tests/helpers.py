@@ -43,6 +43,18 @@ def adversarial_windows():
   return mg.adversarial_windows()
 
 
+def _make_golden():
+  import importlib.util
+  spec = importlib.util.spec_from_file_location('make_golden', os.path.join(GOLDEN, 'make_golden.py'))
+  mg = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mg)
+  return mg
+
+
+def short_windows():
+  return _make_golden().short_windows()
+
+
 def predicate_inputs():
   names, adv = adversarial_windows()
   rec = synth_ref.gen_record(SEED, 7, 150000, kinds=(3,))[:, 0].reshape(-1, 750)

@@ -175,9 +175,8 @@ def test_save_dataloaders_end_to_end(tmp_path, monkeypatch):
 
 
 def test_save_dataloaders_sweep_equals_one_job_per_config(tmp_path, monkeypatch):
-  """`waveform_pipeline.py prepare d1 d2 ...`: one read + one upload of the cohort, one predicate pass and one fan-out pass
+  """`recordutil.py prepare d1 d2 ...`: one read + one upload of the cohort, one predicate pass and one fan-out pass
   per chamber — and every config directory ends up with the loaders a separate save_dataloaders job writes."""
-  import waveform_pipeline
   root = tmp_path / 'data'; root.mkdir()
   monkeypatch.setattr(recordutil, 'PROCESSED_DATA_PATH', str(root))
   monkeypatch.setattr(recordutil, 'wfdb', wfdbio)
@@ -204,7 +203,7 @@ def test_save_dataloaders_sweep_equals_one_job_per_config(tmp_path, monkeypatch)
       dirs[(tag, cfg)] = d
   names = sorted(recordutil.get_record_names())
   monkeypatch.setattr(recordutil, 'get_record_names', lambda: names)     # the reference's order is hash-random (list(set))
-  counts = waveform_pipeline.prepare_all([str(dirs[('sweep', c)]) for c in cfgs])
+  counts = recordutil.prepare_all([str(dirs[('sweep', c)]) for c in cfgs])
   assert all(v for v in counts.values()) and len(counts) == len(cfgs)
   from paramutil import Params
   for cfg in cfgs:
@@ -220,7 +219,7 @@ def test_save_dataloaders_sweep_equals_one_job_per_config(tmp_path, monkeypatch)
     la = (dirs[('sweep', cfg)] / 'record_log.txt').read_text().splitlines()[1:]
     assert la == (dirs[('single', cfg)] / 'record_log.txt').read_text().splitlines()[1:]
   # a second run reports the existing loaders and touches nothing, like the reference's guard
-  assert waveform_pipeline.prepare_all([str(dirs[('sweep', c)]) for c in cfgs[:2]]) == {}
+  assert recordutil.prepare_all([str(dirs[('sweep', c)]) for c in cfgs[:2]]) == {}
 
 
 def test_device_decode_matches_host_dac_and_digital_ingest(tmp_path, monkeypatch):

@@ -68,14 +68,56 @@ def test_predicates_match_reference_golden():
   reason = st.reason.cpu().numpy()
   keep = st.keep.cpu().numpy().astype(bool)
   assert (((reason & N.REASON_FLAT) != 0) == g['flat']).all()
-  # exactly-constant windows: sklearn's R^2 is rounding noise (0.0 or 1.0); they are always flat-rejected
-  const = ys.max(axis=1) == ys.min(axis=1)
-  assert ((((reason & N.REASON_STRAIGHT) != 0) == g['straight']) | const).all()
+  # exactly-constant windows included: sklearn's R^2 is rounding noise there (1.0 iff np.mean(y) is exact)
+  assert (((reason & N.REASON_STRAIGHT) != 0) == g['straight']).all()
   assert (((reason & N.REASON_FLOOR) == 0) == g['in_range']).all()
   assert (keep == ~g['has_noise']).all()
   assert (reason & N.REASON_AMBIGUOUS).sum() == 0
   mm = st.minmax.cpu().numpy()
   assert (mm[:, 2] == ys.min(axis=1)).all() and (mm[:, 3] == ys.max(axis=1)).all()
+
+
+def test_short_and_constant_windows_match_reference_golden():
+  """Windows of 2..50 samples (no flat-line test can fire): the fused kernel decides exactly constant windows the way
+  sklearn's rounding noise does (R^2 = 1.0 iff np.mean(y) is exact, numpy's pairwise summation order), so get_segments
+  and the standalone is_straight_line()/has_noise() cannot disagree for small segment_size."""
+  import waveform_noise
+  import types
+  g = H.load_json('short_windows.json')
+  ys = H.short_windows()
+  assert H.sha(np.concatenate(ys)) == g['inputs_sha']
+  got_s, got_n = {}, {}
+  for L in sorted(set(g['n'])):
+    idx = [i for i, n in enumerate(g['n']) if n == L]
+    block = np.concatenate([ys[i] for i in idx]).reshape(-1, 1)
+    plan = scgrhc.Plan(np.array([(0, 0, len(idx), 0)], dtype=scgrhc.engine.INTERVAL_DTYPE), len(idx), L)
+    st = scgrhc.prepare_windows(torch.from_numpy(block.copy()).to(DEV), plan, [0], 0, -50.0, predicates_only=True)
+    reason, keep = st.reason.cpu().numpy(), st.keep.cpu().numpy().astype(bool)
+    for j, i in enumerate(idx):
+      got_s[i], got_n[i] = bool(reason[j] & N.REASON_STRAIGHT), not keep[j]
+  assert [got_s[i] for i in range(len(ys))] == g['straight']
+  assert [got_n[i] for i in range(len(ys))] == g['has_noise']
+  p = types.SimpleNamespace(min_RHC=-50)
+  for i in range(0, len(ys), 5):                    # the standalone API gives the same answers
+    assert waveform_noise.is_straight_line(ys[i]) == g['straight'][i] and waveform_noise.has_noise(p, ys[i]) == g['has_noise'][i]
+
+
+def test_ambiguous_windows_are_counted():
+  """R^2 planted at 0.8 +- 1e-13 .. 1e-3 (inputs and the reference's verdicts stored in the fixture): windows within 1e-9
+  of the threshold carry REASON_AMBIGUOUS and are counted on the WindowStore; here the closed form still agrees with
+  sklearn on every one of them."""
+  g = np.load(os.path.join(H.GOLDEN, 'ambiguity.npz'))
+  ys, n = g['ys'], len(g['ys'])
+  plan = scgrhc.Plan(np.array([(0, 0, n, 0)], dtype=scgrhc.engine.INTERVAL_DTYPE), n, 750)
+  st = scgrhc.prepare_windows(torch.from_numpy(ys.reshape(-1, 1).copy()).to(DEV), plan, [0], 0, -50.0, predicates_only=True)
+  reason = st.reason.cpu().numpy()
+  assert (((reason & N.REASON_STRAIGHT) != 0) == g['straight']).all()
+  amb = (reason & N.REASON_AMBIGUOUS) != 0
+  assert (amb == (np.abs(g['deltas']) < 5e-10)).all()
+  assert st.n_ambiguous == int(amb.sum()) == 9
+  clean = scgrhc.prepare_windows(torch.from_numpy(ys[-2:].reshape(-1, 1).copy()).to(DEV),
+                                 scgrhc.Plan(np.array([(0, 0, 2, 0)], dtype=scgrhc.engine.INTERVAL_DTYPE), 2, 750), [0], 0, -50.0)
+  assert clean.n_ambiguous == 0
 
 
 @pytest.mark.parametrize('cfg', ['waveform_06', 'waveform_10', 'waveform_11', 'waveform_23', 'waveform_19', 'waveform_15'])
@@ -348,10 +390,10 @@ def test_host_ingest_chunked_equals_resident(tmp_path):
   from scgrhc.engine import HostIngest
   sig = synth_ref.DEFAULT_SIG_NAMES
   kinds = synth_ref.kinds_for(sig)
-  rows = [30011, 752, 15000, 40000, 1500, 8000, 22222]
+  rows = [30011, 752, 15000, 40000, 1500, 8000, 22222, 9000]
   metas = [synth_ref.record_meta(90, events=e) for e in
            ({'PA_1': 0.2, 'RV_1': 50}, {'PA_1': 0}, {'RA_1': 0}, {'RV_1': 1, 'PA_1': 20, 'RA_1': 60, 'PA_2': 70}, {'PA_1': 0.5},
-            {'PA_1': 10}, {'PA_1': 3.3})]
+            {'PA_1': 10}, {'PA_1': 3.3}, {'RV_1': 0})]       # records 2 and 7 (the last) have no PA interval: empty chunks
   recs = [synth_ref.gen_record(H.SEED, 200 + r, T, kinds=kinds) for r, T in enumerate(rows)]
   host = torch.from_numpy(np.concatenate(recs)).pin_memory()
   plan = scgrhc.plan_cohort(metas, 'PA', rows, 750)
@@ -364,9 +406,12 @@ def test_host_ingest_chunked_equals_resident(tmp_path):
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
   # dataset-global pairs over a streamed cohort (two passes over the host data) == the resident two-pass result
   refg = scgrhc.prepare_windows(host.to(DEV), plan, [0, 1, 2], 3, -50.0, use_global_min_max=True)
-  stg = HostIngest(plan, rows, 4, DEV, chunk_records=2).run(host, [0, 1, 2], 3, -50.0, use_global_min_max=True)
-  assert stg.dense and stg.n_kept == refg.n_kept and torch.equal(stg.global_minmax, refg.global_minmax)
-  assert torch.equal(stg.scg[:stg.n_kept], refg.scg[:refg.n_kept]) and torch.equal(stg.rhc[:stg.n_kept], refg.rhc[:refg.n_kept])
+  for chunk in (1, 2, 3):          # chunk_records=1: chunks without a single candidate window, mid-cohort and trailing
+    stg = HostIngest(plan, rows, 4, DEV, chunk_records=chunk).run(host, [0, 1, 2], 3, -50.0, use_global_min_max=True,
+                                                                  buffers={'scg': torch.full((refg.n_kept, 3, 750), float('nan'), device=DEV),
+                                                                           'rhc': torch.full((refg.n_kept, 1, 750), float('nan'), device=DEV)})
+    assert stg.dense and stg.n_kept == refg.n_kept and torch.equal(stg.global_minmax, refg.global_minmax)
+    assert torch.equal(stg.scg[:stg.n_kept], refg.scg[:refg.n_kept]) and torch.equal(stg.rhc[:stg.n_kept], refg.rhc[:refg.n_kept])
   # format-16 digital frames with per-record calibration
   gains = [[1e5 + 10 * r, 2e5, 1.5e5, 400.0 + r] for r in range(len(rows))]
   bases = [[3.0 * r, -7.0, 0.0, 100.0 - r] for r in range(len(rows))]

@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
   with open(os.path.join(ROOT, 'include', 'scgrhc.h')) as f:
-    declared = set(re.findall(r'^(?:int|void|const char\*)\s+(scgrhc_[a-z0-9_]+)\s*\(', f.read(), flags=re.M))
+    declared = set(re.findall(r'^(?:int|void|int64_t|const char\*)\s+(scgrhc_[a-z0-9_]+)\s*\(', f.read(), flags=re.M))
   assert declared == set(N.SYMBOLS), declared ^ set(N.SYMBOLS)
   lib = ctypes.CDLL(scgrhc._native._build.LIB)
   for name in declared:

@@ -34,6 +34,25 @@ def test_predicates_match_reference():
     assert [tuple(s) for s in want] == orc.flat_segments(y)
 
 
+def test_short_windows_and_constant_windows_match_reference():
+  """Windows of 2..50 samples: no flat-line test can fire, so exactly constant windows are decided by sklearn's rounding
+  noise (R^2 = 1.0 iff np.mean(y) is exact) — the oracle restates that literally."""
+  g = H.load_json('short_windows.json')
+  ys = H.short_windows()
+  assert H.sha(np.concatenate(ys)) == g['inputs_sha'] and [len(y) for y in ys] == g['n']
+  assert [bool(orc.is_straight_line(y)) for y in ys] == g['straight']
+  assert [bool(orc.has_noise(y, -50)) for y in ys] == g['has_noise']
+  assert any(s for y, s in zip(ys, g['straight']) if y.max() == y.min()) and any(not s for y, s in zip(ys, g['straight']) if y.max() == y.min())
+
+
+def test_ambiguity_band_fixture():
+  """R^2 planted at 0.8 +- 1e-13 .. 1e-3: the closed form tracks sklearn's score to ~1e-15, so on these inputs it
+  still decides every window the way the reference does."""
+  g = np.load(os.path.join(H.GOLDEN, 'ambiguity.npz'))
+  assert (orc.is_straight_line(g['ys']) == g['straight']).all()
+  assert np.abs(orc.r_squared(g['ys']) - g['r2']).max() < 5e-15
+
+
 def test_flat_quirk_needs_two_positions():
   names, ys = H.predicate_inputs()
   by = dict(zip(names, ys))
