@@ -196,6 +196,14 @@ int scgrhc_gather_windows(scgrhc_ctx* ctx, const void* store, const int64_t* slo
  *      (nquads * 4 words, device, 16-byte aligned) for seed-exact checks against a host implementation. */
 int scgrhc_gather_windows_noise(scgrhc_ctx* ctx, const float* store, const int64_t* slots, int64_t n,
                                 int64_t window_elems, float* out, float sigma, uint64_t seed, uint64_t offset, void* stream);
+/* ---- the train loop's per-batch call in ONE launch (default_collate of recordutil.py:198 for the two tensors
+ *      waveform_train.py:358-359 reads): scg_out[b] = scg_store[slots[b]] (+ sigma * N(0,1) when sigma > 0, the same
+ *      Philox stream as scgrhc_gather_windows_noise) and rhc_out[b] = rhc_store[slots[b]]; fp32 windows of scg_elems
+ *      (= C*W) and rhc_elems (= W) floats; outputs are caller-provided (e.g. a ring of batch buffers).  The caller must
+ *      have the context's device current (no cudaSetDevice per batch). */
+int scgrhc_collate_batch(scgrhc_ctx* ctx, const float* scg_store, const float* rhc_store, const int64_t* slots, int64_t n,
+                         int32_t scg_elems, int32_t rhc_elems, float* scg_out, float* rhc_out, float sigma, uint64_t seed,
+                         uint64_t offset, void* stream);
 int scgrhc_philox_words(scgrhc_ctx* ctx, uint64_t seed, uint64_t offset, int64_t nquads, uint32_t* out, void* stream);
 
 /* ---- evaluation metrics of the consumer (waveform_test.py:21-50,66-70), per window: both fp32 waveforms (n, W) are

@@ -437,6 +437,27 @@ extern "C" int scgrhc_gather_windows_noise(scgrhc_ctx* ctx, const float* store, 
   return SCGRHC_OK;
 }
 
+extern "C" int scgrhc_collate_batch(scgrhc_ctx* ctx, const float* scg_store, const float* rhc_store, const int64_t* slots, int64_t n,
+                                    int32_t scg_elems, int32_t rhc_elems, float* scg_out, float* rhc_out, float sigma,
+                                    uint64_t seed, uint64_t offset, void* stream) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (n < 0 || scg_elems <= 0 || rhc_elems <= 0 || n > INT32_MAX || (n && (!scg_store || !rhc_store || !slots || !scg_out || !rhc_out)))
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "collate_batch: bad arguments");
+  if (n == 0) return SCGRHC_OK;
+  CollateParams P;
+  P.scg_store = scg_store; P.rhc_store = rhc_store; P.slots = reinterpret_cast<const long long*>(slots);
+  P.scg_out = scg_out; P.rhc_out = rhc_out; P.n = n; P.scg_elems = scg_elems; P.rhc_elems = rhc_elems;
+  P.sigma = sigma; P.seed = seed; P.offset = offset;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // no cudaSetDevice here: this is the per-batch call of the train loop; the launch goes to the stream's device
+  const int split = (int)std::min<long long>(8, std::max<long long>(1, (long long)ctx->sm_count * 4 / n));
+  dim3 grid((unsigned)n, (unsigned)split);
+  if (sigma > 0.0f) collate_batch_kernel<true><<<grid, 256, 0, st>>>(P);
+  else collate_batch_kernel<false><<<grid, 256, 0, st>>>(P);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
 extern "C" int scgrhc_philox_words(scgrhc_ctx* ctx, uint64_t seed, uint64_t offset, int64_t nquads, uint32_t* out, void* stream) {
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
   if (nquads < 0 || (nquads && !out)) return fail(ctx, SCGRHC_ERR_BAD_ARG, "philox_words: bad arguments");

@@ -337,6 +337,60 @@ __global__ void __launch_bounds__(256) gather_noise_kernel(const float* __restri
     }
   }
 }
+// ---- one-launch batch collate (default_collate of recordutil.py:198 for the two tensors the trainer reads,
+//      waveform_train.py:358-359): scg_out[b] = scg_store[slot[b]] (+ sigma * N(0,1), the noise extension, element j of
+//      the SCG batch drawing word j & 3 of Philox block j >> 2 exactly as gather_noise_kernel does) and
+//      rhc_out[b] = rhc_store[slot[b]], fp32.  blockIdx.x = batch item; blockIdx.y splits the window when the batch is
+//      too small to fill the GPU.
+struct CollateParams {
+  const float* scg_store; const float* rhc_store;
+  const long long* slots;
+  float* scg_out; float* rhc_out;
+  long long n;
+  int scg_elems, rhc_elems;    // floats per window: C*W and W
+  float sigma;
+  unsigned long long seed, offset;
+};
+template <bool NOISE>
+__global__ void __launch_bounds__(256) collate_batch_kernel(const __grid_constant__ CollateParams P) {
+  const long long b = blockIdx.x;
+  const long long slot = P.slots[b];
+  const int part = blockIdx.y, nparts = gridDim.y;
+  const float* ssrc = P.scg_store + slot * P.scg_elems;
+  const float* rsrc = P.rhc_store + slot * P.rhc_elems;
+  float* sdst = P.scg_out + b * P.scg_elems;
+  float* rdst = P.rhc_out + b * P.rhc_elems;
+  const int tid = part * blockDim.x + threadIdx.x, nthr = nparts * blockDim.x;
+  // RHC window (and the SCG window without noise): 8-byte words when the window offsets allow, else 4-byte
+  const bool r8 = (P.rhc_elems & 1) == 0 && ((reinterpret_cast<uintptr_t>(P.rhc_store) | reinterpret_cast<uintptr_t>(P.rhc_out)) & 7) == 0;
+  if (r8) {
+    for (int i = tid; i < (P.rhc_elems >> 1); i += nthr) reinterpret_cast<float2*>(rdst)[i] = __ldcs(reinterpret_cast<const float2*>(rsrc) + i);
+  } else {
+    for (int i = tid; i < P.rhc_elems; i += nthr) rdst[i] = __ldcs(rsrc + i);
+  }
+  if constexpr (!NOISE) {
+    const bool s8 = (P.scg_elems & 1) == 0 && ((reinterpret_cast<uintptr_t>(P.scg_store) | reinterpret_cast<uintptr_t>(P.scg_out)) & 7) == 0;
+    if (s8) {
+      for (int i = tid; i < (P.scg_elems >> 1); i += nthr) reinterpret_cast<float2*>(sdst)[i] = __ldcs(reinterpret_cast<const float2*>(ssrc) + i);
+    } else {
+      for (int i = tid; i < P.scg_elems; i += nthr) sdst[i] = __ldcs(ssrc + i);
+    }
+  } else {
+    // Philox blocks are aligned to the element index of the whole batch: walk the quads that overlap this window (the
+    // two at its ends are shared with the neighbours and computed by both)
+    const long long j0 = b * P.scg_elems, j1 = j0 + P.scg_elems;
+    for (long long q = (j0 >> 2) + tid; q < ((j1 + 3) >> 2); q += nthr) {
+      const float4 z = philox_normal4(P.seed, P.offset, (unsigned long long)q);
+      const float zs[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const long long j = 4 * q + r;
+        if (j >= j0 && j < j1) sdst[j - j0] = __fmaf_rn(P.sigma, zs[r], __ldcs(ssrc + (j - j0)));
+      }
+    }
+  }
+}
+
 __global__ void philox_words_kernel(unsigned long long seed, unsigned long long offset, long long nquads, uint4* out) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q < nquads)

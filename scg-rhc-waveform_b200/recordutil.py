@@ -154,6 +154,12 @@ class SCGDataset(Dataset):
     self._segments = None
     return self
 
+  def collate_meta(self, h):
+    """Elements 2..6 of a collated batch for the items ``h`` (numpy indices): names, start, stop, the two min/max pairs."""
+    mm = torch.from_numpy(self._mm[h])
+    return [tuple(self._names[i] for i in h), torch.from_numpy(self._start[h]), torch.from_numpy(self._stop[h]),
+            [mm[:, 0], mm[:, 1]], [mm[:, 2], mm[:, 3]]]
+
   def collate(self, idx, noise=None):
     """What default_collate makes of items ``idx`` (recordutil.py:198): [scg (B,C,L), rhc (B,1,L), names,
     start (B,), stop (B,), [scg_min (B,), scg_max (B,)], [rhc_min (B,), rhc_max (B,)]]."""
@@ -161,17 +167,15 @@ class SCGDataset(Dataset):
       ii = idx.to(self.scg.device, torch.int64).contiguous()
       scg = torch.empty((ii.numel(),) + tuple(self.scg.shape[1:]), dtype=self.scg.dtype, device=self.scg.device)
       rhc = torch.empty((ii.numel(),) + tuple(self.rhc.shape[1:]), dtype=self.rhc.dtype, device=self.rhc.device)
-      if noise is not None and noise[0] > 0 and self.scg.dtype == torch.float32:
-        ops.gather_windows_noise(self.scg, ii, scg, float(noise[0]), int(noise[1]), int(noise[2]))   # extension: SCG inputs only
-      else:
+      if self.scg.dtype == torch.float32 and ii.numel():
+        sigma = float(noise[0]) if noise is not None and noise[0] > 0 else 0.0             # extension: SCG inputs only
+        ops.BatchCollator(self.scg, self.rhc, ii)(0, ii.numel(), scg, rhc, sigma, int(noise[1]) if sigma else 0, int(noise[2]) if sigma else 0)
+      elif ii.numel():
         ops.gather_windows(self.scg, ii, scg)
-      ops.gather_windows(self.rhc, ii, rhc)
+        ops.gather_windows(self.rhc, ii, rhc)
     else:
       scg, rhc = self.scg[idx], self.rhc[idx]
-    h = idx.cpu().numpy()
-    mm = torch.from_numpy(self._mm[h])
-    return [scg, rhc, tuple(self._names[i] for i in h), torch.from_numpy(self._start[h]), torch.from_numpy(self._stop[h]),
-            [mm[:, 0], mm[:, 1]], [mm[:, 2], mm[:, 3]]]
+    return [scg, rhc] + self.collate_meta(idx.cpu().numpy())
 
   def __getstate__(self):
     st = dict(self.__dict__)
@@ -220,29 +224,109 @@ class SCGDataset(Dataset):
     return self._item(index)
 
 
+class _Batch(list):
+  """A collated batch ``[scg, rhc, names, start, stop, [scg_min, scg_max], [rhc_min, rhc_max]]`` whose metadata elements
+  are assembled on first access: the trainer reads elements 0 and 1 only (waveform_train.py:358-359), and the tuple of
+  256 names + four small tensors per batch would cost more host time than the gather kernel takes."""
+  __slots__ = ('_fill',)
+
+  def __init__(self, scg, rhc, fill):
+    super().__init__((scg, rhc, None, None, None, None, None))
+    self._fill = fill
+
+  def _materialise(self):
+    if self._fill is not None:
+      fill, self._fill = self._fill, None
+      list.__setitem__(self, slice(2, 7), fill())
+
+  def __getitem__(self, i):
+    if self._fill is not None and not (type(i) is int and 0 <= i < 2):
+      self._materialise()
+    return list.__getitem__(self, i)
+
+  def __iter__(self):
+    self._materialise()
+    return list.__iter__(self)
+
+  def __reduce__(self):
+    self._materialise()
+    return (list, (list(list.__iter__(self)),))
+
+  def __repr__(self):
+    self._materialise()
+    return list.__repr__(self)
+
+  def __eq__(self, other):
+    self._materialise()
+    return list.__eq__(self, other)
+
+  __hash__ = None
+
+
 class WindowLoader:
   """The slice of ``torch.utils.data.DataLoader`` the consumers use (``len``, iteration, ``.dataset``,
-  ``.batch_size``) with device-side batch assembly: a shuffled index permutation + one gather kernel per
-  batch instead of per-item collation (recordutil.py:198-200: shuffle=True, drop_last=False)."""
+  ``.batch_size``) with device-side batch assembly: a shuffled index permutation, uploaded once per epoch, + ONE gather
+  launch per batch instead of per-item collation (recordutil.py:198-200: shuffle=True, drop_last=False).
 
-  noise_std, noise_seed, _batches_served = 0.0, 0, 0      # defaults for loaders pickled before the noise extension existed
+  ``reuse_buffers = R`` (default 0 = fresh tensors per batch, like DataLoader): batches are written into a ring of R
+  preallocated (batch_size, C, L) / (batch_size, 1, L) buffers, so batch k's tensors are overwritten by batch k + R — for
+  train loops that are done with a batch before asking for the R-th next one (the reference's is).
 
-  def __init__(self, dataset, batch_size=1, shuffle=False, generator=None, noise_std=0.0, noise_seed=0):
+  Noise extension (default off): every batch draws from the Philox stream ``(noise_seed, epoch * len(loader) + batch)``;
+  ``epoch`` counts the passes made through THIS object and is not persisted — a trainer that resumes from a checkpoint
+  calls ``set_epoch(e)`` (as with DistributedSampler) to continue the noise sequence instead of replaying it."""
+
+  noise_std, noise_seed, epoch, reuse_buffers = 0.0, 0, 0, 0      # defaults for loaders pickled before these existed
+
+  def __init__(self, dataset, batch_size=1, shuffle=False, generator=None, noise_std=0.0, noise_seed=0, reuse_buffers=0):
     self.dataset, self.batch_size, self.shuffle, self.generator = dataset, int(batch_size), shuffle, generator
     # extension (absent from the reference, default off): Gaussian noise on the SCG inputs of every batch, drawn from a
-    # counter-based Philox stream (seed, batch counter) inside the gather kernel
-    self.noise_std, self.noise_seed, self._batches_served = float(noise_std), int(noise_seed), 0
+    # counter-based Philox stream (seed, epoch, batch) inside the gather kernel
+    self.noise_std, self.noise_seed, self.epoch = float(noise_std), int(noise_seed), 0
+    self.reuse_buffers = int(reuse_buffers)
+
+  def set_epoch(self, epoch):
+    self.epoch = int(epoch)
 
   def __len__(self):
     return (len(self.dataset) + self.batch_size - 1) // self.batch_size
 
+  def __getstate__(self):
+    st = dict(self.__dict__)
+    st.pop('_ring', None)
+    return st
+
   def __iter__(self):
-    n = len(self.dataset)
+    ds = self.dataset
+    n, bs = len(ds), self.batch_size
     order = torch.randperm(n, generator=self.generator) if self.shuffle else torch.arange(n)
-    for b in range(0, n, self.batch_size):
-      noise = (self.noise_std, self.noise_seed, self._batches_served) if self.noise_std > 0 else None
-      self._batches_served += 1
-      yield self.dataset.collate(order[b:b + self.batch_size], noise)
+    base = self.epoch * len(self)
+    self.epoch += 1
+    sigma, seed = (self.noise_std, self.noise_seed) if self.noise_std > 0 else (0.0, 0)
+    if not (ds.scg.is_cuda and ds.scg.dtype == torch.float32 and n):
+      for k, b in enumerate(range(0, n, bs)):
+        yield ds.collate(order[b:b + bs], (sigma, seed, base + k) if sigma else None)
+      return
+    dev = ds.scg.device
+    collate = ops.BatchCollator(ds.scg, ds.rhc, order.to(dev))
+    tail_s, tail_r = tuple(ds.scg.shape[1:]), tuple(ds.rhc.shape[1:])
+    ring = None
+    if self.reuse_buffers > 0:
+      ring = getattr(self, '_ring', None)
+      if ring is None or len(ring) != self.reuse_buffers or ring[0][0].shape != (bs,) + tail_s or ring[0][0].device != dev:
+        ring = self._ring = [(torch.empty((bs,) + tail_s, dtype=torch.float32, device=dev),
+                              torch.empty((bs,) + tail_r, dtype=torch.float32, device=dev)) for _ in range(self.reuse_buffers)]
+    order_np = order.numpy()
+    for k, b in enumerate(range(0, n, bs)):
+      m = min(bs, n - b)
+      if ring is not None:
+        scg, rhc = ring[k % len(ring)]
+        scg, rhc = scg[:m], rhc[:m]
+      else:
+        scg = torch.empty((m,) + tail_s, dtype=torch.float32, device=dev)
+        rhc = torch.empty((m,) + tail_r, dtype=torch.float32, device=dev)
+      collate(b, m, scg, rhc, sigma, seed, base + k)
+      yield _Batch(scg, rhc, lambda h=order_np[b:b + m]: ds.collate_meta(h))
 
 
 def _normalise_block(block, n, minmax_scg, minmax_rhc, out_dtype, L=None):

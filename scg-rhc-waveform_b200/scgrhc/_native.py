@@ -56,7 +56,7 @@ _lib = None
 SYMBOLS = ['scgrhc_abi_version', 'scgrhc_ctx_create', 'scgrhc_ctx_destroy', 'scgrhc_last_error',
            'scgrhc_ctx_set_tuning', 'scgrhc_ctx_sm_count', 'scgrhc_plan_record', 'scgrhc_plan_cohort', 'scgrhc_process_windows',
            'scgrhc_compact_kept', 'scgrhc_normalize_subsets', 'scgrhc_global_minmax', 'scgrhc_check_errors', 'scgrhc_ambiguous_count', 'scgrhc_gather_windows',
-           'scgrhc_window_metrics', 'scgrhc_sosfiltfilt', 'scgrhc_sosfiltfilt_scan', 'scgrhc_resample_poly', 'scgrhc_gather_windows_noise', 'scgrhc_philox_words', 'scgrhc_rolling_range_lt', 'scgrhc_decode_fmt16', 'scgrhc_decode_fmt16_records', 'scgrhc_waveform_stats', 'scgrhc_synth_records', 'scgrhc_selftest_div']
+           'scgrhc_window_metrics', 'scgrhc_sosfiltfilt', 'scgrhc_sosfiltfilt_scan', 'scgrhc_resample_poly', 'scgrhc_gather_windows_noise', 'scgrhc_collate_batch', 'scgrhc_philox_words', 'scgrhc_rolling_range_lt', 'scgrhc_decode_fmt16', 'scgrhc_decode_fmt16_records', 'scgrhc_waveform_stats', 'scgrhc_synth_records', 'scgrhc_selftest_div']
 
 
 def lib():
@@ -92,6 +92,7 @@ def lib():
   L.scgrhc_ambiguous_count.restype = i64
   L.scgrhc_gather_windows.argtypes = [vp, vp, vp, i64, i64, vp, vp]
   L.scgrhc_gather_windows_noise.argtypes = [vp, vp, vp, i64, i64, vp, C.c_float, u64, u64, vp]
+  L.scgrhc_collate_batch.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp, C.c_float, u64, u64, vp]
   L.scgrhc_philox_words.argtypes = [vp, u64, u64, i64, vp, vp]
   L.scgrhc_window_metrics.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp]
   L.scgrhc_sosfiltfilt.argtypes = [vp, vp, vp, vp, vp, C.POINTER(i64), i32, i32, C.POINTER(i32), i32, C.POINTER(dbl), C.POINTER(dbl), i32, i32, vp]

@@ -216,6 +216,40 @@ def gather_windows_noise(store: Tensor, slots: Tensor, out: Tensor, sigma: float
                                                  C.c_uint64(seed & (2 ** 64 - 1)), C.c_uint64(offset & (2 ** 64 - 1)), _stream(dev)))
 
 
+class BatchCollator:
+  """The train loop's per-batch call (default_collate of recordutil.py:198 for the tensors waveform_train.py:358-359
+  reads): ONE launch of scgrhc_collate_batch writes the SCG batch (+ Philox noise) and the RHC batch from one slot list.
+  Bound through plain ctypes with everything resolved once per epoch — the torch.library dispatch of the generic ops
+  costs more than the kernel at batch sizes of a few hundred windows."""
+
+  def __init__(self, scg_store, rhc_store, slots_dev):
+    for t, nm in ((scg_store, 'scg_store'), (rhc_store, 'rhc_store')):
+      _contig(t, torch.float32, nm)
+    _contig(slots_dev, torch.int64, 'slots')
+    self.dev = _dev(scg_store)
+    if not (rhc_store.is_cuda and slots_dev.is_cuda) or rhc_store.shape[0] != scg_store.shape[0]:
+      raise ValueError('collate: stores and slots must live on one CUDA device and hold the same windows')
+    self.scg_store, self.rhc_store, self.slots = scg_store, rhc_store, slots_dev      # keep them alive
+    self.E_s, self.E_r = scg_store[0].numel() if scg_store.shape[0] else 1, rhc_store[0].numel() if rhc_store.shape[0] else 1
+    self.ctx, self.fn = ctx(self.dev), N.lib().scgrhc_collate_batch
+    self.p_s, self.p_r, self.p_i = scg_store.data_ptr(), rhc_store.data_ptr(), slots_dev.data_ptr()
+
+  def __call__(self, first, n, scg_out, rhc_out, sigma=0.0, seed=0, offset=0):
+    """scg_out[b], rhc_out[b] = stores[slots[first + b]] for b < n (outputs: contiguous fp32 CUDA tensors, large enough)."""
+    if first < 0 or first + n > self.slots.numel() or scg_out.numel() < n * self.E_s or rhc_out.numel() < n * self.E_r:
+      raise ValueError('collate: slot range or output buffers out of bounds')
+    stream = torch.cuda.current_stream(self.dev).cuda_stream
+    args = (self.ctx, self.p_s, self.p_r, self.p_i + 8 * first, n, self.E_s, self.E_r, scg_out.data_ptr(), rhc_out.data_ptr(),
+            sigma, seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, stream)
+    if torch.cuda.current_device() != self.dev:
+      with torch.cuda.device(self.dev):
+        rc = self.fn(*args)
+    else:
+      rc = self.fn(*args)
+    if rc:
+      N.check(self.ctx, rc)
+
+
 def philox_words(device_index, seed, offset, nquads):
   """Raw Philox4x32-10 blocks (nquads, 4) uint32 as int64 numpy array, for seed-exact checks."""
   out = torch.empty((nquads, 4), dtype=torch.int32, device='cuda:%d' % device_index)

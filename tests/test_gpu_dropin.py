@@ -289,6 +289,71 @@ def test_device_decode_every_shape_is_bit_exact(nsig_in, sel):
     assert got[~np.isnan(got)].tobytes() == want[~np.isnan(want)].tobytes(), (gains, bases)
 
 
+@pytest.mark.parametrize('nsig_in,sel', [(4, [0, 1, 2, 3]), (5, [4, 0, 3]), (3, [1]), (8, [7, 2, 5, 0, 1])])
+def test_device_decode_per_record_tables_one_launch(nsig_in, sel):
+  """scgrhc_decode_fmt16_records: a chunk of ragged records, every record with its own gain / baseline (device tables),
+  ONE launch — bit for bit numpy's (d - baseline) / gain per record; both the reciprocal path and (a fractional baseline
+  in the table) the IEEE-division path."""
+  from scgrhc import ops
+  rng = np.random.default_rng(nsig_in * 7 + len(sel))
+  rows = [7001, 1, 300, 25000, 64]
+  off = np.concatenate([[0], np.cumsum(rows)])
+  d = rng.integers(-32768, 32768, size=(off[-1], nsig_in), dtype=np.int64).astype(np.int16)
+  for frac in (False, True):
+    gain = rng.uniform(0.5, 3e5, size=(len(rows), len(sel)))
+    gain[1] = 1e-3 / 3
+    base = np.round(rng.uniform(-3e4, 3e4, size=(len(rows), len(sel))))
+    if frac:
+      base[3, 0] += 0.5
+    out = torch.full((off[-1] + 1, len(sel)), -1.0, dtype=torch.float64, device='cuda')
+    ops.decode_fmt16_records(torch.from_numpy(d).cuda(), torch.from_numpy(off).cuda(), max(rows), sel, torch.from_numpy(gain).cuda(),
+                             torch.from_numpy(base).cuda(), not frac, out[:off[-1]])
+    got = out.cpu().numpy()
+    assert (got[-1] == -1.0).all()                                    # nothing written past the chunk
+    for r in range(len(rows)):
+      x = d[off[r]:off[r + 1]][:, sel]
+      want = (x.astype(np.float64) - base[r]) / gain[r]
+      want[x == -32768] = np.nan
+      g = got[off[r]:off[r + 1]]
+      assert np.array_equal(np.isnan(g), np.isnan(want)) and g[~np.isnan(g)].tobytes() == want[~np.isnan(want)].tobytes(), (r, frac)
+
+
+def test_one_launch_collate_equals_the_gathers():
+  """scgrhc_collate_batch (one launch for the SCG and RHC batch, plain ctypes) == the two generic gathers, with the noise
+  extension == scgrhc_gather_windows_noise; the loader's ring of reused batch buffers and its lazy metadata."""
+  from scgrhc import ops
+  g = torch.Generator().manual_seed(3)
+  for C, W, n_store, nb in ((3, 750, 700, 256), (1, 750, 50, 7), (4, 375, 300, 300), (2, 333, 40, 33)):
+    scg_store = torch.rand((n_store, C, W), generator=g).cuda()
+    rhc_store = torch.rand((n_store, 1, W), generator=g).cuda()
+    slots = torch.randint(0, n_store, (nb + 5,), generator=g).cuda()
+    col = ops.BatchCollator(scg_store, rhc_store, slots)
+    a, b = torch.full((nb + 1, C, W), -2.0, device='cuda'), torch.full((nb + 1, 1, W), -2.0, device='cuda')
+    col(3, nb, a, b)
+    assert torch.equal(a[:nb], scg_store[slots[3:3 + nb]]) and torch.equal(b[:nb], rhc_store[slots[3:3 + nb]])
+    assert (a[nb] == -2).all() and (b[nb] == -2).all()
+    want = torch.empty((nb, C, W), device='cuda')
+    ops.gather_windows_noise(scg_store, slots[3:3 + nb].contiguous(), want, 0.07, 1234, 9)
+    col(3, nb, a, b, 0.07, 1234, 9)
+    assert torch.equal(a[:nb], want) and torch.equal(b[:nb], rhc_store[slots[3:3 + nb]]) and (a[nb] == -2).all()
+    with pytest.raises(ValueError):
+      col(3, nb + 3, a, b)
+  n, C, W = 70, 3, 750
+  ds = recordutil.SCGDataset.from_arrays(torch.rand((n, C, W), generator=g).cuda(), torch.rand((n, 1, W), generator=g).cuda(),
+                                         ['r%d' % i for i in range(n)], np.arange(n) * W, np.arange(n) * W + W, np.arange(4 * n, dtype=np.float64).reshape(n, 4), 1.5)
+  fresh = list(recordutil.WindowLoader(ds, batch_size=32))
+  assert [len(x[2]) for x in fresh] == [32, 32, 6] and torch.equal(torch.cat([x[0] for x in fresh]), ds.scg)
+  assert fresh[2][2] == ('r64', 'r65', 'r66', 'r67', 'r68', 'r69') and fresh[1][3].tolist() == (np.arange(32, 64) * W).tolist()
+  assert float(fresh[2][6][1][5]) == 4 * 69 + 3 and len(fresh[0]) == 7 and pickle.loads(pickle.dumps(fresh[0]))[2][0] == 'r0'
+  ring = recordutil.WindowLoader(ds, batch_size=32, reuse_buffers=2)
+  ptrs = []
+  for k, batch in enumerate(ring):
+    assert torch.equal(batch[0], ds.scg[32 * k:32 * k + 32]) and torch.equal(batch[1], ds.rhc[32 * k:32 * k + 32])
+    ptrs.append(batch[0].data_ptr())
+  assert ptrs[0] == ptrs[2] != ptrs[1]                               # batch k + R reuses the buffer of batch k
+  assert len(pickle.dumps(ring)) < len(pickle.dumps(ds)) + 4096      # the ring is not pickled
+
+
 def test_noise_injection_extension_philox():
   """Extension (absent from the reference): seed-exact Philox4x32-10 stream, Box-Muller within fp32 tolerance,
   distribution checks, and the loader wiring (SCG inputs only, a fresh stream per batch, off by default)."""
