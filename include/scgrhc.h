@@ -62,6 +62,11 @@ typedef enum {
                                      z-score instead of min-max: (x - mean) / (std + 0.0001), mean and population std taken
                                      jointly over the (W, C) SCG block and over the RHC window; the minmax output then holds
                                      {scg_mean, scg_std, rhc_mean, rhc_std}.  Not combinable with NORM_GLOBAL / USE_KEPT_LIST. */
+#define SCGRHC_ARENA_PLANAR 128u /* the arena is PLANAR: column c of arena row r at arena[c * arena_rows + r] (one plane per signal over the
+                                     whole arena) instead of wfdb's interleaved (rows, nsig).  The kernel then judges a candidate on its RHC
+                                     plane alone and fetches the SCG planes of KEPT windows only (a rejected window costs 6 KB of DRAM traffic,
+                                     not 24 KB); scgrhc_decode_fmt16* and scgrhc_synth_records can write this layout directly.  The minmax SCG
+                                     pair of a rejected candidate is NaN.  Not combinable with NORM_ZSCORE; W <= 1024. */
 #define SCGRHC_KEEP_ALL      16u  /* evaluate the predicates (reason bits) but keep and normalise every window:
                                      SCGDataset(segments, ...) on caller-chosen segments, no has_noise, no error */
 
@@ -256,6 +261,10 @@ int scgrhc_rolling_range_lt(scgrhc_ctx* ctx, const double* y, int64_t n, int32_t
  *      (d - baseline) / gain, the invalid code -32768 -> NaN.  gain/baseline/cols are host arrays of ncols entries. */
 int scgrhc_decode_fmt16(scgrhc_ctx* ctx, const int16_t* d, int64_t T, int32_t nsig_in, const int32_t* cols,
                         int32_t ncols, const double* gain, const double* baseline, double* out, void* stream);
+/* Output layout of the two decode entry points and of scgrhc_synth_records from now on: plane_stride = 0 (default) is
+ * interleaved (T, ncols); plane_stride = P > 0 writes column j of row t to out[j * P + t] (SCGRHC_ARENA_PLANAR with
+ * arena_rows = P).  Sticky per context; the calls themselves are unchanged. */
+int scgrhc_ctx_set_output_planes(scgrhc_ctx* ctx, int64_t plane_stride);
 
 /* The same for a chunk of n_rec records back to back, each with its own calibration (one launch per chunk instead of one
  * per record): rec_row0 (n_rec+1, device) = first frame of every record inside d / out; gain, baseline (n_rec, ncols)

@@ -14,6 +14,7 @@
 #include "filter_kernels.cuh"
 #include "filter_scan_kernel.cuh"
 #include "window_kernel.cuh"
+#include "window_planar_kernel.cuh"
 #include "subset_kernel.cuh"
 
 using namespace scgrhc;
@@ -24,6 +25,7 @@ struct scgrhc_ctx {
   int ctas_per_sm = 0;  // 0 = from occupancy
   int stages = 0;       // 0 = default
   unsigned long long* err_dev = nullptr;  // 3 words: flags, first bad candidate, ambiguous windows
+  long long out_plane = 0;                // scgrhc_ctx_set_output_planes
   long long last_ambiguous = 0;           // word 2 as read by the last scgrhc_check_errors
   int* block_counts = nullptr;
   long long* block_offsets = nullptr;
@@ -103,6 +105,13 @@ extern "C" int scgrhc_ctx_set_tuning(scgrhc_ctx* ctx, int ctas_per_sm, int stage
     return fail(ctx, SCGRHC_ERR_BAD_ARG, "tuning out of range: ctas_per_sm=%d stages=%d", ctas_per_sm, stages);
   ctx->ctas_per_sm = ctas_per_sm;
   ctx->stages = stages;
+  return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_ctx_set_output_planes(scgrhc_ctx* ctx, int64_t plane_stride) {
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (plane_stride < 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "plane_stride must be >= 0");
+  ctx->out_plane = plane_stride;
   return SCGRHC_OK;
 }
 
@@ -228,6 +237,33 @@ static int dispatch_nsig(scgrhc_ctx* ctx, const KParams& P, long long items, cud
   return dispatch_out<C, false, false>(ctx, P, items, st);
 }
 
+template <int C, int NTH, int PR, typename OutT, int WCT>
+static int launch_planar(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
+  auto kern = window_planar_kernel<C, NTH, PR, OutT, WCT>;
+  const size_t smem = ((sizeof(PScratch<NTH>) + 127) & ~size_t(127)) + (size_t)(2 + 2 * C) * P.stage_elems * sizeof(double);
+  CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTH, smem));
+  if (occ < 1) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "planar window of %d samples x %d channels does not fit in shared memory (%zu B/CTA)", P.job.W, C, smem);
+  if (ctx->ctas_per_sm > 0) occ = std::min(occ, ctx->ctas_per_sm);
+  const long long grid = std::min<long long>(items, (long long)ctx->sm_count * occ);
+  kern<<<(unsigned)grid, NTH, smem, st>>>(P);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+template <int C, typename OutT>
+static int dispatch_planar_w(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
+  if (P.job.W == 750) return launch_planar<C, 128, 3, OutT, 750>(ctx, P, items, st);   // int(1.5 * 500): all 37 configs
+  if (P.job.W <= 384) return launch_planar<C, 64, 3, OutT, 0>(ctx, P, items, st);      // resampled cohorts: 375 samples, 2 warps per window
+  if (P.job.W <= 768) return launch_planar<C, 128, 3, OutT, 0>(ctx, P, items, st);
+  return launch_planar<C, 128, 4, OutT, 0>(ctx, P, items, st);
+}
+template <int C>
+static int dispatch_planar(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
+  if (P.job.flags & SCGRHC_OUT_F64) return dispatch_planar_w<C, double>(ctx, P, items, st);
+  return dispatch_planar_w<C, float>(ctx, P, items, st);
+}
+
 extern "C" int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, const scgrhc_outputs* out, void* stream) {
   NvtxRange nvtx_range("scgrhc_process_windows");
   if (!ctx) return SCGRHC_ERR_BAD_ARG;
@@ -270,6 +306,18 @@ extern "C" int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, co
   P.stages = ctx->stages > 0 ? ctx->stages : 2;
   P.stage_elems = (int)(((long long)J.W * J.nsig + J.nsig + 2 + 1) & ~1LL);  // + one padded row (next-row loads) + lead
   P.arena_elems_cap = J.arena_capacity_bytes / 8;
+  if (J.flags & SCGRHC_ARENA_PLANAR) {
+    if (J.flags & SCGRHC_NORM_ZSCORE) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "ARENA_PLANAR is not combinable with NORM_ZSCORE");
+    if ((reinterpret_cast<uintptr_t>(out->scg_out) & 7) || (reinterpret_cast<uintptr_t>(out->rhc_out) & 7))
+      return fail(ctx, SCGRHC_ERR_BAD_ARG, "scg_out/rhc_out must be 8-byte aligned");
+    P.stage_elems = (J.W + 3 + 1) & ~1;    // lead + window + the next-sample pad, even: plane buffers stay 16-byte aligned
+    switch (J.C) {
+      case 1: return dispatch_planar<1>(ctx, P, items, st);
+      case 2: return dispatch_planar<2>(ctx, P, items, st);
+      case 3: return dispatch_planar<3>(ctx, P, items, st);
+      default: return dispatch_planar<4>(ctx, P, items, st);
+    }
+  }
   switch (J.C) {
     case 1: return dispatch_nsig<1>(ctx, P, items, st);
     case 2: return dispatch_nsig<2>(ctx, P, items, st);
@@ -756,7 +804,8 @@ extern "C" int scgrhc_decode_fmt16(scgrhc_ctx* ctx, const int16_t* d, int64_t T,
   if (T < 0 || nsig_in < 1 || ncols < 1 || ncols > SCGRHC_MAX_C + 1 || !cols || !gain || !baseline || (T && (!d || !out)))
     return fail(ctx, SCGRHC_ERR_BAD_ARG, "decode_fmt16: bad arguments (1..%d output columns)", SCGRHC_MAX_C + 1);
   DecodeParams P;
-  P.d = d; P.out = out; P.T = T; P.nsig_in = nsig_in; P.ncols = ncols;
+  P.d = d; P.out = out; P.T = T; P.nsig_in = nsig_in; P.ncols = ncols; P.plane = ctx->out_plane;
+  if (P.plane && P.plane < T) return fail(ctx, SCGRHC_ERR_BAD_ARG, "decode_fmt16: output plane stride %lld < %lld rows", (long long)P.plane, (long long)T);
   for (int j = 0; j < ncols; ++j) {
     if (cols[j] < 0 || cols[j] >= nsig_in) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "decode_fmt16: column %d outside 0..%d", cols[j], nsig_in - 1);
     if (gain[j] == 0.0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "decode_fmt16: zero gain");
@@ -799,7 +848,7 @@ extern "C" int scgrhc_decode_fmt16_records(scgrhc_ctx* ctx, const int16_t* d, co
   if (n_rec > 65535) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "decode_fmt16_records: at most 65535 records per call");
   DecodeRecParams P;
   P.d = d; P.out = out; P.rec_row0 = reinterpret_cast<const long long*>(rec_row0_dev); P.gain = gain_dev; P.baseline = baseline_dev;
-  P.n_rec = n_rec; P.nsig_in = nsig_in; P.ncols = ncols; P.recip = recip ? 1 : 0;
+  P.n_rec = n_rec; P.nsig_in = nsig_in; P.ncols = ncols; P.recip = recip ? 1 : 0; P.plane = ctx->out_plane;
   for (int j = 0; j < ncols; ++j) {
     if (cols[j] < 0 || cols[j] >= nsig_in) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "decode_fmt16_records: column %d outside 0..%d", cols[j], nsig_in - 1);
     P.cols[j] = cols[j];
@@ -845,6 +894,8 @@ extern "C" int scgrhc_synth_records(scgrhc_ctx* ctx, uint64_t seed, int64_t rec0
   P.seed = seed; P.rec0 = rec0; P.n_rec = n_rec; P.T = T; P.nsig = nsig; P.defect_scale = defect_scale; P.grid = grid;
   for (int i = 0; i < SCGRHC_MAX_NSIG; ++i) P.kinds[i] = i < nsig ? kinds[i] : 0;
   P.out = out;
+  P.plane = ctx->out_plane;
+  if (P.plane && P.plane < n_rec * T) return fail(ctx, SCGRHC_ERR_BAD_ARG, "synth: output plane stride smaller than the cohort");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const long long total = n_rec * T * nsig;

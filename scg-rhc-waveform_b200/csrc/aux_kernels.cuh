@@ -176,6 +176,7 @@ struct DecodeParams {
   const short* d;          // (T, nsig_in) interleaved frames
   double* out;             // (T, ncols)
   long long T;
+  long long plane;         // 0: out is interleaved (T, ncols); P > 0: column j of row t at out[j * P + t]
   int nsig_in, ncols;
   int cols[SCGRHC_MAX_C + 1];
   double gain[SCGRHC_MAX_C + 1], baseline[SCGRHC_MAX_C + 1];
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(256) decode_fmt16_kernel(const __grid_constant
     const int j = (int)(e - t * P.ncols);
     const short d = P.d[t * P.nsig_in + P.cols[j]];
     const double v = __ddiv_rn(__dsub_rn((double)d, P.baseline[j]), P.gain[j]);
-    P.out[e] = d == -32768 ? __longlong_as_double(0x7ff8000000000000LL) : v;
+    P.out[P.plane ? j * P.plane + t : e] = d == -32768 ? __longlong_as_double(0x7ff8000000000000LL) : v;
   }
 }
 
@@ -223,6 +224,11 @@ __global__ void __launch_bounds__(256) decode_fmt16_rows_kernel(const __grid_con
       const double q = div_by_recip(__dsub_rn((double)dv[j], P.baseline[j]), P.gain[j], inv[j]);
       v[j] = dv[j] == -32768 ? qnan : q;
     }
+    if (P.plane) {                     // planar arena: consecutive threads write consecutive rows of each plane
+#pragma unroll
+      for (int j = 0; j < NC; ++j) __stcs(P.out + j * P.plane + t, v[j]);
+      continue;
+    }
     double* o = P.out + t * NC;
     if constexpr (NC % 2 == 0) {
 #pragma unroll
@@ -244,6 +250,7 @@ struct DecodeRecParams {
   const long long* rec_row0; // device (n_rec + 1)
   const double* gain;        // device (n_rec, ncols)
   const double* baseline;    // device (n_rec, ncols)
+  long long plane;           // 0: interleaved output; P > 0: planar, column j of row t at out[j * P + t]
   int n_rec, nsig_in, ncols, recip;
   int cols[SCGRHC_MAX_C + 1];
 };
@@ -281,6 +288,11 @@ __global__ void __launch_bounds__(256) decode_fmt16_records_kernel(const __grid_
       const double a = __dsub_rn((double)dv[j], b[j]);
       const double q = P.recip ? div_by_recip(a, g[j], inv[j]) : __ddiv_rn(a, g[j]);
       v[j] = dv[j] == -32768 ? qnan : q;
+    }
+    if (P.plane) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) __stcs(P.out + j * P.plane + t, v[j]);
+      continue;
     }
     double* o = P.out + t * NC;
     if (NC % 2 == 0 && out16) {
@@ -521,6 +533,7 @@ struct SynthParams {
   int nsig, defect_scale, grid;
   int kinds[SCGRHC_MAX_NSIG];
   double* out;
+  long long plane;           // 0: interleaved (rows, nsig); P > 0: planar, column ch of row r at out[ch * P + r]
 };
 
 __device__ __forceinline__ unsigned long long syn_h(unsigned long long key, unsigned stream, unsigned long long idx) {
@@ -603,7 +616,7 @@ __global__ void __launch_bounds__(256) synth_kernel(const __grid_constant__ Synt
     const long long t = row - rec * P.T;
     const unsigned long long key = mix64(mix64(P.seed) ^ ((unsigned long long)(P.rec0 + rec) * 0xD1342543DE82EF95ull));
     const unsigned long long finc = 7730941ull + syn_h(key, 0, 0) % 7730942ull;
-    P.out[e] = syn_channel(key, finc, P.kinds[ch], t, P.defect_scale, P.grid);
+    P.out[P.plane ? ch * P.plane + row : e] = syn_channel(key, finc, P.kinds[ch], t, P.defect_scale, P.grid);
   }
 }
 

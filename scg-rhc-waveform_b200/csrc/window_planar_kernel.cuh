@@ -1,0 +1,535 @@
+// The hot-path kernel for PLANAR arenas (SCGRHC_ARENA_PLANAR): column c of arena row r lives at arena[c * arena_rows + r].
+//
+// Same arithmetic and the same bit-exact contract as window_kernel.cuh (which reads wfdb's interleaved (rows, nsig)
+// layout); what changes is the data movement the layout allows:
+//   * a candidate window is first judged on its RHC plane alone — ONE contiguous 6,000-byte bulk copy
+//     (has_noise() looks at the RHC channel only, waveform_noise.py:44-49) — and the C SCG planes are fetched only if it is
+//     kept: a rejected window costs 6 KB of DRAM traffic instead of the 24 KB the interleaved rows drag in by sector;
+//   * every thread owns PAIRS of consecutive samples: 16-byte shared loads without bank conflicts, 8-byte global stores
+//     (two fp32 outputs), no column selects and no transposition — the output (C, W) layout IS planar.
+//
+// Software pipeline per CTA (one candidate per iteration j, one __syncthreads per iteration):
+//   phase A, item a = lo + j      RHC window (bulk copy issued two iterations earlier) -> registers -> predicates ->
+//                                 keep / reject -> RHC normalised and stored; if kept, the SCG bulk copies are issued
+//   phase B, item b = lo + j - 2  its SCG planes have landed -> registers -> joint min/max -> normalise -> store
+// Both phases put their per-warp partials into one shared exchange before the barrier of the iteration.
+#pragma once
+#include "window_kernel.cuh"
+
+namespace scgrhc {
+
+constexpr int PNRED = 12;   // phase A: -ymin, ymax | s1, s2, sxy, dense ; phase B: -smin, smax | nan accumulator
+
+struct PMeta {
+  long long cand;   // candidate index
+  long long slot;   // output slot
+  long long row;    // first arena row of the window
+  int win, rec;
+  int fallback;     // bulk copy not possible (capacity edge): cooperative plain loads
+  int pad;
+};
+
+template <int NTH>
+struct PScratch {
+  uint64_t rfull[2], sfull[2];
+  PMeta rmeta[2];                       // item whose RHC window sits in RHC slot s
+  PMeta bmeta[2];                       // kept item whose SCG planes sit (or are landing) in SCG slot s
+  int bkeep[2];                         // 0: nothing for phase B in this slot; 1: kept, bulk copies issued; 2: kept, plain loads
+  double red[2][NTH / 32][PNRED];
+  uint32_t cmask[2][8 * (NTH / 32)];
+  uint32_t a24[8 * (NTH / 32)];
+  int slow_cnt;
+};
+
+// Window of W samples; NTH threads; every thread owns PR pairs (samples 2p, 2p+1 for p = tid + k*NTH): W <= 2*PR*NTH.
+// WCT > 0: compile-time window length (750 = int(1.5 * 500), all 37 configs): pair validity folds away; 0: runtime length.
+template <int C, int NTH, int PR, typename OutT, int WCT>
+__global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(const __grid_constant__ KParams P) {
+  static_assert(WCT == 0 || (WCT + 1) / 2 <= PR * NTH, "window does not fit the pair grid");
+  static_assert(SCGRHC_FLAT_WIN == 50, "run detection below is hard-wired to 24 full pairs inside 49 small steps");
+  constexpr int NW = NTH / 32;
+  constexpr int NWORDS = PR * NW;
+  static_assert(NWORDS <= 32, "one mask word per lane");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  PScratch<NTH>& S = *reinterpret_cast<PScratch<NTH>*>(smem_raw);
+  double* const rbase = reinterpret_cast<double*>(smem_raw + ((sizeof(PScratch<NTH>) + 127) & ~size_t(127)));
+  const int wpad = P.stage_elems;                      // doubles per plane window in shared memory (even, >= W + 3)
+  double* const sbase = rbase + 2 * wpad;
+
+  const scgrhc_job& J = P.job;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W = WCT > 0 ? WCT : J.W;
+  const long long rows = J.arena_rows;
+  const int wstride = J.stride > 0 ? J.stride : W;
+  const bool use_list = (J.flags & SCGRHC_USE_KEPT_LIST) != 0;
+  const bool pred_only = (J.flags & SCGRHC_PREDICATES_ONLY) != 0;
+  const bool norm_global = (J.flags & SCGRHC_NORM_GLOBAL) != 0;
+  const bool keep_all = (J.flags & SCGRHC_KEEP_ALL) != 0;
+  const double thr = J.flat_threshold, min_rhc = J.min_rhc;
+  const double* const yplane = J.arena + (long long)J.rhc_col * rows;
+  const double* xplane[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) xplane[c] = J.arena + (long long)J.scg_cols[c] * rows;
+
+  const long long items = use_list ? J.n_items : J.n_cand;
+  const long long lo = items * (long long)blockIdx.x / gridDim.x;
+  const long long hi = items * (long long)(blockIdx.x + 1) / gridDim.x;
+  if (lo >= hi) return;
+  const long long cnt = hi - lo;
+
+  if (tid == 0) {
+    mbar_init(&S.rfull[0], 1); mbar_init(&S.rfull[1], 1);
+    mbar_init(&S.sfull[0], 1); mbar_init(&S.sfull[1], 1);
+    S.slow_cnt = 0;
+    S.bkeep[0] = 0; S.bkeep[1] = 0;
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  // ---- producer state (thread 0 only) -----------------------------------------------------------
+  int p_iv = 0;
+  long long p_cand0 = 0, p_row0 = 0;
+  int p_nwin = 0, p_rec = 0;
+  auto load_iv = [&](int iv) {
+    const scgrhc_interval I = J.intervals[iv];
+    p_cand0 = I.cand0; p_row0 = I.row0; p_nwin = I.n_win; p_rec = I.rec_id;
+  };
+  // one plane window -> shared memory: 16-byte aligned start (the element before when the offset is odd), even length
+  auto plane_bytes = [&](long long e0) { return (uint32_t)((((long long)W + (e0 & 1) + 1) & ~1LL) * 8); };
+  auto plane_ok = [&](long long e0) { return (e0 - (e0 & 1)) * 8 + plane_bytes(e0) <= (unsigned long long)J.arena_capacity_bytes; };
+  auto issue_rhc = [&](long long item, int s) {
+    const long long cand = use_list ? J.kept_list[item] : item;
+    while (cand >= p_cand0 + p_nwin) load_iv(++p_iv);
+    const int i = (int)(cand - p_cand0);
+    PMeta m;
+    m.cand = cand; m.slot = use_list ? item : cand; m.row = p_row0 + (long long)i * wstride; m.win = i; m.rec = p_rec; m.pad = 0;
+    const long long e0 = (long long)J.rhc_col * rows + m.row;
+    m.fallback = plane_ok(e0) ? 0 : 1;
+    S.rmeta[s] = m;
+    if (m.fallback) {
+      mbar_arrive(&S.rfull[s]);
+    } else {
+      const uint32_t bytes = plane_bytes(e0);
+      mbar_arrive_expect_tx(&S.rfull[s], bytes);
+      bulk_g2s(rbase + (size_t)s * wpad, J.arena + (e0 - (e0 & 1)), bytes, &S.rfull[s]);
+    }
+  };
+  auto issue_scg = [&](const PMeta& m, int s) {      // returns through S.bkeep[s]: 1 = bulk copies in flight, 2 = plain loads
+    bool ok = true;
+    uint32_t total = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const long long e0 = (long long)J.scg_cols[c] * rows + m.row;
+      ok = ok && plane_ok(e0);
+      total += plane_bytes(e0);
+    }
+    S.bmeta[s] = m;
+    if (!ok) { S.bkeep[s] = 2; return; }
+    S.bkeep[s] = 1;
+    mbar_arrive_expect_tx(&S.sfull[s], total);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const long long e0 = (long long)J.scg_cols[c] * rows + m.row;
+      bulk_g2s(sbase + ((size_t)s * C + c) * wpad, J.arena + (e0 - (e0 & 1)), plane_bytes(e0), &S.sfull[s]);
+    }
+  };
+  if (tid == 0) {
+    const long long first = use_list ? J.kept_list[lo] : lo;
+    int a = 0, b = J.n_intervals - 1;  // last interval with cand0 <= first
+    while (a < b) {
+      const int mid = (a + b + 1) >> 1;
+      if (J.intervals[mid].cand0 <= first) a = mid; else b = mid - 1;
+    }
+    p_iv = a;
+    load_iv(a);
+    issue_rhc(lo, 0);
+    if (cnt > 1) issue_rhc(lo + 1, 1);
+  }
+
+  const double xbar = 0.5 * (double)(W - 1);
+  const double sxx = (double)W * ((double)W * (double)W - 1.0) / 12.0;  // sum (t - xbar)^2, exact here
+  const double tx = (double)(2 * tid) - xbar;
+  const double inv_w = 1.0 / (double)W;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  const int npairs = (W + 1) >> 1;
+  // pair p = tid + k*NTH exists / has its second sample: compile-time for all but the last k when the length is known
+  auto pair_ok = [&](int k, int p) { return WCT > 0 ? ((k + 1) * NTH <= (WCT + 1) / 2 || p < (WCT + 1) / 2) : (p < npairs); };
+  auto has_second = [&](int k, int p) { return WCT > 0 ? (WCT % 2 == 0 || (k + 1) * NTH <= WCT / 2 || 2 * p + 1 < WCT) : (2 * p + 1 < W); };
+  auto has_third = [&](int k, int p) { return WCT > 0 ? ((k + 1) * NTH < (WCT + 1) / 2 - (WCT % 2) || 2 * p + 2 < WCT) : (2 * p + 2 < W); };
+  int ppar[C];                                    // parity of the plane base c * rows: lead = (ppar ^ row) & 1
+#pragma unroll
+  for (int c = 0; c < C; ++c) ppar[c] = (int)(((long long)J.scg_cols[c] * rows) & 1);
+  const int ypar = (int)(((long long)J.rhc_col * rows) & 1);
+
+  uint32_t rpar[2] = {0u, 0u}, spar[2] = {0u, 0u};
+  for (long long j = 0; j < cnt + 2; ++j) {
+    const int s = (int)(j & 1);
+    const bool doA = j < cnt;
+    const int bstate = (j >= 2) ? S.bkeep[s] : 0;      // written by thread 0 two iterations ago, before that iteration's end barrier
+    const bool doB = bstate != 0;
+
+    // ================= phase A, before the barrier: RHC window -> registers, per-thread statistics ==================
+    PMeta MA;
+    double y0[PR], y1[PR];
+    double K = 0.0;
+    if (doA) {
+      mbar_wait(&S.rfull[s], rpar[s]);
+      rpar[s] ^= 1u;
+      MA = S.rmeta[s];
+      double* buf = rbase + (size_t)s * wpad;
+      const int lead = (ypar ^ (int)MA.row) & 1;
+      if (MA.fallback) {
+        for (int e = tid; e < W; e += NTH) buf[lead + e] = yplane[MA.row + e];
+        __syncthreads();
+      }
+      const double* win = buf + lead;
+      K = win[0];
+      double a_ymin = CUDART_INF, a_ymax = -CUDART_INF, s1 = 0.0, s2 = 0.0, sB = 0.0, sC = 0.0;
+      bool dense_word = false;
+#pragma unroll
+      for (int k = 0; k < PR; ++k) {
+        const int p = tid + k * NTH;
+        const int i0 = 2 * p;
+        y0[k] = 0.0; y1[k] = 0.0;
+        bool full = false;
+        if (pair_ok(k, p)) {
+          const bool has1 = has_second(k, p);
+          double v0, v1, v2;
+          if (lead == 0) {               // CTA-uniform: 16-byte loads when the window starts on an even element
+            const double2 q = *reinterpret_cast<const double2*>(win + i0);
+            v0 = q.x; v1 = q.y;
+          } else {
+            v0 = win[i0]; v1 = win[i0 + 1];
+          }
+          v2 = win[i0 + 2];              // first sample of the next pair (the buffer is padded past the window)
+          y0[k] = v0; y1[k] = v1;
+          a_ymin = v0 < a_ymin ? v0 : a_ymin;
+          a_ymax = v0 > a_ymax ? v0 : a_ymax;
+          const double d0 = __dsub_rn(v0, K);
+          s1 = __dadd_rn(s1, d0);
+          s2 = __fma_rn(d0, d0, s2);
+          double dd = d0;
+          bool c0 = false, c1 = false;
+          if (has1) {
+            a_ymin = v1 < a_ymin ? v1 : a_ymin;
+            a_ymax = v1 > a_ymax ? v1 : a_ymax;
+            const double d1 = __dsub_rn(v1, K);
+            s1 = __dadd_rn(s1, d1);
+            s2 = __fma_rn(d1, d1, s2);
+            sC = __dadd_rn(sC, d1);
+            dd = __dadd_rn(d0, d1);
+            // c[i] = fl(|y[i+1] - y[i]|) < thr: necessary for any flat 50-window covering (i, i+1)
+            c0 = fabs(__dsub_rn(v1, v0)) < thr;
+            c1 = has_third(k, p) && (fabs(__dsub_rn(v2, v1)) < thr);
+          }
+          sB = __fma_rn((double)k, dd, sB);
+          full = c0 && c1;
+        }
+        const uint32_t word = __ballot_sync(kFull, full);
+        if (lane == 0) S.cmask[s][k * NW + warp] = word;
+        // 49 consecutive small steps contain 24 consecutive full pairs, which span at most 2 mask words
+        dense_word |= __popc(word) >= 12;
+      }
+      // sum_i (i - xbar) dy_i over this thread's samples i = 2(tid + NTH k) + b
+      double sxy = __fma_rn(tx, s1, __fma_rn((double)(2 * NTH), sB, sC));
+      a_ymin = warp_min(a_ymin); a_ymax = warp_max(a_ymax);
+      s1 = warp_sum(s1); s2 = warp_sum(s2); sxy = warp_sum(sxy);
+      if (lane == 0) {
+        double* r = S.red[s][warp];
+        r[0] = -a_ymin; r[1] = a_ymax; r[4] = s1; r[5] = s2; r[6] = sxy; r[7] = dense_word ? 1.0 : 0.0;
+      }
+    }
+
+    // ================= phase B, before the barrier: SCG planes -> registers, joint min/max ==========================
+    PMeta MB;
+    double x0[PR][C], x1[PR][C];
+    if (doB) {
+      MB = S.bmeta[s];
+      double* buf = sbase + (size_t)s * C * wpad;
+      if (bstate == 1) {
+        mbar_wait(&S.sfull[s], spar[s]);
+        spar[s] ^= 1u;
+      } else {                                   // capacity edge: plain loads
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int lead = (ppar[c] ^ (int)MB.row) & 1;
+          for (int e = tid; e < W; e += NTH) buf[(size_t)c * wpad + lead + e] = xplane[c][MB.row + e];
+        }
+        __syncthreads();
+      }
+      double a_smin = CUDART_INF, a_smax = -CUDART_INF, nanacc = 0.0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int lead = (ppar[c] ^ (int)MB.row) & 1;
+        const double* win = buf + (size_t)c * wpad + lead;
+#pragma unroll
+        for (int k = 0; k < PR; ++k) {
+          const int p = tid + k * NTH;
+          const int i0 = 2 * p;
+          x0[k][c] = 0.0; x1[k][c] = 0.0;
+          if (pair_ok(k, p)) {
+            double v0, v1;
+            if (lead == 0) {
+              const double2 q = *reinterpret_cast<const double2*>(win + i0);
+              v0 = q.x; v1 = q.y;
+            } else {
+              v0 = win[i0]; v1 = win[i0 + 1];
+            }
+            x0[k][c] = v0; x1[k][c] = v1;
+            a_smin = v0 < a_smin ? v0 : a_smin;
+            a_smax = v0 > a_smax ? v0 : a_smax;
+            nanacc = __fma_rn(v0, 0.0, nanacc);   // NaN iff some v is NaN or Inf
+            if (has_second(k, p)) {
+              a_smin = v1 < a_smin ? v1 : a_smin;
+              a_smax = v1 > a_smax ? v1 : a_smax;
+              nanacc = __fma_rn(v1, 0.0, nanacc);
+            }
+          }
+        }
+      }
+      a_smin = warp_min(a_smin); a_smax = warp_max(a_smax); nanacc = warp_sum(nanacc);
+      if (lane == 0) {
+        double* r = S.red[s][warp];
+        r[2] = -a_smin; r[3] = a_smax; r[8] = nanacc;
+      }
+    }
+    __syncthreads();  // the barrier of the iteration: partials visible, RHC slot s and SCG slot s are in registers
+
+    // ---- block combine, lane parallel: lane v folds slot v over the warps, results broadcast ---------------------------
+    double ymin, ymax, smin, smax, s1, s2, sxy, dense, nanB;
+    {
+      const int v = lane < PNRED ? lane : 0;
+      double a = S.red[s][0][v];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) {
+        const double b = S.red[s][w][v];
+        const double mx = b > a ? b : a;
+        const double sm = __dadd_rn(a, b);
+        a = v < 4 ? mx : sm;
+      }
+      ymin = -__shfl_sync(kFull, a, 0); ymax = __shfl_sync(kFull, a, 1);
+      smin = -__shfl_sync(kFull, a, 2); smax = __shfl_sync(kFull, a, 3);
+      s1 = __shfl_sync(kFull, a, 4); s2 = __shfl_sync(kFull, a, 5); sxy = __shfl_sync(kFull, a, 6);
+      dense = __shfl_sync(kFull, a, 7); nanB = __shfl_sync(kFull, a, 8);
+    }
+
+    // ================= phase A, after the barrier: decide, publish, normalise the RHC window ============================
+    if (doA) {
+      uint32_t reason = 0;
+      bool keep = true;
+      if (!use_list) {
+        uint32_t a24 = 0u;
+        bool run = false;
+        if (dense != 0.0) {
+          const uint32_t a1 = lane < NWORDS ? S.cmask[s][lane] : 0u;
+          auto down = [&](uint32_t v, int d) {  // word (lane + d) of the mask, 0 past the end
+            const uint32_t o = __shfl_down_sync(kFull, v, d);
+            return (lane + d < 32) ? o : 0u;
+          };
+          auto shr = [&](uint32_t v, int sft) { return __funnelshift_r(v, down(v, 1), sft); };
+          const uint32_t a2 = a1 & shr(a1, 1);
+          const uint32_t a4 = a2 & shr(a2, 2);
+          const uint32_t a8 = a4 & shr(a4, 4);
+          const uint32_t a16 = a8 & shr(a8, 8);
+          a24 = a16 & shr(a8, 16);          // bit p: pairs p .. p+23 are all full
+          run = __any_sync(kFull, a24 != 0u);
+        }
+        const bool s2_bad = !(s2 <= DBL_MAX);   // non-finite RHC sample, or the sum of squares overflowed: recheck exactly
+        int flat_cnt = 0;
+        bool nonfinite = false;
+        if (run || s2_bad) {                    // CTA-uniform and rare: exact work on the RHC window still in shared memory
+          if (warp == 0 && lane < NWORDS) S.a24[lane] = a24;
+          __syncthreads();
+          const double* win = rbase + (size_t)s * wpad + ((ypar ^ (int)MA.row) & 1);
+          int c = 0, fl = 0;
+          if (run) {
+            for (int k = 0; k < PR; ++k) {
+              const int p = tid + k * NTH;
+              if (pair_ok(k, p) && ((S.a24[p >> 5] >> (p & 31)) & 1u)) {
+                for (int q = 2 * p - 1; q <= 2 * p; ++q) {      // a flat 50-window can start at the pair or one sample before it
+                  if (q < 0 || q + SCGRHC_FLAT_WIN > W) continue;
+                  double mx = -CUDART_INF, mn = CUDART_INF;
+                  for (int i = 0; i < SCGRHC_FLAT_WIN; ++i) {
+                    const double v = win[q + i];
+                    mx = v > mx ? v : mx; mn = v < mn ? v : mn;
+                  }
+                  c += (__dsub_rn(mx, mn) < thr) ? 1 : 0;
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < PR; ++k) {
+            const int p = tid + k * NTH;
+            if (pair_ok(k, p)) {
+              if (!(fabs(y0[k]) <= DBL_MAX)) fl = 1;
+              if (has_second(k, p) && !(fabs(y1[k]) <= DBL_MAX)) fl = 1;
+            }
+          }
+          if (c) atomicAdd(&S.slow_cnt, c);
+          nonfinite = __syncthreads_or(fl) != 0;
+          flat_cnt = S.slow_cnt;
+          __syncthreads();
+          if (tid == 0) S.slow_cnt = 0;
+        }
+        // Syy = sum (y-K)^2 - (sum (y-K))^2 / n ; Sxy is shift invariant because sum (t - xbar) = 0.
+        // R^2 > 0.8  <=>  Sxy^2 > 0.8 Sxx Syy (Syy > 0): no division; see window_kernel.cuh for the ambiguity band.
+        const double syy = __dsub_rn(s2, __dmul_rn(__dmul_rn(s1, s1), inv_w));
+        const double lhs = __dmul_rn(sxy, sxy), den = __dmul_rn(sxx, syy);
+        if (flat_cnt >= 2) reason |= SCGRHC_REASON_FLAT;
+        if (syy > 0.0 && lhs > __dmul_rn(0.8, den)) reason |= SCGRHC_REASON_STRAIGHT;
+        if (syy > 0.0 && fabs(__fma_rn(-0.8, den, lhs)) < __dmul_rn(1e-9, den)) reason |= SCGRHC_REASON_AMBIGUOUS;
+        if (ymin == ymax && !nonfinite && np_mean_of_const_is_exact(ymin, W)) reason |= SCGRHC_REASON_STRAIGHT;
+        if (ymin < min_rhc) reason |= SCGRHC_REASON_FLOOR;
+        if (nonfinite) reason |= SCGRHC_REASON_NONFINITE;
+        keep = keep_all ||
+               (reason & (SCGRHC_REASON_FLAT | SCGRHC_REASON_STRAIGHT | SCGRHC_REASON_FLOOR | SCGRHC_REASON_NONFINITE)) == 0;
+        if (tid == 0) {
+          P.out.keep[MA.cand] = keep ? 1 : 0;
+          P.out.reason[MA.cand] = (uint8_t)reason;
+          double2* mm = reinterpret_cast<double2*>(P.out.minmax + 4 * MA.cand);
+          if (!keep) mm[0] = make_double2(qnan, qnan);   // the SCG planes of a rejected window are never read
+          mm[1] = make_double2(ymin, ymax);
+          P.out.cand_win[MA.cand] = MA.win;
+          P.out.cand_rec[MA.cand] = MA.rec;
+          if (!keep_all && (reason & SCGRHC_REASON_NONFINITE) && !(reason & SCGRHC_REASON_FLAT)) {
+            atomicOr(P.err, 1ull);
+            atomicMin(P.err + 1, (unsigned long long)MA.cand);
+          }
+          if (reason & SCGRHC_REASON_AMBIGUOUS) atomicAdd(P.err + 2, 1ull);
+        }
+      } else if (!norm_global) {   // dense re-materialisation with the per-window pairs of an earlier pass
+        const double2 b = reinterpret_cast<const double2*>(P.out.minmax + 4 * MA.cand)[1];
+        ymin = b.x; ymax = b.y;
+      }
+      if (tid == 0) {
+        if (keep) issue_scg(MA, s); else S.bkeep[s] = 0;
+        if (j + 2 < cnt) issue_rhc(lo + j + 2, s);        // RHC slot s is in registers everywhere: refill it
+      }
+      if (keep && !pred_only) {
+        if (norm_global) { ymin = J.global_minmax[2]; ymax = J.global_minmax[3]; }
+        Normaliser nr;
+        nr.init(ymin, ymax);
+        OutT* ro = reinterpret_cast<OutT*>(P.out.rhc_out) + (size_t)MA.slot * W;
+        const bool vec = (WCT > 0 && WCT % 2 == 0) || (((size_t)MA.slot * W) & 1) == 0;     // 8-byte aligned pair stores
+        bool redo = true;
+        if constexpr (sizeof(OutT) == 4) {
+          if (!use_list && !norm_global && nr.quick) {         // tier 1, see window_kernel.cuh
+            uint32_t acc = 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < PR; ++k) {
+              const int p = tid + k * NTH;
+              if (pair_ok(k, p)) {
+                const double q0 = __dmul_rn(__dsub_rn(y0[k], nr.mn), nr.inv), q1 = __dmul_rn(__dsub_rn(y1[k], nr.mn), nr.inv);
+                acc = min(acc, tier1_key(q0));
+                if (has_second(k, p)) {
+                  acc = min(acc, tier1_key(q1));
+                  if (vec) __stcs(reinterpret_cast<float2*>(ro + 2 * p), make_float2(__double2float_rn(q0), __double2float_rn(q1)));
+                  else { st_cs(ro + 2 * p, __double2float_rn(q0)); st_cs(ro + 2 * p + 1, __double2float_rn(q1)); }
+                } else {
+                  st_cs(ro + 2 * p, __double2float_rn(q0));
+                }
+              }
+            }
+            redo = acc <= kTier1Risky;
+          }
+        }
+        if (redo) {
+#pragma unroll 1
+          for (int k = 0; k < PR; ++k) {
+            const int p = tid + k * NTH;
+            if (pair_ok(k, p)) {
+              double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+              for (int kk = 0; kk < PR; ++kk) if (kk == k) { v0 = y0[kk]; v1 = y1[kk]; }
+              OutT o;
+              cvt_out(o, nr.slow ? nr.exact(v0) : nr.fast(v0)); st_cs(ro + 2 * p, o);
+              if (has_second(k, p)) { cvt_out(o, nr.slow ? nr.exact(v1) : nr.fast(v1)); st_cs(ro + 2 * p + 1, o); }
+            }
+          }
+        }
+      }
+    } else if (tid == 0) {
+      S.bkeep[s] = 0;                                        // drain iterations: nothing enters the pipeline any more
+    }
+
+    // ================= phase B, after the barrier: normalise the SCG block from registers, store =======================
+    if (doB) {
+      if (!use_list) {
+        if (nanB != nanB) {     // some SCG sample is NaN or Inf (rare, CTA-uniform): np.min / np.max give NaN iff one is NaN
+          int fl = 0;
+#pragma unroll
+          for (int k = 0; k < PR; ++k) {
+            const int p = tid + k * NTH;
+            if (pair_ok(k, p)) {
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                if (x0[k][c] != x0[k][c]) fl = 1;
+                if (has_second(k, p) && x1[k][c] != x1[k][c]) fl = 1;
+              }
+            }
+          }
+          if (__syncthreads_or(fl)) { smin = qnan; smax = qnan; }
+        }
+        if (tid == 0) reinterpret_cast<double2*>(P.out.minmax + 4 * MB.cand)[0] = make_double2(smin, smax);
+      } else if (!norm_global) {
+        const double2 a = reinterpret_cast<const double2*>(P.out.minmax + 4 * MB.cand)[0];
+        smin = a.x; smax = a.y;
+      }
+      if (!pred_only) {
+        if (norm_global) { smin = J.global_minmax[0]; smax = J.global_minmax[1]; }
+        Normaliser ns;
+        ns.init(smin, smax);
+        OutT* so = reinterpret_cast<OutT*>(P.out.scg_out) + (size_t)MB.slot * C * W;
+        bool redo = true;
+        if constexpr (sizeof(OutT) == 4) {
+          if (!use_list && !norm_global && ns.quick) {
+            uint32_t acc = 0xffffffffu;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const bool vec = (WCT > 0 && WCT % 2 == 0) || ((((size_t)MB.slot * C + c) * W) & 1) == 0;
+#pragma unroll
+              for (int k = 0; k < PR; ++k) {
+                const int p = tid + k * NTH;
+                if (pair_ok(k, p)) {
+                  const double q0 = __dmul_rn(__dsub_rn(x0[k][c], ns.mn), ns.inv), q1 = __dmul_rn(__dsub_rn(x1[k][c], ns.mn), ns.inv);
+                  acc = min(acc, tier1_key(q0));
+                  float* o = so + (size_t)c * W + 2 * p;
+                  if (has_second(k, p)) {
+                    acc = min(acc, tier1_key(q1));
+                    if (vec) __stcs(reinterpret_cast<float2*>(o), make_float2(__double2float_rn(q0), __double2float_rn(q1)));
+                    else { st_cs(o, __double2float_rn(q0)); st_cs(o + 1, __double2float_rn(q1)); }
+                  } else {
+                    st_cs(o, __double2float_rn(q0));
+                  }
+                }
+              }
+            }
+            redo = acc <= kTier1Risky;
+          }
+        }
+        if (redo) {   // tiers 2 / 3: exact quotients; out of line (not unrolled) so the common path stays small
+#pragma unroll 1
+          for (int e = 0; e < PR * C; ++e) {
+            const int k = e / C, c = e - k * C;
+            const int p = tid + k * NTH;
+            if (pair_ok(k, p)) {
+              double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+              for (int kk = 0; kk < PR; ++kk) {
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) if (kk == k && cc == c) { v0 = x0[kk][cc]; v1 = x1[kk][cc]; }
+              }
+              OutT o;
+              OutT* dst = so + (size_t)c * W + 2 * p;
+              cvt_out(o, ns.slow ? ns.exact(v0) : ns.fast(v0)); st_cs(dst, o);
+              if (has_second(k, p)) { cvt_out(o, ns.slow ? ns.exact(v1) : ns.fast(v1)); st_cs(dst + 1, o); }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace scgrhc

@@ -13,7 +13,7 @@ OK = 0
 ERR_BAD_ARG, ERR_MISSING_CHANNEL, ERR_NONFINITE_RHC, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6
 
 REASON_FLAT, REASON_STRAIGHT, REASON_FLOOR, REASON_NONFINITE, REASON_AMBIGUOUS = 1, 2, 4, 8, 16
-OUT_F64, PREDICATES_ONLY, USE_KEPT_LIST, NORM_GLOBAL, KEEP_ALL, KEEP_ERRORS, NORM_ZSCORE = 1, 2, 4, 8, 16, 32, 64
+OUT_F64, PREDICATES_ONLY, USE_KEPT_LIST, NORM_GLOBAL, KEEP_ALL, KEEP_ERRORS, NORM_ZSCORE, ARENA_PLANAR = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 class Interval(C.Structure):
@@ -54,7 +54,7 @@ _lib = None
 
 # every symbol include/scgrhc.h declares (tests check the library exports all of them)
 SYMBOLS = ['scgrhc_abi_version', 'scgrhc_ctx_create', 'scgrhc_ctx_destroy', 'scgrhc_last_error',
-           'scgrhc_ctx_set_tuning', 'scgrhc_ctx_sm_count', 'scgrhc_plan_record', 'scgrhc_plan_cohort', 'scgrhc_process_windows',
+           'scgrhc_ctx_set_tuning', 'scgrhc_ctx_set_output_planes', 'scgrhc_ctx_sm_count', 'scgrhc_plan_record', 'scgrhc_plan_cohort', 'scgrhc_process_windows',
            'scgrhc_compact_kept', 'scgrhc_normalize_subsets', 'scgrhc_global_minmax', 'scgrhc_check_errors', 'scgrhc_ambiguous_count', 'scgrhc_gather_windows',
            'scgrhc_window_metrics', 'scgrhc_sosfiltfilt', 'scgrhc_sosfiltfilt_scan', 'scgrhc_resample_poly', 'scgrhc_gather_windows_noise', 'scgrhc_collate_batch', 'scgrhc_philox_words', 'scgrhc_rolling_range_lt', 'scgrhc_decode_fmt16', 'scgrhc_decode_fmt16_records', 'scgrhc_waveform_stats', 'scgrhc_synth_records', 'scgrhc_selftest_div']
 
@@ -78,6 +78,7 @@ def lib():
   L.scgrhc_last_error.restype = C.c_char_p
   L.scgrhc_ctx_set_tuning.argtypes = [vp, C.c_int, C.c_int]
   L.scgrhc_ctx_sm_count.argtypes = [vp]
+  L.scgrhc_ctx_set_output_planes.argtypes = [vp, i64]
   L.scgrhc_plan_record.argtypes = [C.POINTER(dbl), C.POINTER(C.c_uint8), C.c_int, i64, i32, i32, dbl, i64, i32, i64,
                                    C.POINTER(Interval), C.c_int, C.POINTER(C.c_int), C.POINTER(i64),
                                    C.POINTER(i64), C.c_int, C.POINTER(C.c_int)]

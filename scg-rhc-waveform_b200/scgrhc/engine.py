@@ -209,7 +209,7 @@ def resolve_columns(sig_name, in_channels):
 
 def prepare_windows(arena, plan, scg_cols, rhc_col, min_rhc, use_global_min_max=False, out_dtype=torch.float32,
                     predicates_only=False, keep_all=False, flat_threshold=FLAT_THRESHOLD, group=None,
-                    check=True, buffers=None, normalisation='minmax'):
+                    check=True, buffers=None, normalisation='minmax', planar=False):
   """Run the hot path over every candidate window of ``plan``.
 
   Local normalisation (default): ONE fused kernel pass — predicates, min/max, normalise, transpose,
@@ -229,7 +229,7 @@ def prepare_windows(arena, plan, scg_cols, rhc_col, min_rhc, use_global_min_max=
   n, W, Cn = plan.n_cand, plan.W, len(scg_cols)
   iv = plan.device_intervals(dev)
   f64 = out_dtype == torch.float64
-  base_flags = (N.OUT_F64 if f64 else 0) | (N.KEEP_ALL if keep_all else 0) | zflag
+  base_flags = (N.OUT_F64 if f64 else 0) | (N.KEEP_ALL if keep_all else 0) | zflag | (N.ARENA_PLANAR if planar else 0)
   b = buffers if buffers is not None else {}
 
   def buf(name, shape, dtype):
@@ -377,11 +377,12 @@ class SynthSource:
     self.seed, self.T, self.kinds, self.defect_scale, self.grid, self.rec0 = seed, int(T), list(kinds), defect_scale, grid, rec0
 
   def begin(self, ingest):
-    pass
+    self.planar = bool(getattr(ingest, 'planar_run', False))
 
   def enqueue(self, k, chunk, stage):
     r0, r1 = chunk[5], chunk[6]
-    ops.synth_records(stage, self.seed, self.rec0 + r0, r1 - r0, self.T, self.kinds, self.defect_scale, self.grid)
+    ops.synth_records(stage, self.seed, self.rec0 + r0, r1 - r0, self.T, self.kinds, self.defect_scale, self.grid,
+                      plane_stride=(r1 - r0) * self.T if self.planar else 0)
 
   def end(self):
     pass
@@ -456,7 +457,7 @@ class HostIngest:
   (compute stream).  This is the end-to-end path a caller with records outside HBM uses (the reference reads each record
   from disk into host numpy arrays, recordutil.py:137)."""
 
-  def __init__(self, plan, record_rows, nsig, device, chunk_records=64, digital_nsig=None, stages=None):
+  def __init__(self, plan, record_rows, nsig, device, chunk_records=64, digital_nsig=None, stages=None, planar=None):
     """``nsig``: columns of the fp64 arena the window kernel reads.  ``digital_nsig``: the host cohort is WFDB
     format-16 int16 frames with that many signals per frame; they are copied as int16 (4x fewer PCIe bytes than
     fp64 physical samples) and converted on the device (scgrhc_decode_fmt16).
@@ -464,9 +465,20 @@ class HostIngest:
     ``stages`` (extension, default off): the optional per-record stages run on every chunk between the copy and the
     window kernel, so they overlap the next chunk's copy and the cohort never has to be resident:
     ``{'sos': (n, 6) sections, 'filter_cols': [...], 'filter_exact': bool, 'resample': (up, down), 'out_rows': [...]}``;
-    with ``resample`` the plan's rows are rows AFTER resampling (``out_rows`` per record)."""
+    with ``resample`` the plan's rows are rows AFTER resampling (``out_rows`` per record).
+
+    ``planar`` (default off): the fp64 chunk arenas on the device are PLANAR (one plane per signal,
+    csrc/window_planar_kernel.cuh): the device decode (digital cohorts) or generator (SynthSource) writes that layout at
+    no extra cost and a rejected window then costs 6 KB of DRAM traffic instead of 24 KB.  Measured: DRAM
+    traffic drops to the algorithmic bytes, but the two-phase kernel executes ~25 % more instructions per window and the
+    path is issue-bound before it is DRAM-bound, so the interleaved kernel stays the default.  Not for fp64 host cohorts
+    (they arrive interleaved over PCIe) nor with the optional stages (the filters read interleaved rows)."""
     self.plan, self.nsig, self.device = plan, nsig, torch.device(device)
     self.stages = stages or None
+    self.planar = bool(planar)
+    if self.planar and stages:
+      raise ValueError('planar chunk arenas cannot feed the optional filter / resample stages (they read interleaved rows)')
+    self.planar_run = False
     rows = np.asarray(record_rows, dtype=np.int64)
     self.record_rows = rows
     base = np.concatenate([[0], np.cumsum(rows)])
@@ -517,7 +529,7 @@ class HostIngest:
     self._tables = (key,) + t
     return t
 
-  def _stream(self, source, decode, body):
+  def _stream(self, source, decode, body, planar=False):
     """Copy (and, for digital cohorts, decode) chunk after chunk, double buffered, and hand each resident chunk to
     ``body(dst, chunk)`` on the compute stream.  ``source``: a CPU tensor (the whole cohort in host memory) or a chunk
     source (PinnedArenaSource / DiskSource / SynthSource)."""
@@ -533,12 +545,16 @@ class HostIngest:
     per_record = digital and len(decode[1]) and isinstance(decode[1][0], (list, tuple, np.ndarray))
     if per_record:
       gain_t, base_t, recip, offs, longest = self._decode_tables(decode)
+    self.planar_run = bool(planar)
     source.begin(self)
     try:
       for k, chunk in enumerate(self.chunks):
         lo, hi, cand_lo, nc, iv, r0, r1 = chunk
         dst = self.bufs[k & 1][:hi - lo]
+        if planar:                  # (nsig, rows of this chunk): one contiguous plane per signal
+          dst = self.bufs[k & 1].view(-1)[:(hi - lo) * self.nsig].view(self.nsig, hi - lo)
         stage = self.dbufs[k & 1][:hi - lo] if digital else dst
+        plane = (hi - lo) if planar else 0
         with torch.cuda.stream(self.copy_stream):
           if done[k & 1] is not None:
             self.copy_stream.wait_event(done[k & 1])
@@ -548,9 +564,9 @@ class HostIngest:
         compute.wait_event(ready)
         if digital and nc:
           if per_record:       # every record has its own gain / baseline (WFDB headers): device tables, one launch per chunk
-            ops.decode_fmt16_records(stage, offs[k], longest[k], list(decode[0]), gain_t[r0:r1], base_t[r0:r1], recip, dst)
+            ops.decode_fmt16_records(stage, offs[k], longest[k], list(decode[0]), gain_t[r0:r1], base_t[r0:r1], recip, dst, plane)
           else:
-            ops.decode_fmt16(stage, list(decode[0]), [float(v) for v in decode[1]], [float(v) for v in decode[2]], dst)
+            ops.decode_fmt16(stage, list(decode[0]), [float(v) for v in decode[1]], [float(v) for v in decode[2]], dst, plane)
         if nc:
           body(self._run_stages(dst, r0, r1), chunk)
         done[k & 1] = torch.cuda.Event()
@@ -603,7 +619,11 @@ class HostIngest:
     cand_win, cand_rec = buf('cand_win', (n,), torch.int32), buf('cand_rec', (n,), torch.int32)
     kept_idx, start_idx, stop_idx = (buf(k, (n,), torch.int64) for k in ('kept_idx', 'start_idx', 'stop_idx'))
     rec_id, n_kept_t = buf('rec_id', (n,), torch.int32), buf('n_kept', (1,), torch.int64)
-    base_flags = (N.OUT_F64 if out_dtype == torch.float64 else 0) | _norm_flag(normalisation, use_global_min_max)
+    planar = self.planar and normalisation in (None, 'minmax')
+    if planar and self.digital_nsig is None and isinstance(host_arena, (torch.Tensor, PinnedArenaSource)):
+      raise ValueError('planar=True needs a source that writes planes (digital cohort or SynthSource); fp64 host rows are interleaved')
+    base_flags = (N.OUT_F64 if out_dtype == torch.float64 else 0) | _norm_flag(normalisation, use_global_min_max) | \
+        (N.ARENA_PLANAR if planar else 0)
     scg = rhc = None
     ring = None
     if sink is not None:
@@ -630,7 +650,7 @@ class HostIngest:
       if ring is not None and not use_global_min_max:
         sink(k, so[:nc], ro[:nc], {'cand_lo': cand_lo, 'n_cand': nc, 'dense': False, 'keep': keep[cand_lo:cand_lo + nc]})
 
-    self._stream(host_arena, decode, pass_a)
+    self._stream(host_arena, decode, pass_a, planar)
     ops.compact_kept(keep, cand_win, cand_rec, n, W, plan.stride, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
     gmm = None
     if use_global_min_max:
@@ -662,6 +682,6 @@ class HostIngest:
             sink(k, so[:e - a], ro[:e - a], {'cand_lo': cand_lo, 'n_cand': nc, 'dense': True, 'kept_lo': a, 'kept_hi': e})
 
       if n_kept:
-        self._stream(host_arena, decode, pass_b)
+        self._stream(host_arena, decode, pass_b, planar)
     return WindowStore(scg, rhc, minmax, keep, reason, kept_idx[:n_kept], start_idx[:n_kept], stop_idx[:n_kept],
                        rec_id[:n_kept], n_kept, n, bool(use_global_min_max), gmm, n_ambiguous=n_amb)

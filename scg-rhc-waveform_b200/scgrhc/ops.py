@@ -57,6 +57,21 @@ def _ptr(t):
   return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+class _output_planes:
+  """Planar output layout for the next decode / synth call (sticky per context in the C ABI: always reset here)."""
+
+  def __init__(self, c, plane_stride):
+    self.c, self.p = c, int(plane_stride)
+
+  def __enter__(self):
+    if self.p:
+      N.check(self.c, N.lib().scgrhc_ctx_set_output_planes(self.c, self.p))
+
+  def __exit__(self, *exc):
+    if self.p:
+      N.lib().scgrhc_ctx_set_output_planes(self.c, 0)
+
+
 def _contig(t, dtype, name):
   if t is None:
     return
@@ -75,8 +90,9 @@ def process_windows(arena: Tensor, intervals: Tensor, n_cand: int, W: int, strid
   """has_noise + SCGDataset.init_segments fused (recordutil.py:141-148,55-66; waveform_noise.py:6-49)."""
   dev = _dev(arena)
   if arena.dim() != 2:
-    raise ValueError('arena must be (rows, nsig)')
+    raise ValueError('arena must be (rows, nsig), or (nsig, rows) with ARENA_PLANAR')
   _contig(arena, torch.float64, 'arena')
+  planar = bool(flags & N.ARENA_PLANAR)
   _contig(intervals, torch.int64, 'intervals')
   out_dtype = torch.float64 if flags & N.OUT_F64 else torch.float32
   _contig(scg_out, out_dtype, 'scg_out'); _contig(rhc_out, out_dtype, 'rhc_out')
@@ -87,9 +103,9 @@ def process_windows(arena: Tensor, intervals: Tensor, n_cand: int, W: int, strid
     raise N.ScgrhcError(N.ERR_UNSUPPORTED, 'at most %d SCG channels' % N.MAX_C)
   j = N.Job()
   j.arena = arena.data_ptr()
-  j.arena_rows = arena.shape[0]
+  j.arena_rows = arena.shape[1 if planar else 0]
   j.arena_capacity_bytes = arena.numel() * 8
-  j.nsig = arena.shape[1]
+  j.nsig = arena.shape[0 if planar else 1]
   j.W = W
   j.stride = stride
   j.C = len(scg_cols)
@@ -282,7 +298,8 @@ def rolling_range_lt(y: Tensor, m: int, threshold: float, flags: Tensor) -> None
 
 
 @torch.library.custom_op('scgrhc::decode_fmt16', mutates_args=('out',), device_types='cuda')
-def decode_fmt16(d: Tensor, cols: Sequence[int], gain: Sequence[float], baseline: Sequence[float], out: Tensor) -> None:
+def decode_fmt16(d: Tensor, cols: Sequence[int], gain: Sequence[float], baseline: Sequence[float], out: Tensor,
+                 plane_stride: int = 0) -> None:
   """WFDB format-16 frames (T, nsig) int16 -> physical fp64 (T, len(cols)): (d - baseline) / gain, -32768 -> NaN
   (the host-side dac of wfdb.rdrecord, recordutil.py:137, moved onto the device)."""
   dev = _dev(d)
@@ -291,13 +308,14 @@ def decode_fmt16(d: Tensor, cols: Sequence[int], gain: Sequence[float], baseline
   if d.dim() != 2 or out.numel() < d.shape[0] * n or len(gain) != n or len(baseline) != n:
     raise ValueError('decode_fmt16: d must be (T, nsig), out (T, len(cols)); one gain and baseline per column')
   c = ctx(dev)
-  N.check(c, N.lib().scgrhc_decode_fmt16(c, _ptr(d), d.shape[0], d.shape[1], (C.c_int32 * n)(*cols), n,
-                                         (C.c_double * n)(*gain), (C.c_double * n)(*baseline), _ptr(out), _stream(dev)))
+  with _output_planes(c, plane_stride):        # plane_stride > 0: planar output, column j of row t at out[j * plane_stride + t]
+    N.check(c, N.lib().scgrhc_decode_fmt16(c, _ptr(d), d.shape[0], d.shape[1], (C.c_int32 * n)(*cols), n,
+                                           (C.c_double * n)(*gain), (C.c_double * n)(*baseline), _ptr(out), _stream(dev)))
 
 
 @torch.library.custom_op('scgrhc::decode_fmt16_records', mutates_args=('out',), device_types='cuda')
 def decode_fmt16_records(d: Tensor, rec_row0: Tensor, max_rec_rows: int, cols: Sequence[int], gain: Tensor, baseline: Tensor,
-                         recip: bool, out: Tensor) -> None:
+                         recip: bool, out: Tensor, plane_stride: int = 0) -> None:
   """decode_fmt16 for a chunk of records with per-record calibration in ONE launch: ``rec_row0`` (n_rec+1,) int64 device,
   ``gain`` / ``baseline`` (n_rec, len(cols)) fp64 device tables (every WFDB header carries its own pair)."""
   dev = _dev(d)
@@ -307,9 +325,10 @@ def decode_fmt16_records(d: Tensor, rec_row0: Tensor, max_rec_rows: int, cols: S
   if d.dim() != 2 or out.numel() < d.shape[0] * n or gain.numel() < n_rec * n or baseline.numel() < n_rec * n:
     raise ValueError('decode_fmt16_records: d must be (T, nsig), out (T, len(cols)), tables (n_rec, len(cols))')
   c = ctx(dev)
-  N.check(c, N.lib().scgrhc_decode_fmt16_records(c, _ptr(d), _ptr(rec_row0), n_rec, int(max_rec_rows), d.shape[1],
-                                                 (C.c_int32 * n)(*cols), n, _ptr(gain), _ptr(baseline), 1 if recip else 0,
-                                                 _ptr(out), _stream(dev)))
+  with _output_planes(c, plane_stride):
+    N.check(c, N.lib().scgrhc_decode_fmt16_records(c, _ptr(d), _ptr(rec_row0), n_rec, int(max_rec_rows), d.shape[1],
+                                                   (C.c_int32 * n)(*cols), n, _ptr(gain), _ptr(baseline), 1 if recip else 0,
+                                                   _ptr(out), _stream(dev)))
 
 
 @torch.library.custom_op('scgrhc::waveform_stats', mutates_args=('stats',), device_types='cuda')
@@ -326,7 +345,7 @@ def waveform_stats(y: Tensor, min_rhc: float, stats: Tensor) -> None:
 
 @torch.library.custom_op('scgrhc::synth_records', mutates_args=('out',), device_types='cuda')
 def synth_records(out: Tensor, seed: int, rec0: int, n_rec: int, T: int, kinds: Sequence[int], defect_scale: int,
-                  grid: int) -> None:
+                  grid: int, plane_stride: int = 0) -> None:
   """Synthetic cohort generator, bit-identical to oracle/synth_ref.py."""
   dev = _dev(out)
   _contig(out, torch.float64, 'out')
@@ -335,8 +354,9 @@ def synth_records(out: Tensor, seed: int, rec0: int, n_rec: int, T: int, kinds: 
     raise ValueError('out too small')
   arr = (C.c_int32 * nsig)(*kinds)
   c = ctx(dev)
-  N.check(c, N.lib().scgrhc_synth_records(c, C.c_uint64(seed), rec0, n_rec, T, nsig, arr, defect_scale, grid,
-                                          _ptr(out), _stream(dev)))
+  with _output_planes(c, plane_stride):
+    N.check(c, N.lib().scgrhc_synth_records(c, C.c_uint64(seed), rec0, n_rec, T, nsig, arr, defect_scale, grid,
+                                            _ptr(out), _stream(dev)))
 
 
 def check_errors(device_index):

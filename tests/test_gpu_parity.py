@@ -208,6 +208,106 @@ def test_cohort_vs_oracle(nsig, out_dtype):
   assert total == st.n_kept and 0 < total < plan.n_cand
 
 
+def _same_store(a, b, check_windows=True):
+  """Two WindowStores hold the same decisions, kept list, pairs and (bit for bit) windows."""
+  assert a.n_kept == b.n_kept and torch.equal(a.keep, b.keep) and torch.equal(a.reason, b.reason)
+  assert torch.equal(a.kept_idx, b.kept_idx) and torch.equal(a.start_idx, b.start_idx) and torch.equal(a.rec_id, b.rec_id)
+  ka, kb = a.kept_minmax().cpu().numpy(), b.kept_minmax().cpu().numpy()
+  assert ka.tobytes() == kb.tobytes() or (np.array_equal(np.isnan(ka), np.isnan(kb)) and np.array_equal(ka[~np.isnan(ka)], kb[~np.isnan(kb)]))
+  if not a.dense:
+    assert torch.equal(a.minmax[:, 2:], b.minmax[:, 2:])                     # the RHC pair of every candidate
+  if check_windows and a.scg is not None:
+    xa, xb = a.materialise(), b.materialise()
+    assert xa[0].cpu().numpy().tobytes() == xb[0].cpu().numpy().tobytes()
+    assert xa[1].cpu().numpy().tobytes() == xb[1].cpu().numpy().tobytes()
+
+
+@pytest.mark.parametrize('nsig,chans,W,out_dtype', [
+    (4, ['patch_ACC_lat', 'patch_ACC_hf', 'patch_ACC_dv'], 750, torch.float32),
+    (4, ['patch_ACC_lat', 'patch_ACC_hf', 'patch_ACC_dv'], 750, torch.float64),
+    (5, ['patch_ACC_dv'], 750, torch.float32), (5, ['patch_ACC_hf', 'patch_ECG'], 375, torch.float32),
+    (5, ['patch_ACC_lat', 'patch_ACC_hf', 'patch_ACC_dv', 'patch_ECG'], 333, torch.float32),
+    (7, ['patch_ACC_lat', 'patch_ACC_hf', 'patch_ACC_dv', 'patch_ECG'], 1024, torch.float64),
+    (4, ['patch_ACC_dv', 'patch_ACC_lat'], 1000, torch.float32), (4, ['patch_ACC_hf'], 52, torch.float32), (4, ['patch_ACC_hf'], 7, torch.float32)])
+def test_planar_arena_equals_interleaved(nsig, chans, W, out_dtype):
+  """ARENA_PLANAR (one plane per signal; RHC plane first, SCG planes of kept windows only; pair ownership) gives exactly
+  what the interleaved kernel gives: decisions, reasons, kept list, pairs, windows — for every template shape, odd row
+  offsets (leading element), odd window lengths, planted NaN / Inf, dataset-level pairs (two passes) and KEEP_ALL."""
+  sig = (synth_ref.SIG_NAMES_5 + ['x5', 'x6'])[:nsig] if nsig != 4 else synth_ref.DEFAULT_SIG_NAMES
+  kinds = synth_ref.kinds_for(sig)
+  n_rec, T = 6, 30011
+  metas = [synth_ref.record_meta(60, events=e) for e in ({'PA_1': 0.002, 'RV_1': 31}, {'PA_1': 0}, {'RA_1': 0}, {'RV_1': 1, 'PA_1': 20.005, 'RA_1': 40, 'PA_2': 44.444},
+                                                         {'PA_1': 0.5}, {'PA_1': 3.3})]
+  cols, rcol = scgrhc.resolve_columns(sig, chans)
+  arena = torch.empty((n_rec * T, nsig), dtype=torch.float64, device=DEV)
+  ops.synth_records(arena, 4242, 0, n_rec, T, list(kinds), 16, W)
+  arena[1000:1003, cols[0]] = float('nan')                 # NaN in an SCG column of a kept window
+  arena[T + 5000, cols[-1]] = float('inf')                 # Inf in an SCG column: min/max stay finite-or-inf, not NaN
+  planes = arena.t().contiguous()
+  plan = scgrhc.plan_cohort(metas, 'PA', [T] * n_rec, W, stride=0)
+  assert plan.n_cand > 20 and (plan.intervals['row0'] % 2 == 1).any() and (plan.intervals['row0'] % 2 == 0).any()
+  # the device generator writes the planar layout itself
+  gen = torch.empty((nsig, n_rec * T), dtype=torch.float64, device=DEV)
+  ops.synth_records(gen, 4242, 0, n_rec, T, list(kinds), 16, W, n_rec * T)
+  clean = torch.empty_like(arena)
+  ops.synth_records(clean, 4242, 0, n_rec, T, list(kinds), 16, W)
+  assert torch.equal(gen, clean.t().contiguous())
+  for kw in (dict(), dict(use_global_min_max=True), dict(keep_all=True), dict(predicates_only=True)):
+    if kw.get('use_global_min_max'):
+      a2, p2 = clean, clean.t().contiguous()                # NaN pairs would poison the dataset-level min/max
+    else:
+      a2, p2 = arena, planes
+    a = scgrhc.prepare_windows(a2, plan, cols, rcol, -50.0, out_dtype=out_dtype, **kw)
+    b = scgrhc.prepare_windows(p2, plan, cols, rcol, -50.0, out_dtype=out_dtype, planar=True, **kw)
+    _same_store(a, b)
+    assert 0 < b.n_kept and (kw.get('keep_all') or b.n_kept < plan.n_cand)
+    if kw.get('use_global_min_max'):
+      assert torch.equal(a.global_minmax, b.global_minmax)
+    elif not kw:
+      rej = (~b.keep.bool()).cpu().numpy()
+      assert np.isnan(b.minmax.cpu().numpy()[rej][:, :2]).all()      # SCG planes of rejected windows were never read
+  # non-finite RHC reaches the regression -> ValueError, as in the interleaved kernel
+  bad = planes.clone(); bad[rcol, plan.intervals['row0'][0] + 10] = float('nan')
+  with pytest.raises(ValueError):
+    scgrhc.prepare_windows(bad, plan, cols, rcol, -50.0, planar=True)
+  # capacity edge: the last window of the last plane ends exactly at the end of an odd-sized arena
+  tail_rows = (planes.shape[1] // W) * W - (1 - (planes.shape[1] // W * W) % 2)
+  if W > 50:
+    odd = planes[:, :tail_rows].contiguous()
+    last = scgrhc.Plan(np.array([(tail_rows - 2 * W, 0, 2, 0)], dtype=scgrhc.engine.INTERVAL_DTYPE), 2, W)
+    a = scgrhc.prepare_windows(odd.t().contiguous(), last, cols, rcol, -50.0, out_dtype=out_dtype, keep_all=True)
+    b = scgrhc.prepare_windows(odd, last, cols, rcol, -50.0, out_dtype=out_dtype, keep_all=True, planar=True)
+    _same_store(a, b)
+
+
+def test_planar_digital_ingest_equals_interleaved_ingest():
+  """HostIngest(planar=True) decodes format-16 chunks into planar arenas; the interleaved decode + kernel gives the same store."""
+  from scgrhc.engine import HostIngest
+  sig = synth_ref.DEFAULT_SIG_NAMES
+  kinds = synth_ref.kinds_for(sig)
+  rows = [30011, 752, 15000, 40001, 1500, 8000, 22222]
+  metas = [synth_ref.record_meta(90, events=e) for e in
+           ({'PA_1': 0.2, 'RV_1': 50}, {'PA_1': 0}, {'RA_1': 0}, {'RV_1': 1, 'PA_1': 20, 'RA_1': 60, 'PA_2': 70}, {'PA_1': 0.5}, {'PA_1': 10}, {'PA_1': 3.3})]
+  recs = [synth_ref.gen_record(H.SEED, 500 + r, T, kinds=kinds) for r, T in enumerate(rows)]
+  gains = [[1e5 + 10 * r, 2e5, 1.5e5, 400.0 + r] for r in range(len(rows))]
+  bases = [[3.0 * r, -7.0, 0.0, 100.0 - r] for r in range(len(rows))]
+  d = [np.clip(np.round(p * np.array(g) + np.array(b)), -32767, 32767).astype(np.int16) for p, g, b in zip(recs, gains, bases)]
+  hostd = torch.from_numpy(np.concatenate(d)).pin_memory()
+  plan = scgrhc.plan_cohort(metas, 'PA', rows, 750)
+  for chunk in (1, 3, 100):
+    for kw in (dict(), dict(use_global_min_max=True)):
+      a = HostIngest(plan, rows, 4, DEV, chunk_records=chunk, digital_nsig=4, planar=False).run(hostd, [0, 1, 2], 3, -50.0, decode=([0, 1, 2, 3], gains, bases), **kw)
+      ing = HostIngest(plan, rows, 4, DEV, chunk_records=chunk, digital_nsig=4, planar=True)
+      assert ing.planar and not HostIngest(plan, rows, 4, DEV, chunk_records=chunk, digital_nsig=4).planar
+      b = ing.run(hostd, [0, 1, 2], 3, -50.0, decode=([0, 1, 2, 3], gains, bases), **kw)
+      _same_store(a, b)
+      assert b.n_kept > 0
+  # one calibration for the whole cohort (the other decode kernel)
+  a = HostIngest(plan, rows, 4, DEV, chunk_records=2, digital_nsig=4, planar=False).run(hostd, [0, 1, 2], 3, -50.0, decode=([0, 1, 2, 3], gains[0], bases[0]))
+  b = HostIngest(plan, rows, 4, DEV, chunk_records=2, digital_nsig=4, planar=True).run(hostd, [0, 1, 2], 3, -50.0, decode=([0, 1, 2, 3], gains[0], bases[0]))
+  _same_store(a, b)
+
+
 def test_capacity_edge_uses_fallback_loads():
   """Odd number of arena elements: the last window cannot be bulk-copied with 16-byte granularity."""
   sig = synth_ref.SIG_NAMES_5
