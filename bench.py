@@ -874,13 +874,27 @@ def run_b200(args):
       ms_d, = over_ranks([a.elapsed_time(b) / k_e2e], 'max')
       kept_d, = over_ranks([std.n_kept], 'sum')
       launches[0] += (k_e2e + 2) * (2 * len(ingd.chunks) + 3)
-      e2e['fmt16'] = {'value': kept_d / (ms_d * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': ingd.h2d_bytes, 'ms_per_step': ms_d,
-                      'kept_windows_per_step': int(kept_d), 'h2d_gbs': ingd.h2d_bytes / (ms_d * 1e-3) / 1e9,
-                      'note': 'host buffers are the records as stored on disk (WFDB format 16, int16 frames); '
-                              '(d - baseline) / gain runs on the device (scgrhc_decode_fmt16); cohort quantised with gains %s' % gains}
+      d2h_d = 8 + sum(t.numel() * t.element_size() for t in meta_host)
+      fmt16 = {'value': kept_d / (ms_d * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': ingd.h2d_bytes, 'd2h_bytes_per_step': d2h_d,
+               'ms_per_step': ms_d, 'steps': k_e2e,
+               'kept_windows_per_step': int(kept_d), 'h2d_gbs': ingd.h2d_bytes / (ms_d * 1e-3) / 1e9,
+               'api': 'scgrhc.engine.HostIngest.run(digital_nsig=4): pinned host int16 frames, %d-record chunks, copy / device decode / window kernel overlapped' % args.chunk_records,
+               'note': 'host buffers are the records as stored on disk (WFDB format 16, int16 frames — what wfdb.rdrecord reads at recordutil.py:137); '
+                       '(d - baseline) / gain runs on the device (scgrhc_decode_fmt16); cohort quantised with gains %s; per rank; D2H per step is the '
+                       'kept-window list only: the windows stay in HBM for the trainer by design (north_star: "receive device-resident window tensors")' % gains}
+      # headline e2e = the on-disk record format; the fp64 p_signal variant (the reference's in-memory format, 4x the PCIe bytes) beside it
+      fp64_leg = {k: e2e[k] for k in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step', 'ms_per_step', 'steps', 'api', 'h2d_gbs', 'frac_of_h2d_ceiling', 'note')}
+      rest = {k: v for k, v in e2e.items() if k not in fp64_leg}
+      e2e = dict(fmt16, fp64_p_signal=fp64_leg, **rest)
+      e2e['frac_of_h2d_ceiling'] = e2e['h2d_gbs'] / e2e['h2d_ceiling_gbs']
+      if not args.no_dropin:
+        try:
+          e2e['dropin'] = run_dropin(hostd)
+        except Exception as exc:
+          e2e['dropin'] = {'error': str(exc)[:300]}
       del hostd
 
-  def run_dropin():
+  def run_dropin(hostd):
     """Format-16 records + JSON side-cars on tmpfs -> recordutil.prepare_cohort(params) (the drop-in's own public entry:
     header parse, plan, reader pool -> pinned ring -> H2D -> device decode with per-record tables -> fused window kernel),
     wall clock, sharded by record over the ranks like any multi-GPU job."""
@@ -895,7 +909,18 @@ def run_b200(args):
     if rank == 0:
       shutil.rmtree(root, ignore_errors=True)
     barrier()
-    write_fmt16_cohort(root, n_d, rank * n_d, device_arena=arena)            # every rank writes the records it generated
+    os.makedirs(root, exist_ok=True)
+    frames = hostd.numpy()
+    side = json.dumps(meta())
+    for r in range(n_d):                                                     # every rank writes the (quantised) records it generated
+      name = 'rec%05d' % (rank * n_d + r)
+      frames[r * T_ROWS:(r + 1) * T_ROWS].tofile(os.path.join(root, name + '.dat'))
+      with open(os.path.join(root, name + '.hea'), 'w') as f:
+        f.write('%s %d 500 %d\n' % (name, len(SIG), T_ROWS))
+        for k2, g in enumerate([2.0e5, 2.0e5, 2.0e5, 500.0]):
+          f.write('%s.dat 16 %.17g(0)/%s 16 0 %d 0 0 %s\n' % (name, g, 'mmHg' if k2 == 3 else 'g', int(frames[r * T_ROWS, k2]), SIG[k2]))
+      with open(os.path.join(root, name + '.json'), 'w') as f:
+        f.write(side)
     barrier()
     saved = recordutil.PROCESSED_DATA_PATH, recordutil.wfdb
     recordutil.PROCESSED_DATA_PATH, recordutil.wfdb = root, wfdbio
@@ -935,12 +960,6 @@ def run_b200(args):
       run_e2e()
     except (RuntimeError, MemoryError) as exc:      # e.g. pinned host memory exhausted with 8 ranks on one host
       e2e = dict(e2e or {}, error=str(exc)[:300])
-    if not args.no_dropin:
-      try:
-        dropin = run_dropin()
-      except Exception as exc:
-        dropin = {'error': str(exc)[:300]}
-      e2e = dict(e2e or {}, dropin=dropin)
 
   # the big buffers of the headline leg are no longer needed
   del arena, scg, rhc, minmax, keep, reason, cand_win, cand_rec, kept_idx, start_idx, stop_idx, rec_id
@@ -1017,7 +1036,7 @@ def main():
   ap.add_argument('--config4-records', type=int, default=100000, help='BASELINE configs[3]: records of the whole cohort (all ranks)')
   ap.add_argument('--config4-chunk', type=int, default=500)
   ap.add_argument('--sweep-records', type=int, default=1000, help='BASELINE configs[4]: 5-signal records per GPU')
-  ap.add_argument('--dropin-records', type=int, default=200, help='format-16 records per GPU written to tmpfs for e2e.dropin')
+  ap.add_argument('--dropin-records', type=int, default=500, help='format-16 records per GPU written to tmpfs for e2e.dropin')
   ap.add_argument('--dropin-chunk', type=int, default=25)
   ap.add_argument('--ctas-per-sm', type=int, default=0)
   ap.add_argument('--stages', type=int, default=0)

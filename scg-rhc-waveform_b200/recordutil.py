@@ -497,30 +497,49 @@ def _stage_spec(params, C, rows, metas, names, rec0):
   return plan, stages
 
 
-def prepare_cohort(params, record_names=None, chunk_records=None, group=None):
-  """Records -> HBM -> fused window kernel.  Returns (WindowStore, record_names): every kept window of this rank's
-  records, device resident, in the reference's order (records in ``record_names`` order).
+class _Heterogeneous(Exception):
+  """The records of a cohort do not share one frame layout: the streamed ingest hands over to the eager one."""
 
-  Multi-GPU (one process per GPU under torchrun, SURVEY.md §8e): the per-record loop of get_segments
-  (recordutil.py:131-132) shards by contiguous blocks of ``record_names`` (``engine.shard_records``); every rank runs
-  the same pipeline on its block, ``use_global_min_max`` (recordutil.py:152-169,185-189) goes through ONE MIN all-reduce
-  of {min, -max}, and one all-gather of the kept counts gives ``store.shard`` (this rank's offset in the cohort-wide
-  ordered list), so the concatenation of the ranks' stores in rank order IS the single-GPU store.  ``rec_id`` indexes
-  the full ``record_names`` list on every rank.
 
-  Ingest: format-16 records (scgrhc.wfdbio) are STREAMED — headers only are parsed up front, a reader pool fills a ring
-  of pinned chunk buffers straight from the ``.dat`` files (``engine.DiskSource``), the int16 frames cross PCIe as
-  they are (4x fewer bytes than fp64) and ``(d - baseline) / gain`` runs on the device with the per-record calibration
-  in a device table (what wfdb.rdrecord does on the host at recordutil.py:137); host memory holds a few chunks whatever
-  the cohort size.  Other readers (the real ``wfdb`` package, other formats) take the resident path: ``p_signal`` of
-  every record of the shard in one pinned buffer."""
-  from scgrhc import dist as sdist
-  names_all = list(record_names) if record_names is not None else get_record_names()
-  rank, world = sdist.current(group)
-  lo, hi = engine.shard_records(len(names_all), rank, world)
-  names = names_all[lo:hi]
-  C = len(params.in_channels)
-  dev = _device()
+def _prepare_streamed(params, names, rec0, C, dev, chunk_records, group):
+  """Format-16 files through ``engine.LazyDiskIngest``: only the file sizes are looked at before the first chunk moves;
+  side-cars and headers are parsed, and intervals planned, chunk by chunk while earlier chunks are being read / copied /
+  processed.  Returns None when the cohort does not qualify (other formats, records with different frame layouts)."""
+  W = int(params.segment_size * SAMPLE_FREQ)
+  try:
+    first = wfdb.read_header(os.path.join(PROCESSED_DATA_PATH, names[0]))
+    cols0, rcol0 = engine.resolve_columns(first[0], params.in_channels)
+    nsig_file = len(first[0])
+    sizes = [os.path.getsize(os.path.join(PROCESSED_DATA_PATH, n + '.dat')) // (2 * nsig_file) for n in names]
+  except (NotImplementedError, OSError):
+    return None
+  sel = cols0 + [rcol0]
+
+  def parse_chunk(r0, r1):
+    paths, rows, gains, bases, metas = [], [], [], [], []
+    for name in names[r0:r1]:
+      h = wfdb.read_header(os.path.join(PROCESSED_DATA_PATH, name))
+      if len(h[0]) != nsig_file or engine.resolve_columns(h[0], params.in_channels) != (cols0, rcol0):
+        raise _Heterogeneous(name)
+      paths.append(h[5]); rows.append(h[2])
+      gains.append([float(h[3][j]) for j in sel]); bases.append([float(h[4][j]) for j in sel])
+      metas.append(_read_meta(name))
+    return paths, rows, gains, bases, metas
+
+  def plan_chunk(metas, rows, r0):
+    return engine.plan_cohort(metas, params.chamber, rows, W, rec0=rec0 + r0)
+
+  ing = engine.LazyDiskIngest(sizes, C + 1, dev, W, nsig_file, parse_chunk, plan_chunk, chunk_records=chunk_records or 32)
+  try:
+    return ing.run_files(list(range(C)), C, params.min_RHC, sel, use_global_min_max=bool(params.use_global_min_max), group=group,
+                         normalisation=getattr(params, 'normalisation', None))
+  except (_Heterogeneous, NotImplementedError):
+    return None
+
+
+def _prepare_eager(params, names, names_all, lo, C, dev, chunk_records, group):
+  """Every side-car and header (or, for readers without digital access, every record) is read first, then one plan for the
+  whole shard and a chunked ingest: the path of the optional stages and of readers other than scgrhc.wfdbio."""
   metas = [_read_meta(name) for name in names]
   plan = stages = source = decode = host = None
   rows = []
@@ -565,6 +584,45 @@ def prepare_cohort(params, record_names=None, chunk_records=None, group=None):
   ing = engine.HostIngest(plan, rows, C + 1, dev, chunk_records=chunk_records, digital_nsig=digital_nsig, stages=stages)
   store = ing.run(source, list(range(C)), C, params.min_RHC, decode=decode, use_global_min_max=bool(params.use_global_min_max),
                   group=group, normalisation=getattr(params, 'normalisation', None))
+  return store
+
+
+def prepare_cohort(params, record_names=None, chunk_records=None, group=None):
+  """Records -> HBM -> fused window kernel.  Returns (WindowStore, record_names): every kept window of this rank's
+  records, device resident, in the reference's order (records in ``record_names`` order).
+
+  Multi-GPU (one process per GPU under torchrun, SURVEY.md §8e): the per-record loop of get_segments
+  (recordutil.py:131-132) shards by contiguous blocks of ``record_names`` (``engine.shard_records``); every rank runs
+  the same pipeline on its block, ``use_global_min_max`` (recordutil.py:152-169,185-189) goes through ONE MIN all-reduce
+  of {min, -max}, and one all-gather of the kept counts gives ``store.shard`` (this rank's offset in the cohort-wide
+  ordered list), so the concatenation of the ranks' stores in rank order IS the single-GPU store.  ``rec_id`` indexes
+  the full ``record_names`` list on every rank.
+
+  Ingest: the SIGNAL DATA of format-16 records (scgrhc.wfdbio) is always streamed: a reader pool fills a ring of pinned
+  chunk buffers straight from the ``.dat`` files (``engine.DiskSource``) while the previous chunk crosses PCIe and the
+  one before is in the window kernel; the int16 frames travel as they are (4x fewer bytes than fp64) and
+  ``(d - baseline) / gain`` runs on the device with the per-record calibration in a device table (what wfdb.rdrecord does
+  on the host at recordutil.py:137).  Host memory holds a few chunks whatever the cohort size.  The per-record METADATA
+  (side-car JSON, header, interval maths: ~60 us of Python per record) is parsed up front for shards below
+  ``SCGRHC_LAZY_MIN_RECORDS`` (4096) records and chunk by chunk, overlapped with the stream, above
+  (``engine.LazyDiskIngest``).  Readers without digital access (the real ``wfdb`` package, other formats) upload
+  ``p_signal`` of every record of the shard from one pinned buffer."""
+  from scgrhc import dist as sdist
+  names_all = list(record_names) if record_names is not None else get_record_names()
+  rank, world = sdist.current(group)
+  lo, hi = engine.shard_records(len(names_all), rank, world)
+  names = names_all[lo:hi]
+  C = len(params.in_channels)
+  dev = _device()
+  store = None
+  plain = not (_bandpass_sos(params) is not None or getattr(params, 'resample_rate', None) or getattr(params, 'segment_stride', None))
+  # parse-as-you-go pays off on large shards (100k records: ~8 s of side-car / header parsing hidden behind the stream);
+  # on small ones the host parse of the whole shard is a few ms and the simpler eager ingest is just as fast (measured)
+  lazy_from = int(os.environ.get('SCGRHC_LAZY_MIN_RECORDS', '4096'))
+  if hasattr(wfdb, 'read_header') and plain and len(names) >= lazy_from:
+    store = _prepare_streamed(params, names, lo, C, dev, chunk_records, group)
+  if store is None:
+    store = _prepare_eager(params, names, names_all, lo, C, dev, chunk_records, group)
   store.shard = sdist.exchange_counts(store.n_kept, dev, group)
   return store, names_all
 

@@ -416,26 +416,30 @@ class DiskSource:
     return want
 
   def _submit(self, j):
-    lo, hi, r0, r1 = self.ingest.chunks[j][0], self.ingest.chunks[j][1], self.ingest.chunks[j][5], self.ingest.chunks[j][6]
+    r0, r1 = self.ingest.chunks[j][5], self.ingest.chunks[j][6]
     buf = self.slots[j % self.ring]
-    base = self.ingest.record_base
-    self.futures[j] = [self.pool.submit(self._read, r, buf[int(base[r]) - lo:int(base[r + 1]) - lo]) for r in range(r0, r1)]
+    at, futs = 0, []
+    for r in range(r0, r1):
+      futs.append(self.pool.submit(self._read, r, buf[at:at + self.rows[r]]))
+      at += self.rows[r]
+    self.futures[j] = futs
 
   def begin(self, ingest):
     from concurrent.futures import ThreadPoolExecutor
     self.ingest = ingest
-    max_rows = max((c[1] - c[0] for c in ingest.chunks), default=0)
+    max_rows = ingest.max_chunk_rows
     if self.slots is None or self.slots[0].shape[0] < max_rows:
       self.slots = [torch.empty((max_rows, self.nsig), dtype=torch.int16, pin_memory=True).numpy() for _ in range(self.ring)]
       self.pinned = [torch.from_numpy(a) for a in self.slots]
     self.pool = ThreadPoolExecutor(self.workers)
     self.futures, self.copied = {}, {}
-    for j in range(min(self.ring - 1, len(ingest.chunks))):
-      self._submit(j)
+    for j in range(self.ring - 1):
+      if ingest._ensure_chunk(j):
+        self._submit(j)
 
   def enqueue(self, k, chunk, stage):
     nxt = k + self.ring - 1
-    if nxt < len(self.ingest.chunks):
+    if self.ingest._ensure_chunk(nxt):            # lazy ingests parse + plan that chunk now, while earlier ones are in flight
       if k >= 1:
         self.copied.pop(k - 1).synchronize()      # slot (k-1) % R is free once chunk k-1 has left host memory
       self._submit(nxt)
@@ -449,6 +453,7 @@ class DiskSource:
   def end(self):
     self.pool.shutdown(wait=True)
     self.copied.clear()
+    self.ingest = None                            # no ingest <-> source cycle: the pinned ring goes back to the allocator at once
 
 
 class HostIngest:
@@ -504,6 +509,8 @@ class HostIngest:
       t = torch.from_numpy(sub.view(np.int64).reshape(-1, 3).copy()).to(self.device) if len(sub) else None
       self.chunks.append((lo, hi, cand_lo, n, t, r0, r1))
       max_rows = max(max_rows, hi - lo)
+    self.max_chunk_rows = max_rows
+    self.W, self.stride, self.n_alloc, self.n_total = plan.W, plan.stride, plan.n_cand, plan.n_cand
     self.bufs = [torch.empty((max_rows, nsig), dtype=torch.float64, device=self.device) for _ in range(2)]
     self.digital_nsig = digital_nsig
     self.dbufs = [torch.empty((max_rows, digital_nsig), dtype=torch.int16, device=self.device) for _ in range(2)] \
@@ -511,6 +518,16 @@ class HostIngest:
     self.copy_stream = torch.cuda.Stream(self.device)
     self.h2d_bytes = self.total_rows * (digital_nsig * 2 if digital_nsig else nsig * 8)
     self._tables = None
+
+  def _ensure_chunk(self, k):
+    """True iff chunk k exists (lazy ingests build it on demand)."""
+    return k < len(self.chunks)
+
+  def _chunk_decode(self, k, decode):
+    """(record offsets, longest record, gain table, baseline table, recip) of chunk k for the one-launch decode."""
+    gain_t, base_t, recip, offs, longest = self._decode_tables(decode)
+    r0, r1 = self.chunks[k][5], self.chunks[k][6]
+    return offs[k], longest[k], gain_t[r0:r1], base_t[r0:r1], recip
 
   def _decode_tables(self, decode):
     """Per-record calibration as device tables (gain, baseline: (n_rec, ncols) fp64) + per-chunk record offsets, so that
@@ -542,14 +559,15 @@ class HostIngest:
     digital = self.digital_nsig is not None
     if digital and decode is None:
       raise ValueError('digital cohort: decode=(cols, gain, baseline) is required')
-    per_record = digital and len(decode[1]) and isinstance(decode[1][0], (list, tuple, np.ndarray))
-    if per_record:
-      gain_t, base_t, recip, offs, longest = self._decode_tables(decode)
+    per_record = digital and (decode[1] is None or (len(decode[1]) and isinstance(decode[1][0], (list, tuple, np.ndarray))))
     self.planar_run = bool(planar)
     source.begin(self)
     try:
-      for k, chunk in enumerate(self.chunks):
-        lo, hi, cand_lo, nc, iv, r0, r1 = chunk
+      k = -1
+      while self._ensure_chunk(k + 1):
+        k += 1
+        chunk = self.chunks[k]
+        lo, hi, cand_lo, nc, iv, r0, r1 = chunk[:7]
         dst = self.bufs[k & 1][:hi - lo]
         if planar:                  # (nsig, rows of this chunk): one contiguous plane per signal
           dst = self.bufs[k & 1].view(-1)[:(hi - lo) * self.nsig].view(self.nsig, hi - lo)
@@ -564,11 +582,12 @@ class HostIngest:
         compute.wait_event(ready)
         if digital and nc:
           if per_record:       # every record has its own gain / baseline (WFDB headers): device tables, one launch per chunk
-            ops.decode_fmt16_records(stage, offs[k], longest[k], list(decode[0]), gain_t[r0:r1], base_t[r0:r1], recip, dst, plane)
+            off_k, longest_k, gain_k, base_k, recip = self._chunk_decode(k, decode)
+            ops.decode_fmt16_records(stage, off_k, longest_k, list(decode[0]), gain_k, base_k, recip, dst, plane)
           else:
             ops.decode_fmt16(stage, list(decode[0]), [float(v) for v in decode[1]], [float(v) for v in decode[2]], dst, plane)
         if nc:
-          body(self._run_stages(dst, r0, r1), chunk)
+          body(self._run_stages(dst, r0, r1), chunk, k)
         done[k & 1] = torch.cuda.Event()
         done[k & 1].record(compute)
     finally:
@@ -605,8 +624,8 @@ class HostIngest:
     the compute stream right after the chunk's kernel (``info``: candidate range, and in global mode the kept-list
     range — the tensors are then dense); the consumer must enqueue its reads on the current stream.  The returned
     store then carries no window tensors, only the per-candidate metadata and the ordered kept list."""
-    plan, dev = self.plan, self.device
-    n, W, Cn = plan.n_cand, plan.W, len(scg_cols)
+    dev = self.device
+    n, W, Cn, stride = self.n_alloc, self.W, len(scg_cols), self.stride      # n: allocation (an upper bound for lazy ingests)
     b = buffers if buffers is not None else {}
 
     def buf(name, shape, dtype):
@@ -627,23 +646,21 @@ class HostIngest:
     scg = rhc = None
     ring = None
     if sink is not None:
-      cmax = max((c[3] for c in self.chunks), default=0)
+      cmax = getattr(self, 'max_chunk_cand', None) or max((c[3] for c in self.chunks), default=0)
       ring = [(buf('scg_ring%d' % i, (cmax, Cn, W), out_dtype), buf('rhc_ring%d' % i, (cmax, 1, W), out_dtype)) for i in range(2)]
     elif not use_global_min_max:
       scg, rhc = buf('scg', (n, Cn, W), out_dtype), buf('rhc', (n, 1, W), out_dtype)
     launched = [0]
-    index = {id(c): i for i, c in enumerate(self.chunks)}
 
-    def pass_a(dst, chunk):
-      lo, hi, cand_lo, nc, iv, r0, r1 = chunk
+    def pass_a(dst, chunk, k):
+      lo, hi, cand_lo, nc, iv, r0, r1 = chunk[:7]
       flags = base_flags | (N.PREDICATES_ONLY if use_global_min_max else 0) | (N.KEEP_ERRORS if launched[0] else 0)
-      k = index[id(chunk)]
       so = ro = None
       if ring is not None and not use_global_min_max:
         so, ro = ring[k & 1]
       elif scg is not None:
         so, ro = scg[cand_lo:], rhc[cand_lo:]
-      ops.process_windows(dst, iv, nc, W, plan.stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
+      ops.process_windows(dst, iv, nc, W, stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
                           [0.0] * 4, None, 0, so, ro,
                           minmax[cand_lo:], keep[cand_lo:], reason[cand_lo:], cand_win[cand_lo:], cand_rec[cand_lo:])
       launched[0] += 1
@@ -651,7 +668,9 @@ class HostIngest:
         sink(k, so[:nc], ro[:nc], {'cand_lo': cand_lo, 'n_cand': nc, 'dense': False, 'keep': keep[cand_lo:cand_lo + nc]})
 
     self._stream(host_arena, decode, pass_a, planar)
-    ops.compact_kept(keep, cand_win, cand_rec, n, W, plan.stride, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
+    n = self.n_total                      # lazy ingests know the candidate count only now
+    minmax, keep, reason = minmax[:n], keep[:n], reason[:n]
+    ops.compact_kept(keep, cand_win, cand_rec, n, W, stride, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
     gmm = None
     if use_global_min_max:
       gmm = buf('gmm', (4,), torch.float64)
@@ -669,13 +688,12 @@ class HostIngest:
       pos = torch.searchsorted(kept, edges).cpu().tolist()        # kept-list range of every chunk (plumbing, not arithmetic)
       gm = gmm.cpu().tolist()
 
-      def pass_b(dst, chunk):
-        lo, hi, cand_lo, nc, iv, r0, r1 = chunk
-        k = index[id(chunk)]
+      def pass_b(dst, chunk, k):
+        lo, hi, cand_lo, nc, iv, r0, r1 = chunk[:7]
         a, e = pos[k], pos[k + 1]
         if e > a:
           so, ro = (ring[k & 1]) if ring is not None else (scg[a:], rhc[a:])
-          ops.process_windows(dst, iv, nc, W, plan.stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold),
+          ops.process_windows(dst, iv, nc, W, stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold),
                               base_flags | N.USE_KEPT_LIST | N.NORM_GLOBAL, gm, (kept[a:e] - cand_lo).contiguous(), e - a,
                               so, ro, None, None, None, None, None)
           if ring is not None:
@@ -685,3 +703,67 @@ class HostIngest:
         self._stream(host_arena, decode, pass_b, planar)
     return WindowStore(scg, rhc, minmax, keep, reason, kept_idx[:n_kept], start_idx[:n_kept], stop_idx[:n_kept],
                        rec_id[:n_kept], n_kept, n, bool(use_global_min_max), gmm, n_ambiguous=n_amb)
+
+
+class LazyDiskIngest(HostIngest):
+  """HostIngest for cohorts of format-16 FILES that are parsed, planned, read, copied and processed chunk by chunk: the
+  per-record host work of the reference's loop (side-car JSON, header, interval maths — recordutil.py:96-109,137) for chunk
+  k+2 runs on the CPU while chunk k+1 is being read into the pinned ring and chunk k is in the window kernel, instead of
+  all of it up front.  Only the file SIZES are needed before the first byte moves (buffer capacities); nothing about the
+  cohort is held in host memory beyond the ring.
+
+  ``rows_est[r]``: upper bound of the frames of record r (file size / frame bytes); ``parse_chunk(r0, r1)`` ->
+  ``(dat_paths, rows, gains, baselines, metas)`` of records r0..r1; ``plan_chunk(metas, rows, r0)`` -> engine.Plan of the
+  chunk alone (rows and candidates chunk-local, record ids global)."""
+
+  def __init__(self, rows_est, nsig, device, W, nsig_file, parse_chunk, plan_chunk, chunk_records=32, planar=False):
+    self.plan, self.nsig, self.device = None, nsig, torch.device(device)
+    self.stages, self.planar, self.planar_run = None, bool(planar), False
+    est = [int(v) for v in rows_est]
+    self.n_records, self.chunk_records = len(est), int(chunk_records)
+    self.record_rows = np.zeros(len(est), dtype=np.int64)
+    self.bounds = [(r0, min(len(est), r0 + self.chunk_records)) for r0 in range(0, len(est), self.chunk_records)]
+    self.max_chunk_rows = max((sum(est[a:b]) for a, b in self.bounds), default=0)
+    self.max_chunk_cand = max((sum(v // W for v in est[a:b]) for a, b in self.bounds), default=0)
+    self.W, self.stride = int(W), 0
+    self.n_alloc, self.n_total = sum(v // W for v in est), 0
+    self.parse_chunk, self.plan_chunk = parse_chunk, plan_chunk
+    self.chunks, self._dec = [], []
+    self.total_rows = 0
+    self.bufs = [torch.empty((self.max_chunk_rows, nsig), dtype=torch.float64, device=self.device) for _ in range(2)]
+    self.digital_nsig = int(nsig_file)
+    self.dbufs = [torch.empty((self.max_chunk_rows, self.digital_nsig), dtype=torch.int16, device=self.device) for _ in range(2)]
+    self.copy_stream = torch.cuda.Stream(self.device)
+    self.h2d_bytes = 0
+    self.source = DiskSource([], [], self.digital_nsig)
+
+  def _ensure_chunk(self, k):
+    while len(self.chunks) <= k and len(self.chunks) < len(self.bounds):
+      r0, r1 = self.bounds[len(self.chunks)]
+      paths, rows, gains, bases, metas = self.parse_chunk(r0, r1)
+      rows = [int(v) for v in rows]
+      plan = self.plan_chunk(metas, rows, r0)
+      if sum(rows) > self.max_chunk_rows or plan.n_cand > self.max_chunk_cand or plan.W != self.W or plan.stride not in (0, self.W):
+        raise RuntimeError('record files changed under the ingest (chunk %d larger than its size estimate)' % len(self.chunks))
+      self.record_rows[r0:r1] = rows
+      self.source.paths.extend(paths); self.source.rows.extend(rows); self.source.offsets.extend([0] * len(paths))
+      iv = plan.device_intervals(self.device) if plan.n_cand else None
+      g = np.ascontiguousarray(np.asarray(gains, dtype=np.float64).reshape(len(rows), -1))
+      b = np.ascontiguousarray(np.asarray(bases, dtype=np.float64).reshape(len(rows), -1))
+      ag = np.abs(g)
+      recip = bool(g.size and (ag >= 2.0 ** -40).all() and (ag <= 2.0 ** 60).all() and (np.abs(b) < 65536.0).all() and (b == np.floor(b)).all())
+      off = torch.from_numpy(np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)).to(self.device)
+      self._dec.append((off, max(rows) if rows else 0, torch.from_numpy(g).to(self.device), torch.from_numpy(b).to(self.device), recip))
+      lo = self.total_rows
+      self.total_rows += sum(rows)
+      self.chunks.append((lo, self.total_rows, self.n_total, plan.n_cand, iv, r0, r1))
+      self.n_total += plan.n_cand
+      self.h2d_bytes = self.total_rows * self.digital_nsig * 2
+    return k < len(self.chunks)
+
+  def _chunk_decode(self, k, decode):
+    return self._dec[k]
+
+  def run_files(self, scg_cols, rhc_col, min_rhc, sel_cols, **kw):
+    """``run`` over the files: ``sel_cols`` = the file's signal columns that become arena columns 0..nsig-1."""
+    return self.run(self.source, scg_cols, rhc_col, min_rhc, decode=(list(sel_cols), None, None), **kw)

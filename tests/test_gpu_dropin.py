@@ -174,6 +174,49 @@ def test_save_dataloaders_end_to_end(tmp_path, monkeypatch):
   assert seen == set(want)                                  # every kept window lands in exactly one split
 
 
+def test_streamed_ingest_equals_eager_ingest(tmp_path, monkeypatch):
+  """prepare_cohort streams format-16 cohorts chunk by chunk (parse / plan / read / copy / kernel overlapped,
+  engine.LazyDiskIngest); parsing everything first (_prepare_eager) gives the same store — ragged records, records
+  without windows, dataset-level pairs; a cohort whose records list their signals differently falls back by itself."""
+  root = tmp_path / 'data'; root.mkdir()
+  monkeypatch.setattr(recordutil, 'PROCESSED_DATA_PATH', str(root))
+  monkeypatch.setattr(recordutil, 'wfdb', wfdbio)
+  sig = synth_ref.SIG_NAMES_5
+  events = [{'RA_1': 0, 'PA_1': 12, 'RV_1': 70}, {'PA_1': 0}, {'RV_1': 0}, {'PA_1': 3.2, 'PCW_1': 40, 'PA_2': 55}, {'PA_1': 1}, {'RA_1': 3},
+            {'PA_1': 0.001}]
+  for r, ev in enumerate(events):
+    p = synth_ref.gen_record(H.SEED, 700 + r, 30000 + 1111 * r, kinds=synth_ref.kinds_for(sig))
+    wfdbio.wrsamp('rec%d' % r, 500, ['g', 'g', 'g', 'mmHg', 'mV'], sig, p, write_dir=str(root))
+    (root / ('rec%d.json' % r)).write_text(json.dumps(synth_ref.record_meta(100, events=ev)))
+  names = sorted(recordutil.get_record_names())
+  dev = torch.device('cuda', torch.cuda.current_device())
+  for cfg in ('waveform_06', 'waveform_04', 'waveform_25'):
+    c = H.effective_config(cfg)
+    params = types.SimpleNamespace(**{k: c[k] for k in ('in_channels', 'chamber', 'segment_size', 'min_RHC', 'use_global_min_max')})
+    C = len(params.in_channels)
+    for chunk in (1, 2, 3, 50):
+      a = recordutil._prepare_streamed(params, names, 0, C, dev, chunk, None)
+      b = recordutil._prepare_eager(params, names, names, 0, C, dev, chunk, None)
+      assert a is not None and a.n_kept == b.n_kept > 0 and a.n_cand == b.n_cand
+      assert torch.equal(a.kept_idx, b.kept_idx) and torch.equal(a.rec_id, b.rec_id) and torch.equal(a.start_idx, b.start_idx)
+      assert torch.equal(a.keep, b.keep) and torch.equal(a.kept_minmax(), b.kept_minmax())
+      x, y = a.materialise(), b.materialise()
+      assert torch.equal(x[0], y[0]) and torch.equal(x[1], y[1])
+    monkeypatch.setenv('SCGRHC_LAZY_MIN_RECORDS', '1' if cfg == 'waveform_06' else '4096')   # both ingests through the public entry
+    st, _ = recordutil.prepare_cohort(params, record_names=names)
+    assert st.n_kept == b.n_kept and torch.equal(st.materialise()[0], y[0])
+  # a record that lists its signals in another order: not one frame layout -> the streamed ingest declines
+  p = synth_ref.gen_record(H.SEED, 799, 20000, kinds=synth_ref.kinds_for(sig))
+  order = [3, 0, 1, 2, 4]
+  wfdbio.wrsamp('rec9', 500, ['mmHg', 'g', 'g', 'g', 'mV'], [sig[i] for i in order], p[:, order], write_dir=str(root))
+  (root / 'rec9.json').write_text(json.dumps(synth_ref.record_meta(40, events={'PA_1': 0})))
+  names = sorted(recordutil.get_record_names())
+  assert recordutil._prepare_streamed(params, names, 0, C, dev, 2, None) is None
+  monkeypatch.setenv('SCGRHC_LAZY_MIN_RECORDS', '1')
+  st, _ = recordutil.prepare_cohort(params, record_names=names)
+  assert st.n_kept > b.n_kept and int(st.rec_id.max()) == len(names) - 1
+
+
 def test_save_dataloaders_sweep_equals_one_job_per_config(tmp_path, monkeypatch):
   """`recordutil.py prepare d1 d2 ...`: one read + one upload of the cohort, one predicate pass and one fan-out pass
   per chamber — and every config directory ends up with the loaders a separate save_dataloaders job writes."""
