@@ -155,6 +155,26 @@ int scgrhc_plan_cohort(const double* event_time, const uint8_t* event_match, con
  *      waveform_noise.py:6-49).  Asynchronous. */
 int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, const scgrhc_outputs* out, void* stream);
 
+/* ---- extension (named by the project brief, ABSENT from the reference; default off): the hot path with a DECIMATING front
+ *      end.  job->arena holds the records at their native rate, (rows, 4) fp64; every candidate window of job->W rows at the
+ *      MODEL rate (native / down) is produced inside the kernel by the polyphase FIR of scipy.signal.resample_poly (up == 1;
+ *      taps = scipy's flipped table, every tap a separately rounded multiply and add, oldest sample first; zero padding
+ *      outside the record) — bit-identical to scgrhc_resample_poly followed by scgrhc_process_windows, without the
+ *      resampled cohort ever existing in HBM.  job->intervals / n_cand / stride are in model-rate rows as planned on the
+ *      resampled cohort (row0 is not used); per interval: iv_in0 = arena row of its record's first native-rate row,
+ *      iv_len = native-rate rows of that record, iv_rel = the interval's first model-rate row relative to its record.
+ *      fp32 outputs, per-window normalisation (min-max or NORM_ZSCORE), W <= 384, 1..3 SCG channels. */
+typedef struct {
+  const double* taps;      /* host, per_phase doubles */
+  int32_t per_phase, down, n_pre_remove;
+  int32_t fused;           /* != 0: one FMA per tap (within ~1e-15 of scipy) instead of the bit-identical multiply + add */
+  const int64_t* iv_in0;   /* device (n_intervals) */
+  const int64_t* iv_len;   /* device (n_intervals) */
+  const int64_t* iv_rel;   /* device (n_intervals) */
+} scgrhc_decim;
+int scgrhc_process_windows_decim(scgrhc_ctx* ctx, const scgrhc_job* job, const scgrhc_outputs* out, const scgrhc_decim* dec,
+                                 void* stream);
+
 /* ---- sweep fan-out (the loadable waveform_NN configs are 4 chambers x 8 channel subsets; for one
  *      chamber has_noise() looks at the RHC channel only, waveform_noise.py:44-49): after ONE predicate pass
  *      (SCGRHC_PREDICATES_ONLY) and scgrhc_compact_kept, normalise every kept window for up to SCGRHC_MAX_SUBSETS channel

@@ -326,6 +326,88 @@ extern "C" int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, co
   }
 }
 
+// ---- the same with the decimating front end (extension): native-rate arena -> model-rate windows inside the kernel --------
+template <int C, bool IDENT, int DDOWN, int DPP, bool DFMA>
+static int launch_window_decim_t(scgrhc_ctx* ctx, const KParamsDecim& P, long long items, cudaStream_t st) {
+  auto kern = window_kernel<C, true, IDENT, float, -3, true, DDOWN, DPP, DFMA>;
+  const size_t smem = ((sizeof(Scratch) + 127) & ~size_t(127)) +
+                      ((size_t)P.k.stage_elems + (size_t)(P.k.job.W + 1) * 4 + kDecimMaxTaps) * sizeof(double);
+  CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+  if (occ < 1) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "decimating window of %d samples (x%d, %d taps) does not fit in shared memory (%zu B/CTA)", P.k.job.W, P.d.down, P.d.pp, smem);
+  if (ctx->ctas_per_sm > 0) occ = std::min(occ, ctx->ctas_per_sm);
+  const long long grid = std::min<long long>(items, (long long)ctx->sm_count * occ);
+  kern<<<(unsigned)grid, NT, smem, st>>>(P);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return SCGRHC_OK;
+}
+
+template <int C, bool IDENT>
+static int launch_window_decim(scgrhc_ctx* ctx, const KParamsDecim& P, long long items, bool fma, cudaStream_t st) {
+  if (P.d.down == 2 && P.d.pp == 43)                     // 500 -> 250 Hz, scipy's kaiser-5 design: unrolled, taps as constant operands
+    return fma ? launch_window_decim_t<C, IDENT, 2, 43, true>(ctx, P, items, st) : launch_window_decim_t<C, IDENT, 2, 43, false>(ctx, P, items, st);
+  return fma ? launch_window_decim_t<C, IDENT, 0, 0, true>(ctx, P, items, st) : launch_window_decim_t<C, IDENT, 0, 0, false>(ctx, P, items, st);
+}
+
+extern "C" int scgrhc_process_windows_decim(scgrhc_ctx* ctx, const scgrhc_job* job, const scgrhc_outputs* out, const scgrhc_decim* dec,
+                                            void* stream) {
+  NvtxRange nvtx_range("scgrhc_process_windows_decim");
+  if (!ctx) return SCGRHC_ERR_BAD_ARG;
+  if (!job || !out || !dec) return fail(ctx, SCGRHC_ERR_BAD_ARG, "job/out/dec is NULL");
+  const scgrhc_job& J = *job;
+  if (J.nsig != 4) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "the decimating front end reads 4-signal records (nsig=%d)", J.nsig);
+  if (J.C < 1 || J.C > 3) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "C=%d SCG channels (supported 1..3 of the 4 signals)", J.C);
+  if (J.W < 2 || J.W > kDecimR * NT) return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "window of %d samples (supported 2..%d)", J.W, kDecimR * NT);
+  if (J.flags & (SCGRHC_USE_KEPT_LIST | SCGRHC_NORM_GLOBAL | SCGRHC_OUT_F64 | SCGRHC_ARENA_PLANAR))
+    return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "process_windows_decim: fp32 outputs, per-window pairs, interleaved arena only");
+  if (dec->per_phase < 1 || dec->per_phase > kDecimMaxTaps || dec->down < 1 || dec->down > 16 || dec->n_pre_remove < 0 || !dec->taps)
+    return fail(ctx, SCGRHC_ERR_UNSUPPORTED, "process_windows_decim: 1..%d taps per output, down 1..16", kDecimMaxTaps);
+  if (J.rhc_col < 0 || J.rhc_col >= 4) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "RHC column %d outside 0..3", J.rhc_col);
+  for (int c = 0; c < J.C; ++c)
+    if (J.scg_cols[c] < 0 || J.scg_cols[c] >= 4) return fail(ctx, SCGRHC_ERR_MISSING_CHANNEL, "SCG column %d outside 0..3", J.scg_cols[c]);
+  if (J.n_cand < 0 || J.n_intervals < 0 || J.stride < 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "negative counts");
+  if ((reinterpret_cast<uintptr_t>(J.arena) & 15) != 0) return fail(ctx, SCGRHC_ERR_BAD_ARG, "arena must be 16-byte aligned");
+  const bool pred_only = J.flags & SCGRHC_PREDICATES_ONLY;
+  if (J.n_cand && (!out->keep || !out->reason || !out->minmax || !out->cand_win || !out->cand_rec))
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "keep/reason/minmax/cand_win/cand_rec outputs are required");
+  if (!pred_only && (!out->scg_out || !out->rhc_out) && J.n_cand) return fail(ctx, SCGRHC_ERR_BAD_ARG, "scg_out/rhc_out are required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (!(J.flags & SCGRHC_KEEP_ERRORS)) {
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->err_dev, 0, sizeof(unsigned long long), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->err_dev + 1, 0xFF, sizeof(unsigned long long), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->err_dev + 2, 0, sizeof(unsigned long long), st));
+  }
+  if (J.n_cand == 0) return SCGRHC_OK;
+  if (!J.intervals || J.n_intervals == 0 || !dec->iv_in0 || !dec->iv_len || !dec->iv_rel)
+    return fail(ctx, SCGRHC_ERR_BAD_ARG, "candidates without intervals / record tables");
+  KParamsDecim P;
+  memset(&P, 0, sizeof P);
+  P.k.job = J;
+  P.k.out = *out;
+  P.k.err = ctx->err_dev;
+  P.k.stages = 1;
+  const int PB = kDecimR * dec->down;
+  const int rows_tot = ((J.W + kDecimR - 1) / kDecimR) * PB + dec->per_phase;      // rows the last thread's sliding pass may touch
+  P.k.stage_elems = (rows_tot + rows_tot / PB + 2) * 4;
+  P.k.arena_elems_cap = J.arena_capacity_bytes / 8;
+  for (int i = 0; i < dec->per_phase; ++i) P.d.taps[i] = dec->taps[i];
+  P.d.pp = dec->per_phase; P.d.down = dec->down; P.d.npr = dec->n_pre_remove;
+  P.d.rows_in = (J.W - 1) * dec->down + dec->per_phase;
+  P.d.pb_magic = (unsigned)(((1ULL << 32) + PB - 1) / PB);
+  P.d.iv_in0 = reinterpret_cast<const long long*>(dec->iv_in0);
+  P.d.iv_len = reinterpret_cast<const long long*>(dec->iv_len);
+  P.d.iv_rel = reinterpret_cast<const long long*>(dec->iv_rel);
+  const bool ident = J.C == 3 && J.scg_cols[0] == 0 && J.scg_cols[1] == 1 && J.scg_cols[2] == 2 && J.rhc_col == 3;
+  const bool fma = dec->fused != 0;
+  switch (J.C) {
+    case 1: return launch_window_decim<1, false>(ctx, P, J.n_cand, fma, st);
+    case 2: return launch_window_decim<2, false>(ctx, P, J.n_cand, fma, st);
+    default: return ident ? launch_window_decim<3, true>(ctx, P, J.n_cand, fma, st) : launch_window_decim<3, false>(ctx, P, J.n_cand, fma, st);
+  }
+}
+
 extern "C" int scgrhc_normalize_subsets(scgrhc_ctx* ctx, const scgrhc_job* job, const scgrhc_subset* subsets, int32_t n_subsets,
                                         void* rhc_out, void* stream) {
   NvtxRange nvtx_range("scgrhc_normalize_subsets");

@@ -56,6 +56,31 @@ struct KParams {
   long long arena_elems_cap;
 };
 
+// Decimating front end (extension): the arena holds the records at their NATIVE rate; every candidate window
+// of W rows at the model rate is produced on the fly by the polyphase FIR of scipy.signal.resample_poly (up == 1, integer
+// `down`; every tap a separately rounded multiply and add, oldest sample first: bit-identical to the standalone
+// decimator and hence to scipy), straight from the staged native-rate rows into the shared-memory window the rest of the
+// kernel reads.  The resampled cohort never exists in HBM.
+constexpr int kDecimMaxTaps = 128;
+constexpr int kDecimR = 3;           // consecutive outputs per thread: W <= kDecimR * NT
+struct DecimK {
+  double taps[kDecimMaxTaps];        // scipy's flipped polyphase table for up == 1 (resample_design)
+  int pp, down, npr;                 // taps per output, decimation factor, n_pre_remove
+  int rows_in;                       // native-rate rows one window needs: (W - 1) * down + pp
+  unsigned pb_magic;                 // r / (kDecimR * down) == umulhi(r, pb_magic)
+  const long long* iv_in0;           // device (n_intervals): arena row of the first native-rate row of the interval's record
+  const long long* iv_len;           // device: native-rate rows of that record
+  const long long* iv_rel;           // device: first model-rate row of the interval, relative to its record
+};
+struct KParamsDecim {
+  KParams k;
+  DecimK d;
+};
+template <bool DECIM> struct KParamsOf { typedef KParams type; };
+template <> struct KParamsOf<true> { typedef KParamsDecim type; };
+__device__ __forceinline__ const KParams& kparams_base(const KParams& p) { return p; }
+__device__ __forceinline__ const KParams& kparams_base(const KParamsDecim& p) { return p.k; }
+
 constexpr int NRED = 8;  // smin, smax, ymin, ymax, s1, s2 (+ 0*v NaN accumulator), sxy, run-candidate flag
 
 struct Scratch {
@@ -206,8 +231,14 @@ __global__ void __launch_bounds__(256) selftest_div_kernel(unsigned long long se
 // C      SCG channels;  NSIG4  rows are 4 doubles (16-byte shared loads);
 // IDENT  columns are (0..C-1 | C) in order (no selects);  WCT  > 0: compile-time window length; 0: runtime length, RMAX rows per thread;
 //        < 0: runtime length <= -WCT * NT with -WCT rows per thread (resampled cohorts: 375 samples = 3 rows)
-template <int C, bool NSIG4, bool IDENT, typename OutT, int WCT>
-__global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ KParams P) {
+// DDOWN / DPP > 0 (DECIM only): compile-time decimation factor and taps per output — the FIR is then fully unrolled, the
+// taps are immediate constant-bank operands and the pad-row bookkeeping folds away (500 -> 250 Hz: down 2, 43 taps).
+// DFMA (DECIM only): one fused multiply-add per tap instead of a separately rounded multiply and add — half the fp64
+// instructions, within ~1e-15 of scipy instead of bit-identical (the `fused` mode of scgrhc_resample_poly).
+template <int C, bool NSIG4, bool IDENT, typename OutT, int WCT, bool DECIM = false, int DDOWN = 0, int DPP = 0, bool DFMA = false>
+__global__ void __launch_bounds__(NT, DECIM ? 5 : 4) window_kernel(const __grid_constant__ typename KParamsOf<DECIM>::type PP) {
+  const KParams& P = kparams_base(PP);
+  static_assert(!DECIM || (NSIG4 && WCT < 0 && -WCT <= kDecimR), "the decimating front end feeds the 4-signal, <= 3 rows per thread variant");
   static_assert(SCGRHC_FLAT_WIN == 50, "run detection below is hard-wired to 49 = 32 + 16 + 1 pairs");
   constexpr int R = WCT > 0 ? (WCT + NT - 1) / NT : (WCT < 0 ? -WCT : RMAX);
   static_assert(R * NWARP <= 32 && R <= RMAX, "one mask word per lane");
@@ -273,7 +304,57 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
       bulk_g2s(stage_base + (size_t)s * P.stage_elems, J.arena + (elem0 - lead), bytes, &S.full[s]);
     }
   };
-  if (tid == 0) {
+  // ---- decimating front end: every thread walks the intervals itself (two cursors: prefetch and consume) and stages its
+  //      share of the native-rate rows with 16-byte cp.async copies (zero fill outside the record = upfirdn's zero padding)
+  double* wbuf = nullptr;               // the model-rate window the FIR writes: (W + 1) rows of 4 doubles
+  double* s_taps = nullptr;
+  int c_iv = 0;                         // consumer cursor
+  long long c_cand0 = 0, c_in0 = 0, c_len = 0, c_rel = 0;
+  int c_nwin = 0, c_rec = 0;
+  long long q_in0 = 0, q_len = 0, q_rel = 0;   // producer cursor shares p_iv / p_cand0 / p_nwin
+  auto stage_in = [&](long long item, int st) {
+    if constexpr (DECIM) {
+      const DecimK& D = PP.d;
+      while (item >= p_cand0 + p_nwin) {
+        ++p_iv;
+        const scgrhc_interval I = J.intervals[p_iv];
+        p_cand0 = I.cand0; p_nwin = I.n_win;
+        q_in0 = D.iv_in0[p_iv]; q_len = D.iv_len[p_iv]; q_rel = D.iv_rel[p_iv];
+      }
+      const long long m0 = q_rel + (item - p_cand0) * wstride;            // first model-rate row of the window in its record
+      const long long first = (m0 + D.npr) * D.down - D.pp + 1;          // native-rate row of staged row 0 (may be < 0)
+      double* dst = stage_base + (size_t)st * P.stage_elems;
+      // chunk q = tid + i * NT of the window's 16-byte chunks: row r = (tid >> 1) + 64 i, half h = tid & 1 (fixed per thread)
+      const int h = tid & 1;
+      const double* src0 = J.arena + q_in0 * 4 + 2 * h;
+      for (int r = tid >> 1; r < D.rows_in; r += NT / 2) {
+        const long long xi = first + r;
+        const bool in = xi >= 0 && xi < q_len;
+        const int pr = r + (int)__umulhi((unsigned)r, D.pb_magic);       // one pad row per thread span: conflict-free FIR loads
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst + (size_t)pr * 4 + 2 * h)),
+                     "l"(src0 + (in ? xi : 0) * 4), "r"(in ? 16 : 0) : "memory");
+      }
+    }
+  };
+  if constexpr (DECIM) {
+    const DecimK& D = PP.d;
+    wbuf = stage_base + (size_t)P.stage_elems;
+    s_taps = wbuf + (size_t)(W + 1) * 4;
+    for (int i = tid; i < D.pp; i += NT) s_taps[i] = D.taps[i];
+    int a = 0, b = J.n_intervals - 1;  // last interval with cand0 <= lo
+    while (a < b) {
+      const int mid = (a + b + 1) >> 1;
+      if (J.intervals[mid].cand0 <= lo) a = mid; else b = mid - 1;
+    }
+    const scgrhc_interval I = J.intervals[a];
+    p_iv = c_iv = a;
+    p_cand0 = c_cand0 = I.cand0; p_nwin = c_nwin = I.n_win; c_rec = I.rec_id;
+    q_in0 = c_in0 = D.iv_in0[a]; q_len = c_len = D.iv_len[a]; q_rel = c_rel = D.iv_rel[a];
+    // ONE raw stage per CTA (5 CTAs per SM instead of 3): the copy of window n+1 is issued as soon as the FIR of window n has
+    // drained the stage and overlaps the statistics / normalisation / stores of window n; the other CTAs cover the rest
+    stage_in(lo, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  } else if (tid == 0) {
     const long long first = use_list ? J.kept_list[lo] : lo;
     int a = 0, b = J.n_intervals - 1;  // last interval with cand0 <= first
     while (a < b) {
@@ -294,15 +375,128 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
   int s = 0;
   uint32_t parity = 0, par2 = 0;
   for (long long n = 0; n < hi - lo; ++n) {
-    mbar_wait(&S.full[s], parity);
-    const StageMeta M = S.meta[s];
-    double* sbuf = stage_base + (size_t)s * P.stage_elems;
-    if (M.fallback) {  // capacity edge: plain loads, rare
-      const long long ne = (long long)W * nsig;
-      for (long long e = tid; e < ne; e += NT) sbuf[M.lead + e] = J.arena[M.elem0 + e];
-      __syncthreads();
+    StageMeta M;
+    const double* win;
+    if constexpr (DECIM) {
+      const DecimK& D = PP.d;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");      // this thread's copies of window n have landed
+      __syncthreads();                                            // ... and everybody else's; the previous window is out of wbuf
+      {
+        // polyphase FIR, kDecimR consecutive outputs per thread from ONE sliding pass over pp + (kDecimR - 1) * down staged
+        // rows (the arithmetic and the conflict-free staging of resample_decim_kernel, filter_kernels.cuh)
+        const int down = D.down, pp = D.pp, PB = kDecimR * down;
+        const int swap = (tid >> 2) & 1;
+        const double* base = stage_base + (size_t)tid * (PB + 1) * 4;
+        double acc[kDecimR][4];
+#pragma unroll
+        for (int r = 0; r < kDecimR; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+        if constexpr (DPP > 0) {
+          if (tid * kDecimR < W) {
+            constexpr int CPB = kDecimR * DDOWN, CJ = DPP + (kDecimR - 1) * DDOWN;
+#pragma unroll
+            for (int j = 0; j < CJ; ++j) {
+              const double* prow = base + (size_t)(j + j / CPB) * 4;       // compile-time offset: one pad row per CPB rows
+              const double2 a = *reinterpret_cast<const double2*>(prow + (swap ? 2 : 0));
+              const double2 b = *reinterpret_cast<const double2*>(prow + (swap ? 0 : 2));
+#pragma unroll
+              for (int r = 0; r < kDecimR; ++r) {
+                if (j - r * DDOWN >= 0 && j - r * DDOWN < DPP) {
+                  const double hk = D.taps[j - r * DDOWN >= 0 && j - r * DDOWN < DPP ? j - r * DDOWN : 0];   // constant-bank operand
+                  if constexpr (DFMA) {
+                    acc[r][0] = __fma_rn(a.x, hk, acc[r][0]); acc[r][1] = __fma_rn(a.y, hk, acc[r][1]);
+                    acc[r][2] = __fma_rn(b.x, hk, acc[r][2]); acc[r][3] = __fma_rn(b.y, hk, acc[r][3]);
+                  } else {
+                    acc[r][0] = __dadd_rn(acc[r][0], __dmul_rn(a.x, hk)); acc[r][1] = __dadd_rn(acc[r][1], __dmul_rn(a.y, hk));
+                    acc[r][2] = __dadd_rn(acc[r][2], __dmul_rn(b.x, hk)); acc[r][3] = __dadd_rn(acc[r][3], __dmul_rn(b.y, hk));
+                  }
+                }
+              }
+            }
+          }
+        } else if (tid * kDecimR < W) {
+          const int Jn = pp + (kDecimR - 1) * down, ramp = (kDecimR - 1) * down;
+          auto load_row = [&](const double* p, double (&xv)[4]) {
+            const double2 a = *reinterpret_cast<const double2*>(p + (swap ? 2 : 0));
+            const double2 b = *reinterpret_cast<const double2*>(p + (swap ? 0 : 2));
+            xv[0] = a.x; xv[1] = a.y; xv[2] = b.x; xv[3] = b.y;
+          };
+          auto some = [&](int j, const double (&xv)[4]) {   // ramp-up / ramp-down: output r takes rows r*down .. r*down + pp - 1
+#pragma unroll
+            for (int r = 0; r < kDecimR; ++r) {
+              const int k = j - r * down;
+              if (k >= 0 && k < pp) {
+                const double hk = s_taps[k];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = DFMA ? __fma_rn(xv[c], hk, acc[r][c]) : __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
+              }
+            }
+          };
+          const double* pb = base;
+          int j = 0, bend = PB;
+          for (; j < ramp; ++j) {                             // ramp < PB: all in block 0
+            double xv[4];
+            load_row(pb + (size_t)j * 4, xv);
+            some(j, xv);
+          }
+          while (j < pp) {                                    // steady state: every output takes the row
+            const int je = min(pp, bend);
+#pragma unroll 4
+            for (; j < je; ++j) {
+              double xv[4];
+              load_row(pb + (size_t)j * 4, xv);
+#pragma unroll
+              for (int r = 0; r < kDecimR; ++r) {
+                const double hk = s_taps[j - r * down];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = DFMA ? __fma_rn(xv[c], hk, acc[r][c]) : __dadd_rn(acc[r][c], __dmul_rn(xv[c], hk));
+              }
+            }
+            if (j == bend) { bend += PB; pb += 4; }
+          }
+          while (j < Jn) {
+            const int je = min(Jn, bend);
+            for (; j < je; ++j) {
+              double xv[4];
+              load_row(pb + (size_t)j * 4, xv);
+              some(j, xv);
+            }
+            if (j == bend) { bend += PB; pb += 4; }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < kDecimR; ++r) {
+          const int o = tid * kDecimR + r;
+          if (o < W) {
+            double2* dst = reinterpret_cast<double2*>(wbuf + (size_t)o * 4);
+            dst[swap ? 1 : 0] = make_double2(acc[r][0], acc[r][1]);     // odd lane groups hold the two halves swapped
+            dst[swap ? 0 : 1] = make_double2(acc[r][2], acc[r][3]);
+          }
+        }
+      }
+      __syncthreads();                                            // the window is in wbuf; stage s is free
+      if (lo + n + 1 < hi) stage_in(lo + n + 1, 0);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      const long long item = lo + n;
+      while (item >= c_cand0 + c_nwin) {
+        ++c_iv;
+        const scgrhc_interval I = J.intervals[c_iv];
+        c_cand0 = I.cand0; c_nwin = I.n_win; c_rec = I.rec_id;
+      }
+      M.cand = item; M.slot = item; M.elem0 = 0; M.win = (int)(item - c_cand0); M.rec = c_rec; M.lead = 0; M.fallback = 0;
+      win = wbuf;
+    } else {
+      mbar_wait(&S.full[s], parity);
+      M = S.meta[s];
+      double* sbuf = stage_base + (size_t)s * P.stage_elems;
+      if (M.fallback) {  // capacity edge: plain loads, rare
+        const long long ne = (long long)W * nsig;
+        for (long long e = tid; e < ne; e += NT) sbuf[M.lead + e] = J.arena[M.elem0 + e];
+        __syncthreads();
+      }
+      win = sbuf + M.lead;
     }
-    const double* win = sbuf + M.lead;
 
     // ---- rows -> registers (+ the next row's RHC sample for the small-step bit) --------------------
     double x[R][C], y[R], yn[R];
@@ -571,7 +765,9 @@ __global__ void __launch_bounds__(NT, 4) window_kernel(const __grid_constant__ K
     }
 
     // ---- the stage buffer is dead: refill it with window n + stages ---------------------------
-    if (tid == 0 && lo + n + nstage < hi) issue(lo + n + nstage, s);
+    if constexpr (!DECIM) {
+      if (tid == 0 && lo + n + nstage < hi) issue(lo + n + nstage, s);
+    }
     if (++s == nstage) { s = 0; parity ^= 1; }
 
     // ---- normalise from registers, transpose, cast, store ---------------------------------------

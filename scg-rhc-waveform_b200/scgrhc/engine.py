@@ -6,6 +6,7 @@
                               device-resident cohort (recordutil.py:141-148,55-66,152-169)
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from datetime import datetime
 from typing import List, Optional, Sequence
@@ -209,7 +210,7 @@ def resolve_columns(sig_name, in_channels):
 
 def prepare_windows(arena, plan, scg_cols, rhc_col, min_rhc, use_global_min_max=False, out_dtype=torch.float32,
                     predicates_only=False, keep_all=False, flat_threshold=FLAT_THRESHOLD, group=None,
-                    check=True, buffers=None, normalisation='minmax', planar=False):
+                    check=True, buffers=None, normalisation='minmax', planar=False, decim=None):
   """Run the hot path over every candidate window of ``plan``.
 
   Local normalisation (default): ONE fused kernel pass — predicates, min/max, normalise, transpose,
@@ -256,8 +257,16 @@ def prepare_windows(arena, plan, scg_cols, rhc_col, min_rhc, use_global_min_max=
     scg = buf('scg', (n, Cn, W), out_dtype)
     rhc = buf('rhc', (n, 1, W), out_dtype)
   flags = base_flags | (N.PREDICATES_ONLY if (predicates_only or two_pass) else 0)
-  ops.process_windows(arena, iv, n, W, plan.stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
-                      [0.0] * 4, None, 0, scg, rhc, minmax, keep, reason, cand_win, cand_rec)
+  if decim is not None:
+    if two_pass or f64 or planar:
+      raise ValueError('decim: fp32 outputs with per-window pairs on an interleaved arena only')
+    t_in0, t_len, t_rel = decim.tables(plan, dev)
+    ops.process_windows_decim(arena, iv, n, W, plan.stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
+                              decim.taps, decim.per_phase, decim.down, decim.n_pre_remove, t_in0, t_len, t_rel,
+                              scg, rhc, minmax, keep, reason, cand_win, cand_rec, fused=decim.fused)
+  else:
+    ops.process_windows(arena, iv, n, W, plan.stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
+                        [0.0] * 4, None, 0, scg, rhc, minmax, keep, reason, cand_win, cand_rec)
   ops.compact_kept(keep, cand_win, cand_rec, n, W, plan.stride, kept_idx, start_idx, stop_idx, rec_id, n_kept_t)
   gmm = None
   if use_global_min_max:
@@ -511,6 +520,28 @@ class HostIngest:
       max_rows = max(max_rows, hi - lo)
     self.max_chunk_rows = max_rows
     self.W, self.stride, self.n_alloc, self.n_total = plan.W, plan.stride, plan.n_cand, plan.n_cand
+    # Integer decimation with bit-identical taps can run INSIDE the window kernel (scgrhc_process_windows_decim): the
+    # resampled chunk is never written.  Per chunk: the native-rate position / length of every interval's record.
+    self.decim, self._decim_tabs, self._fuse_decim = None, None, False
+    if self.stages and self.stages.get('resample') and self.stages.get('fuse_decim', os.environ.get('SCGRHC_FUSE_DECIM', '1') != '0') \
+        and nsig == 4 and plan.W <= 384:
+      import math
+      from . import filters
+      up, down = self.stages['resample']
+      g = math.gcd(int(up), int(down))
+      if up // g == 1 and down // g >= 2:
+        try:
+          self.decim = filters.DecimSpec.design(rows, up, down, fused=not self.stages.get('resample_exact', True))
+        except NotImplementedError:
+          self.decim = None
+      if self.decim is not None:
+        self._decim_tabs = []
+        for (lo, hi, cand_lo, n, t, r0, r1) in self.chunks:
+          a, b = np.searchsorted(iv['row0'], [int(plan_base[r0]), int(plan_base[r1])], side='left')
+          row0 = iv['row0'][a:b].astype(np.int64)
+          r = np.searchsorted(plan_base, row0, side='right') - 1                    # record of every interval
+          mk = lambda v: torch.from_numpy(np.ascontiguousarray(v, dtype=np.int64)).to(self.device)
+          self._decim_tabs.append((mk(base[r] - lo), mk(rows[r]), mk(row0 - plan_base[r])) if len(row0) else None)
     self.bufs = [torch.empty((max_rows, nsig), dtype=torch.float64, device=self.device) for _ in range(2)]
     self.digital_nsig = digital_nsig
     self.dbufs = [torch.empty((max_rows, digital_nsig), dtype=torch.int16, device=self.device) for _ in range(2)] \
@@ -603,7 +634,7 @@ class HostIngest:
     if st.get('sos') is not None:
       exact = bool(st.get('filter_exact', True)) or len(st['sos']) > 4
       dst = filters.sosfiltfilt(dst, rows, st['sos'], list(st['filter_cols']), exact=exact, inplace=not exact)
-    if st.get('resample'):
+    if st.get('resample') and not self._fuse_decim:
       up, down = st['resample']
       dst, _ = filters.resample_poly(dst, rows, up, down, exact=bool(st.get('resample_exact', True)))
     return dst
@@ -643,6 +674,9 @@ class HostIngest:
       raise ValueError('planar=True needs a source that writes planes (digital cohort or SynthSource); fp64 host rows are interleaved')
     base_flags = (N.OUT_F64 if out_dtype == torch.float64 else 0) | _norm_flag(normalisation, use_global_min_max) | \
         (N.ARENA_PLANAR if planar else 0)
+    # decimation inside the window kernel when it applies (fp32 outputs, per-window pairs); else the resample stage runs
+    self._fuse_decim = fuse = getattr(self, 'decim', None) is not None and not use_global_min_max and out_dtype == torch.float32 \
+        and len(scg_cols) <= 3
     scg = rhc = None
     ring = None
     if sink is not None:
@@ -660,9 +694,15 @@ class HostIngest:
         so, ro = ring[k & 1]
       elif scg is not None:
         so, ro = scg[cand_lo:], rhc[cand_lo:]
-      ops.process_windows(dst, iv, nc, W, stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
-                          [0.0] * 4, None, 0, so, ro,
-                          minmax[cand_lo:], keep[cand_lo:], reason[cand_lo:], cand_win[cand_lo:], cand_rec[cand_lo:])
+      if fuse:
+        dc, (t_in0, t_len, t_rel) = self.decim, self._decim_tabs[k]
+        ops.process_windows_decim(dst, iv, nc, W, stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
+                                  dc.taps, dc.per_phase, dc.down, dc.n_pre_remove, t_in0, t_len, t_rel, so, ro,
+                                  minmax[cand_lo:], keep[cand_lo:], reason[cand_lo:], cand_win[cand_lo:], cand_rec[cand_lo:], fused=dc.fused)
+      else:
+        ops.process_windows(dst, iv, nc, W, stride, list(scg_cols), rhc_col, float(min_rhc), float(flat_threshold), flags,
+                            [0.0] * 4, None, 0, so, ro,
+                            minmax[cand_lo:], keep[cand_lo:], reason[cand_lo:], cand_win[cand_lo:], cand_rec[cand_lo:])
       launched[0] += 1
       if ring is not None and not use_global_min_max:
         sink(k, so[:nc], ro[:nc], {'cand_lo': cand_lo, 'n_cand': nc, 'dense': False, 'keep': keep[cand_lo:cand_lo + nc]})

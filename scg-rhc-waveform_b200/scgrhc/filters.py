@@ -162,3 +162,40 @@ def resample_poly(arena, record_rows, up, down, window=('kaiser', 5.0), exact=Tr
                                             n, max(out_rows[lo:lo + n]), arena.shape[1], first[0], first[1], first[4], first[5],
                                             0 if exact else 1, ops._stream(dev.index)))
   return out, out_rows
+
+
+class DecimSpec:
+  """What the decimating front end of the window kernel needs (``engine.prepare_windows(..., decim=...)``): the FIR of
+  scipy.signal.resample_poly for an integer decimation and the native / model-rate row counts of every record of the
+  arena.  ``DecimSpec.design(record_rows, rate, native)`` derives it exactly as ``resample_poly`` does."""
+
+  def __init__(self, taps, per_phase, down, n_pre_remove, in_rows, out_rows, fused=False):
+    self.fused = bool(fused)        # one FMA per tap (~1e-15 of scipy) instead of the bit-identical multiply + add
+    self.taps, self.per_phase, self.down, self.n_pre_remove = np.ascontiguousarray(taps, dtype=np.float64), int(per_phase), int(down), int(n_pre_remove)
+    self.in_rows, self.out_rows = [int(v) for v in in_rows], [int(v) for v in out_rows]
+
+  @classmethod
+  def design(cls, record_rows, up, down, window=('kaiser', 5.0), fused=False):
+    import math
+    rows = [int(r) for r in record_rows]
+    g = math.gcd(int(up), int(down))
+    if up // g != 1 or down // g < 2:
+      raise ValueError('the decimating front end does integer decimation (up/down = 1/k, k >= 2); got %d/%d' % (up, down))
+    lengths = sorted(set(rows))
+    designs = {n: resample_design(n, up, down, window) for n in lengths}
+    first = designs[lengths[0]]
+    if any(d[6] != first[6] for d in designs.values()):
+      raise NotImplementedError('records whose lengths need different FIR post-padding in one cohort')
+    if first[4] > 128:
+      raise NotImplementedError('more than 128 taps per output')
+    return cls(first[3], first[4], first[1], first[5], rows, [designs[n][2] for n in rows], fused)
+
+  def tables(self, plan, device):
+    """Per interval of ``plan`` (planned on the model-rate rows): arena row of the record's first native-rate row, its
+    native-rate length, and the interval's first model-rate row relative to the record — int64 CUDA tensors."""
+    out_base = np.concatenate([[0], np.cumsum(self.out_rows)]).astype(np.int64)
+    in_base = np.concatenate([[0], np.cumsum(self.in_rows)]).astype(np.int64)
+    row0 = plan.intervals['row0'].astype(np.int64)
+    r = np.searchsorted(out_base, row0, side='right') - 1
+    mk = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(device)
+    return mk(in_base[r]), mk(np.asarray(self.in_rows, dtype=np.int64)[r]), mk(row0 - out_base[r])

@@ -134,6 +134,44 @@ def process_windows(arena: Tensor, intervals: Tensor, n_cand: int, W: int, strid
   N.check(c, N.lib().scgrhc_process_windows(c, C.byref(j), C.byref(o), _stream(dev)))
 
 
+def process_windows_decim(arena, intervals, n_cand, W, stride, scg_cols, rhc_col, min_rhc, flat_threshold, flags, taps, per_phase, down,
+                          n_pre_remove, iv_in0, iv_len, iv_rel, scg_out, rhc_out, minmax, keep, reason, cand_win, cand_rec, fused=False):
+  """Extension: process_windows with the decimating front end (scgrhc_process_windows_decim): ``arena`` holds native-rate
+  (rows, 4) records, the windows are W rows at the model rate; ``taps`` = numpy fp64 (per_phase,), the three ``iv_*`` =
+  int64 CUDA tensors (n_intervals,)."""
+  dev = _dev(arena)
+  _contig(arena, torch.float64, 'arena'); _contig(intervals, torch.int64, 'intervals')
+  for t, nm in ((iv_in0, 'iv_in0'), (iv_len, 'iv_len'), (iv_rel, 'iv_rel')):
+    _contig(t, torch.int64, nm)
+    if t.numel() < intervals.shape[0]:
+      raise ValueError('%s: one entry per interval' % nm)
+  _contig(scg_out, torch.float32, 'scg_out'); _contig(rhc_out, torch.float32, 'rhc_out')
+  _contig(minmax, torch.float64, 'minmax'); _contig(keep, torch.uint8, 'keep'); _contig(reason, torch.uint8, 'reason')
+  _contig(cand_win, torch.int32, 'cand_win'); _contig(cand_rec, torch.int32, 'cand_rec')
+  if arena.dim() != 2 or arena.shape[1] != 4:
+    raise N.ScgrhcError(N.ERR_UNSUPPORTED, 'the decimating front end reads (rows, 4) arenas')
+  j = N.Job()
+  j.arena = arena.data_ptr(); j.arena_rows = arena.shape[0]; j.arena_capacity_bytes = arena.numel() * 8; j.nsig = 4
+  j.W = W; j.stride = stride; j.C = len(scg_cols)
+  for i, c in enumerate(scg_cols):
+    j.scg_cols[i] = c
+  j.rhc_col = rhc_col; j.flags = flags
+  j.intervals = intervals.data_ptr(); j.n_intervals = intervals.shape[0]; j.n_cand = n_cand
+  j.min_rhc = min_rhc; j.flat_threshold = flat_threshold
+  if not flags & N.PREDICATES_ONLY and n_cand:
+    if scg_out is None or rhc_out is None or scg_out.numel() < n_cand * j.C * W or rhc_out.numel() < n_cand * W:
+      raise ValueError('scg_out/rhc_out too small for %d slots' % n_cand)
+  for t, nm in ((minmax, 4), (keep, 1), (reason, 1), (cand_win, 1), (cand_rec, 1)):
+    if t is None or t.numel() < n_cand * nm:
+      raise ValueError('per-candidate output too small')
+  import numpy as np
+  tp = np.ascontiguousarray(taps, dtype=np.float64)
+  d = N.Decim(tp.ctypes.data, int(per_phase), int(down), int(n_pre_remove), 1 if fused else 0, iv_in0.data_ptr(), iv_len.data_ptr(), iv_rel.data_ptr())
+  o = N.Outputs(_ptr(scg_out), _ptr(rhc_out), _ptr(minmax), _ptr(keep), _ptr(reason), _ptr(cand_win), _ptr(cand_rec))
+  c = ctx(dev)
+  N.check(c, N.lib().scgrhc_process_windows_decim(c, C.byref(j), C.byref(o), C.byref(d), _stream(dev)))
+
+
 @torch.library.custom_op('scgrhc::compact_kept', mutates_args=('kept_idx', 'start_idx', 'stop_idx', 'rec_id', 'n_kept'),
                          device_types='cuda')
 def compact_kept(keep: Tensor, cand_win: Tensor, cand_rec: Tensor, n_cand: int, W: int, stride: int, kept_idx: Tensor,

@@ -111,6 +111,46 @@ def test_resample_poly_matches_scipy(up, down, ncols):
   assert (np.abs(fast.cpu().numpy() - out) / scale).max() <= 1e-14
 
 
+@pytest.mark.parametrize('down,chans,norm', [(2, ['patch_ACC_lat', 'patch_ACC_hf', 'patch_ACC_dv'], 'minmax'), (2, ['patch_ACC_lat', 'patch_ACC_hf', 'patch_ACC_dv'], 'zscore'),
+                                             (2, ['patch_ACC_dv'], 'minmax'), (4, ['patch_ACC_hf', 'patch_ACC_lat'], 'minmax'), (5, ['patch_ACC_lat', 'patch_ACC_hf', 'patch_ACC_dv'], 'minmax')])
+def test_decimating_window_kernel_equals_resample_then_window(down, chans, norm):
+  """scgrhc_process_windows_decim: native-rate arena -> model-rate windows INSIDE the window kernel (the polyphase FIR of
+  scipy.signal.resample_poly, separately rounded taps) == resample_poly (bit-identical to scipy) followed by the window
+  kernel, bit for bit — decisions, pairs, windows; ragged records, intervals that start at the very first / end at the
+  very last row of a record (the FIR's zero padding), several decimation factors, sub-sets of columns, z-score."""
+  import scgrhc
+  sig = synth_ref.DEFAULT_SIG_NAMES
+  kinds = synth_ref.kinds_for(sig)
+  rows = [60000, 20011, 30000, 45007]
+  fs = 500 // down
+  W = int(1.5 * fs)
+  metas = [synth_ref.record_meta(120, events=e) for e in ({'PA_1': 0, 'RV_1': 95}, {'RV_1': 0, 'PA_1': 1.234}, {'RA_1': 0}, {'PA_1': 0.002, 'RV_1': 30, 'PA_2': 50.5})]
+  recs = [synth_ref.gen_record(H.SEED, 610 + r, T, kinds=kinds) for r, T in enumerate(rows)]
+  arena = torch.from_numpy(np.concatenate(recs)).to(DEV)
+  cols, rcol = scgrhc.resolve_columns(sig, chans)
+  spec = filters.DecimSpec.design(rows, fs, 500)
+  r, out_rows = filters.resample_poly(arena, rows, fs, 500)
+  assert out_rows == spec.out_rows
+  plan = scgrhc.plan_cohort(metas, 'PA', out_rows, W, fs=float(fs))
+  assert plan.n_cand > 50 and (plan.intervals['row0'] == np.concatenate([[0], np.cumsum(out_rows)])[[0]]).any()
+  for kw in (dict(), dict(keep_all=True), dict(predicates_only=True)):
+    a = scgrhc.prepare_windows(r, plan, cols, rcol, -50.0, normalisation=norm, **kw)
+    b = scgrhc.prepare_windows(arena, plan, cols, rcol, -50.0, normalisation=norm, decim=spec, **kw)
+    assert a.n_kept == b.n_kept > 0 and torch.equal(a.keep, b.keep) and torch.equal(a.reason, b.reason)
+    assert torch.equal(a.kept_idx, b.kept_idx) and torch.equal(a.start_idx, b.start_idx) and torch.equal(a.rec_id, b.rec_id)
+    assert a.minmax.cpu().numpy().tobytes() == b.minmax.cpu().numpy().tobytes()
+    if not kw.get('predicates_only'):
+      x, y = a.materialise(), b.materialise()
+      assert x[0].cpu().numpy().tobytes() == y[0].cpu().numpy().tobytes() and x[1].cpu().numpy().tobytes() == y[1].cpu().numpy().tobytes()
+  with pytest.raises(ValueError):
+    scgrhc.prepare_windows(arena, plan, cols, rcol, -50.0, decim=spec, use_global_min_max=True)
+  # one FMA per tap instead of multiply + add: not bit-identical, within 1e-5 of the exact windows after normalisation
+  fast = scgrhc.prepare_windows(arena, plan, cols, rcol, -50.0, normalisation=norm, decim=filters.DecimSpec.design(rows, fs, 500, fused=True))
+  exact = scgrhc.prepare_windows(arena, plan, cols, rcol, -50.0, normalisation=norm, decim=spec)
+  assert torch.equal(fast.keep, exact.keep)
+  assert (fast.materialise()[0] - exact.materialise()[0]).abs().max().item() <= 1e-5
+
+
 def test_filter_resample_window_pipeline_against_scipy_plus_oracle():
   """All extensions chained the way recordutil does when the optional params keys are present: band-pass the SCG
   columns, resample every column 500 -> 250 Hz, plan the chamber intervals at the new rate, window + normalise."""
@@ -259,6 +299,14 @@ def test_extension_stages_stream_per_chunk(tmp_path, monkeypatch):
     a, b = one.materialise(), whole.materialise()
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     assert torch.equal(one.kept_minmax(), whole.kept_minmax())
+    # integer decimation runs inside the window kernel when it applies (bit-identical taps, fp32, per-window pairs); the
+    # separate resample stage gives the same windows
+    monkeypatch.setenv('SCGRHC_FUSE_DECIM', '0')
+    sep, _ = recordutil.prepare_cohort(params, names, chunk_records=2)
+    monkeypatch.delenv('SCGRHC_FUSE_DECIM')
+    assert sep.n_kept == whole.n_kept and torch.equal(sep.kept_idx, whole.kept_idx) and torch.equal(sep.kept_minmax(), whole.kept_minmax())
+    c = sep.materialise()
+    assert torch.equal(c[0], b[0]) and torch.equal(c[1], b[1])
 
 
 def _guarded(shape, dtype, pad=4096):
