@@ -68,6 +68,10 @@ class Params:
   def _get(self, key):
     if key in self.data or self.strict or key not in LEGACY_DEFAULTS:
       return self.data[key]            # KeyError for a missing key, as the reference (paramutil.py:9-29)
+    if key in ('chamber', 'min_RHC', 'use_global_min_max'):      # the keys that change which windows are produced
+      import warnings
+      warnings.warn('%s has no %r: using the documented legacy default %r (the reference raises KeyError here; '
+                    'Params(path, strict=True) does too)' % (self.path, key, LEGACY_DEFAULTS[key]), stacklevel=3)
     return LEGACY_DEFAULTS[key]
 
   def init_json(self, path):
