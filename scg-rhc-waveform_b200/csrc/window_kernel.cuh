@@ -81,6 +81,10 @@ template <> struct KParamsOf<true> { typedef KParamsDecim type; };
 __device__ __forceinline__ const KParams& kparams_base(const KParams& p) { return p; }
 __device__ __forceinline__ const KParams& kparams_base(const KParamsDecim& p) { return p.k; }
 
+// Conflict-free row loads in the identity-column variant (see the kernel).  Measured in round 2 and NOT adopted: shared-memory
+// bank conflicts 154 M -> 21 M per launch, but the selects that put the halves back cost +16 % instructions (3,331 -> 3,875 per
+// window): burst 2.22 -> 2.26 ms, sustained 2.62 -> 2.56 ms, i.e. within noise of each other.
+constexpr bool kSwizzleLoads = false;
 constexpr int NRED = 8;  // smin, smax, ymin, ymax, s1, s2 (+ 0*v NaN accumulator), sxy, run-candidate flag
 
 struct Scratch {
@@ -507,7 +511,20 @@ __global__ void __launch_bounds__(NT, DECIM ? 5 : 4) window_kernel(const __grid_
       y[k] = 0.0; yn[k] = 0.0;
 #pragma unroll
       for (int c = 0; c < C; ++c) x[k][c] = 0.0;
-      if (valid) {
+      if constexpr (NSIG4 && IDENT && kSwizzleLoads) {
+        // Rows are 32 bytes: consecutive lanes reading the same half of their rows hit every other 16-byte bank group twice
+        // (2-way conflict, 153.8 M per launch in round 1).  Odd groups of four lanes fetch the two halves in the opposite
+        // order instead: each quarter-warp then covers all 32 banks.  The RHC sample of the next row comes from the next lane.
+        if (valid) {
+          const int sw = (tid >> 2) & 1;
+          const double2 d0 = *reinterpret_cast<const double2*>(win + 4 * t + (sw ? 2 : 0));
+          const double2 d1 = *reinterpret_cast<const double2*>(win + 4 * t + (sw ? 0 : 2));
+          x[k][0] = sw ? d1.x : d0.x; x[k][1] = sw ? d1.y : d0.y; x[k][2] = sw ? d0.x : d1.x; y[k] = sw ? d0.y : d1.y;
+        }
+        const double up = __shfl_down_sync(kFull, y[k], 1);
+        yn[k] = up;
+        if (lane == 31 && valid) yn[k] = win[4 * (t + 1) + 3];      // row t+1 lives in the next warp (the stage is padded)
+      } else if (valid) {
         if constexpr (NSIG4) {
           const double2 a = *reinterpret_cast<const double2*>(win + 4 * t);
           const double2 b = *reinterpret_cast<const double2*>(win + 4 * t + 2);
