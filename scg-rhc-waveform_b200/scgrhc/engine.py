@@ -484,8 +484,8 @@ class HostIngest:
     ``planar`` (default off): the fp64 chunk arenas on the device are PLANAR (one plane per signal,
     csrc/window_planar_kernel.cuh): the device decode (digital cohorts) or generator (SynthSource) writes that layout at
     no extra cost and a rejected window then costs 6 KB of DRAM traffic instead of 24 KB.  Measured: DRAM
-    traffic drops to the algorithmic bytes, but the two-phase kernel executes ~25 % more instructions per window and the
-    path is issue-bound before it is DRAM-bound, so the interleaved kernel stays the default.  Not for fp64 host cohorts
+    traffic drops to the algorithmic bytes, but the two-phase kernel has the longer critical path per window and the path is
+    latency / issue-bound before it is DRAM-bound, so the interleaved kernel stays the default.  Not for fp64 host cohorts
     (they arrive interleaved over PCIe) nor with the optional stages (the filters read interleaved rows)."""
     self.plan, self.nsig, self.device = plan, nsig, torch.device(device)
     self.stages = stages or None
