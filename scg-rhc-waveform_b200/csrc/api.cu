@@ -240,7 +240,7 @@ static int dispatch_nsig(scgrhc_ctx* ctx, const KParams& P, long long items, cud
 template <int C, int NTH, int PR, typename OutT, int WCT>
 static int launch_planar(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
   auto kern = window_planar_kernel<C, NTH, PR, OutT, WCT>;
-  const size_t smem = ((sizeof(PScratch<NTH>) + 127) & ~size_t(127)) + (size_t)(2 + 2 * C) * P.stage_elems * sizeof(double);
+  const size_t smem = ((sizeof(PScratch<NTH>) + 127) & ~size_t(127)) + (size_t)(PNR + 2 * C) * P.stage_elems * sizeof(double);
   CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTH, smem));

@@ -18,6 +18,10 @@
 
 namespace scgrhc {
 
+#ifndef SCGRHC_PNR
+#define SCGRHC_PNR 3
+#endif
+constexpr int PNR = SCGRHC_PNR;      // RHC windows in flight per CTA (6 KB each); 3 keeps 4 CTAs/SM at C = 3 (4 slots: 3 CTAs, slower)
 constexpr int PNRED = 12;   // phase A: -ymin, ymax | s1, s2, sxy, dense ; phase B: -smin, smax | nan accumulator
 
 struct PMeta {
@@ -31,8 +35,8 @@ struct PMeta {
 
 template <int NTH>
 struct PScratch {
-  uint64_t rfull[2], sfull[2];
-  PMeta rmeta[2];                       // item whose RHC window sits in RHC slot s
+  uint64_t rfull[PNR], sfull[2];
+  PMeta rmeta[PNR];                       // item whose RHC window sits in RHC slot s
   PMeta bmeta[2];                       // kept item whose SCG planes sit (or are landing) in SCG slot s
   int bkeep[2];                         // 0: nothing for phase B in this slot; 1: kept, bulk copies issued; 2: kept, plain loads
   double red[2][NTH / 32][PNRED];
@@ -54,7 +58,7 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
   PScratch<NTH>& S = *reinterpret_cast<PScratch<NTH>*>(smem_raw);
   double* const rbase = reinterpret_cast<double*>(smem_raw + ((sizeof(PScratch<NTH>) + 127) & ~size_t(127)));
   const int wpad = P.stage_elems;                      // doubles per plane window in shared memory (even, >= W + 3)
-  double* const sbase = rbase + 2 * wpad;
+  double* const sbase = rbase + PNR * wpad;
 
   const scgrhc_job& J = P.job;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
   const long long cnt = hi - lo;
 
   if (tid == 0) {
-    mbar_init(&S.rfull[0], 1); mbar_init(&S.rfull[1], 1);
+    for (int i = 0; i < PNR; ++i) mbar_init(&S.rfull[i], 1);
     mbar_init(&S.sfull[0], 1); mbar_init(&S.sfull[1], 1);
     S.slow_cnt = 0;
     S.bkeep[0] = 0; S.bkeep[1] = 0;
@@ -142,8 +146,7 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
     }
     p_iv = a;
     load_iv(a);
-    issue_rhc(lo, 0);
-    if (cnt > 1) issue_rhc(lo + 1, 1);
+    for (int i = 0; i < PNR && i < cnt; ++i) issue_rhc(lo + i, i);
   }
 
   const double xbar = 0.5 * (double)(W - 1);
@@ -161,7 +164,9 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
   for (int c = 0; c < C; ++c) ppar[c] = (int)(((long long)J.scg_cols[c] * rows) & 1);
   const int ypar = (int)(((long long)J.rhc_col * rows) & 1);
 
-  uint32_t rpar[2] = {0u, 0u}, spar[2] = {0u, 0u};
+  uint32_t spar[2] = {0u, 0u};
+  int rs = 0;                 // RHC slot of item j: j % PNR, parity (j / PNR) & 1
+  uint32_t rparity = 0u;
   for (long long j = 0; j < cnt + 2; ++j) {
     const int s = (int)(j & 1);
     const bool doA = j < cnt;
@@ -173,10 +178,9 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
     double y0[PR], y1[PR];
     double K = 0.0;
     if (doA) {
-      mbar_wait(&S.rfull[s], rpar[s]);
-      rpar[s] ^= 1u;
-      MA = S.rmeta[s];
-      double* buf = rbase + (size_t)s * wpad;
+      mbar_wait(&S.rfull[rs], rparity);
+      MA = S.rmeta[rs];
+      double* buf = rbase + (size_t)rs * wpad;
       const int lead = (ypar ^ (int)MA.row) & 1;
       if (MA.fallback) {
         for (int e = tid; e < W; e += NTH) buf[lead + e] = yplane[MA.row + e];
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
         if (run || s2_bad) {                    // CTA-uniform and rare: exact work on the RHC window still in shared memory
           if (warp == 0 && lane < NWORDS) S.a24[lane] = a24;
           __syncthreads();
-          const double* win = rbase + (size_t)s * wpad + ((ypar ^ (int)MA.row) & 1);
+          const double* win = rbase + (size_t)rs * wpad + ((ypar ^ (int)MA.row) & 1);
           int c = 0, fl = 0;
           if (run) {
             for (int k = 0; k < PR; ++k) {
@@ -402,9 +406,11 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
         const double2 b = reinterpret_cast<const double2*>(P.out.minmax + 4 * MA.cand)[1];
         ymin = b.x; ymax = b.y;
       }
-      if (tid == 0) {
+      // two producers, in different warps, so that neither serial section sits alone on the iteration's critical path:
+      // thread 0 refills the RHC slot (it owns the interval cursor), thread 32 issues the SCG planes of the kept window
+      if (tid == 0 && j + PNR < cnt) issue_rhc(lo + j + PNR, rs);    // RHC slot rs is in registers everywhere
+      if (tid == 32) {
         if (keep) issue_scg(MA, s); else S.bkeep[s] = 0;
-        if (j + 2 < cnt) issue_rhc(lo + j + 2, s);        // RHC slot s is in registers everywhere: refill it
       }
       if (keep && !pred_only) {
         if (norm_global) { ymin = J.global_minmax[2]; ymax = J.global_minmax[3]; }
@@ -449,7 +455,7 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
           }
         }
       }
-    } else if (tid == 0) {
+    } else if (tid == 32) {
       S.bkeep[s] = 0;                                        // drain iterations: nothing enters the pipeline any more
     }
 
@@ -529,6 +535,7 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
         }
       }
     }
+    if (++rs == PNR) { rs = 0; rparity ^= 1u; }
   }
 }
 
