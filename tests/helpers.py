@@ -71,3 +71,11 @@ def small_record():
 def full_record(r):
   sig = synth_ref.SIG_NAMES_5
   return sig, synth_ref.gen_record(SEED, r, 300000, kinds=synth_ref.kinds_for(sig)), synth_ref.record_meta(600)
+
+
+def free_port():
+  """A TCP port nobody listens on right now (torch.distributed rendezvous of the multi-process tests)."""
+  import socket
+  with socket.socket() as so:
+    so.bind(('127.0.0.1', 0))
+    return so.getsockname()[1]

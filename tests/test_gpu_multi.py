@@ -61,9 +61,10 @@ def test_two_rank_sharding_equals_one_rank(tmp_path, monkeypatch):
                    _params_dir(tmp_path, 'multi/s06_sharded', 'waveform_06', train_layout='sharded')],
           'sweep': [_params_dir(tmp_path, 'multi/w%s' % c[-2:], c) for c in ('waveform_06', 'waveform_07', 'waveform_25', 'waveform_04')]}
   (out / 'jobs.json').write_text(json.dumps(jobs))
-  env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29541')
+  port = str(H.free_port())
+  env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT=port)
   run = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=%d' % WORLD,
-                        '--master-addr', '127.0.0.1', '--master-port', '29541', os.path.join(ROOT, 'tests', 'dist_gpu_worker.py'),
+                        '--master-addr', '127.0.0.1', '--master-port', port, os.path.join(ROOT, 'tests', 'dist_gpu_worker.py'),
                         str(root), str(out)], capture_output=True, text=True, env=env, timeout=900)
   assert run.returncode == 0 and 'MULTI_OK' in run.stdout, run.stdout[-3000:] + run.stderr[-3000:]
 

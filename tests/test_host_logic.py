@@ -130,9 +130,11 @@ def test_split_arithmetic_matches_sklearn():
 
 def test_gloo_minmax_allreduce_and_sharding():
   script = os.path.join(ROOT, 'tests', 'dist_worker.py')
-  env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29533')
+  from tests import helpers as H
+  port = str(H.free_port())
+  env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT=port)
   out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
-                        '--master-addr', '127.0.0.1', '--master-port', '29533', script],
+                        '--master-addr', '127.0.0.1', '--master-port', port, script],
                        capture_output=True, text=True, env=env, timeout=300)
   assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
   assert 'DIST_OK' in out.stdout
