@@ -24,21 +24,18 @@ namespace scgrhc {
 constexpr int PNR = SCGRHC_PNR;      // RHC windows in flight per CTA (6 KB each); 3 keeps 4 CTAs/SM at C = 3 (4 slots: 3 CTAs, slower)
 constexpr int PNRED = 12;   // phase A: -ymin, ymax | s1, s2, sxy, dense ; phase B: -smin, smax | nan accumulator
 
-struct PMeta {
-  long long cand;   // candidate index
-  long long slot;   // output slot
-  long long row;    // first arena row of the window
-  int win, rec;
-  int fallback;     // bulk copy not possible (capacity edge): cooperative plain loads
-  int pad;
+struct PMeta {      // what every thread reads per item: 16 bytes
+  long long cand;   // candidate index (the output slot too, unless the job walks a kept list)
+  long long rowf;   // first arena row of the window; bit 62: bulk copy not possible (capacity edge) -> cooperative plain loads
 };
+constexpr long long kPFallback = 1LL << 62;
 
 template <int NTH>
 struct PScratch {
   uint64_t rfull[PNR], sfull[2];
   PMeta rmeta[PNR];                       // item whose RHC window sits in RHC slot s
   PMeta bmeta[2];                       // kept item whose SCG planes sit (or are landing) in SCG slot s
-  int bkeep[2];                         // 0: nothing for phase B in this slot; 1: kept, bulk copies issued; 2: kept, plain loads
+  int2 raux[PNR];                       // (window number inside its interval, record id) of the item in RHC slot s: thread 0 only
   double red[2][NTH / 32][PNRED];
   uint32_t cmask[2][8 * (NTH / 32)];
   uint32_t a24[8 * (NTH / 32)];
@@ -85,10 +82,14 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
     for (int i = 0; i < PNR; ++i) mbar_init(&S.rfull[i], 1);
     mbar_init(&S.sfull[0], 1); mbar_init(&S.sfull[1], 1);
     S.slow_cnt = 0;
-    S.bkeep[0] = 0; S.bkeep[1] = 0;
     fence_barrier_init();
   }
   __syncthreads();
+
+  int ppar[C];                                    // parity of the plane base c * rows: lead = (ppar ^ row) & 1
+#pragma unroll
+  for (int c = 0; c < C; ++c) ppar[c] = (int)(((long long)J.scg_cols[c] * rows) & 1);
+  const int ypar = (int)(((long long)J.rhc_col * rows) & 1);
 
   // ---- producer state (thread 0 only) -----------------------------------------------------------
   int p_iv = 0;
@@ -98,43 +99,42 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
     const scgrhc_interval I = J.intervals[iv];
     p_cand0 = I.cand0; p_row0 = I.row0; p_nwin = I.n_win; p_rec = I.rec_id;
   };
-  // one plane window -> shared memory: 16-byte aligned start (the element before when the offset is odd), even length
-  auto plane_bytes = [&](long long e0) { return (uint32_t)((((long long)W + (e0 & 1) + 1) & ~1LL) * 8); };
-  auto plane_ok = [&](long long e0) { return (e0 - (e0 & 1)) * 8 + plane_bytes(e0) <= (unsigned long long)J.arena_capacity_bytes; };
+  // one plane window -> shared memory: 16-byte aligned start (the element before when the offset is odd), even length.
+  // A window within two rows of the end of the planes takes cooperative plain loads instead (the copy of the LAST plane
+  // would read past the arena; for the other planes the one-element overshoot lands in the next plane, harmlessly).
+  const uint32_t bytes_even = (uint32_t)(((W + 1) & ~1) * 8), bytes_odd = (uint32_t)(((W + 2) & ~1) * 8);
+  const bool tail_ok = (long long)J.arena_capacity_bytes >= (long long)J.nsig * rows * 8 + 16;   // room behind the last plane
   auto issue_rhc = [&](long long item, int s) {
     const long long cand = use_list ? J.kept_list[item] : item;
     while (cand >= p_cand0 + p_nwin) load_iv(++p_iv);
     const int i = (int)(cand - p_cand0);
+    const long long row = p_row0 + (long long)i * wstride;
+    const bool fb = !tail_ok && row + W + 2 > rows;
     PMeta m;
-    m.cand = cand; m.slot = use_list ? item : cand; m.row = p_row0 + (long long)i * wstride; m.win = i; m.rec = p_rec; m.pad = 0;
-    const long long e0 = (long long)J.rhc_col * rows + m.row;
-    m.fallback = plane_ok(e0) ? 0 : 1;
+    m.cand = cand; m.rowf = row | (fb ? kPFallback : 0);
     S.rmeta[s] = m;
-    if (m.fallback) {
+    S.raux[s] = make_int2(i, p_rec);
+    if (fb) {
       mbar_arrive(&S.rfull[s]);
     } else {
-      const uint32_t bytes = plane_bytes(e0);
+      const int lead = (ypar ^ (int)row) & 1;
+      const uint32_t bytes = lead ? bytes_odd : bytes_even;
       mbar_arrive_expect_tx(&S.rfull[s], bytes);
-      bulk_g2s(rbase + (size_t)s * wpad, J.arena + (e0 - (e0 & 1)), bytes, &S.rfull[s]);
+      bulk_g2s(rbase + (size_t)s * wpad, yplane + (row - lead), bytes, &S.rfull[s]);
     }
   };
-  auto issue_scg = [&](const PMeta& m, int s) {      // returns through S.bkeep[s]: 1 = bulk copies in flight, 2 = plain loads
-    bool ok = true;
-    uint32_t total = 0;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const long long e0 = (long long)J.scg_cols[c] * rows + m.row;
-      ok = ok && plane_ok(e0);
-      total += plane_bytes(e0);
-    }
+  auto issue_scg = [&](const PMeta& m, int s) {      // the SCG planes of a kept window; plain loads in phase B if the item is at the edge
     S.bmeta[s] = m;
-    if (!ok) { S.bkeep[s] = 2; return; }
-    S.bkeep[s] = 1;
-    mbar_arrive_expect_tx(&S.sfull[s], total);
+    if (m.rowf & kPFallback) return;
+    const long long row = m.rowf;
+    int odd = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) odd += (ppar[c] ^ (int)row) & 1;
+    mbar_arrive_expect_tx(&S.sfull[s], (uint32_t)C * bytes_even + (uint32_t)odd * (bytes_odd - bytes_even));
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const long long e0 = (long long)J.scg_cols[c] * rows + m.row;
-      bulk_g2s(sbase + ((size_t)s * C + c) * wpad, J.arena + (e0 - (e0 & 1)), plane_bytes(e0), &S.sfull[s]);
+      const int lead = (ppar[c] ^ (int)row) & 1;
+      bulk_g2s(sbase + ((size_t)s * C + c) * wpad, xplane[c] + (row - lead), lead ? bytes_odd : bytes_even, &S.sfull[s]);
     }
   };
   if (tid == 0) {
@@ -159,19 +159,15 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
   auto pair_ok = [&](int k, int p) { return WCT > 0 ? ((k + 1) * NTH <= (WCT + 1) / 2 || p < (WCT + 1) / 2) : (p < npairs); };
   auto has_second = [&](int k, int p) { return WCT > 0 ? (WCT % 2 == 0 || (k + 1) * NTH <= WCT / 2 || 2 * p + 1 < WCT) : (2 * p + 1 < W); };
   auto has_third = [&](int k, int p) { return WCT > 0 ? ((k + 1) * NTH < (WCT + 1) / 2 - (WCT % 2) || 2 * p + 2 < WCT) : (2 * p + 2 < W); };
-  int ppar[C];                                    // parity of the plane base c * rows: lead = (ppar ^ row) & 1
-#pragma unroll
-  for (int c = 0; c < C; ++c) ppar[c] = (int)(((long long)J.scg_cols[c] * rows) & 1);
-  const int ypar = (int)(((long long)J.rhc_col * rows) & 1);
 
   uint32_t spar[2] = {0u, 0u};
+  uint32_t khist = 0u;        // bit k: the item of iteration j - 1 - k was kept (its SCG planes were requested)
   int rs = 0;                 // RHC slot of item j: j % PNR, parity (j / PNR) & 1
   uint32_t rparity = 0u;
   for (long long j = 0; j < cnt + 2; ++j) {
     const int s = (int)(j & 1);
     const bool doA = j < cnt;
-    const int bstate = (j >= 2) ? S.bkeep[s] : 0;      // written by thread 0 two iterations ago, before that iteration's end barrier
-    const bool doB = bstate != 0;
+    const bool doB = ((khist >> 1) & 1u) != 0;         // the (CTA-uniform) decision of iteration j - 2
 
     // ================= phase A, before the barrier: RHC window -> registers, per-thread statistics ==================
     PMeta MA;
@@ -181,9 +177,10 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
       mbar_wait(&S.rfull[rs], rparity);
       MA = S.rmeta[rs];
       double* buf = rbase + (size_t)rs * wpad;
-      const int lead = (ypar ^ (int)MA.row) & 1;
-      if (MA.fallback) {
-        for (int e = tid; e < W; e += NTH) buf[lead + e] = yplane[MA.row + e];
+      const long long rowA = MA.rowf & ~kPFallback;
+      const int lead = (ypar ^ (int)rowA) & 1;
+      if (MA.rowf & kPFallback) {
+        for (int e = tid; e < W; e += NTH) buf[lead + e] = yplane[rowA + e];
         __syncthreads();
       }
       const double* win = buf + lead;
@@ -250,21 +247,22 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
     if (doB) {
       MB = S.bmeta[s];
       double* buf = sbase + (size_t)s * C * wpad;
-      if (bstate == 1) {
+      const long long rowB = MB.rowf & ~kPFallback;
+      if (!(MB.rowf & kPFallback)) {
         mbar_wait(&S.sfull[s], spar[s]);
         spar[s] ^= 1u;
       } else {                                   // capacity edge: plain loads
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          const int lead = (ppar[c] ^ (int)MB.row) & 1;
-          for (int e = tid; e < W; e += NTH) buf[(size_t)c * wpad + lead + e] = xplane[c][MB.row + e];
+          const int lead = (ppar[c] ^ (int)rowB) & 1;
+          for (int e = tid; e < W; e += NTH) buf[(size_t)c * wpad + lead + e] = xplane[c][rowB + e];
         }
         __syncthreads();
       }
       double a_smin = CUDART_INF, a_smax = -CUDART_INF, nanacc = 0.0;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const int lead = (ppar[c] ^ (int)MB.row) & 1;
+        const int lead = (ppar[c] ^ (int)rowB) & 1;
         const double* win = buf + (size_t)c * wpad + lead;
 #pragma unroll
         for (int k = 0; k < PR; ++k) {
@@ -344,7 +342,7 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
         if (run || s2_bad) {                    // CTA-uniform and rare: exact work on the RHC window still in shared memory
           if (warp == 0 && lane < NWORDS) S.a24[lane] = a24;
           __syncthreads();
-          const double* win = rbase + (size_t)rs * wpad + ((ypar ^ (int)MA.row) & 1);
+          const double* win = rbase + (size_t)rs * wpad + ((ypar ^ (int)MA.rowf) & 1);
           int c = 0, fl = 0;
           if (run) {
             for (int k = 0; k < PR; ++k) {
@@ -394,8 +392,9 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
           double2* mm = reinterpret_cast<double2*>(P.out.minmax + 4 * MA.cand);
           if (!keep) mm[0] = make_double2(qnan, qnan);   // the SCG planes of a rejected window are never read
           mm[1] = make_double2(ymin, ymax);
-          P.out.cand_win[MA.cand] = MA.win;
-          P.out.cand_rec[MA.cand] = MA.rec;
+          const int2 aux = S.raux[rs];
+          P.out.cand_win[MA.cand] = aux.x;
+          P.out.cand_rec[MA.cand] = aux.y;
           if (!keep_all && (reason & SCGRHC_REASON_NONFINITE) && !(reason & SCGRHC_REASON_FLAT)) {
             atomicOr(P.err, 1ull);
             atomicMin(P.err + 1, (unsigned long long)MA.cand);
@@ -409,15 +408,15 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
       // two producers, in different warps, so that neither serial section sits alone on the iteration's critical path:
       // thread 0 refills the RHC slot (it owns the interval cursor), thread 32 issues the SCG planes of the kept window
       if (tid == 0 && j + PNR < cnt) issue_rhc(lo + j + PNR, rs);    // RHC slot rs is in registers everywhere
-      if (tid == 32) {
-        if (keep) issue_scg(MA, s); else S.bkeep[s] = 0;
-      }
+      if (tid == 32 && keep) issue_scg(MA, s);
+      khist = (khist << 1) | (keep ? 1u : 0u);
       if (keep && !pred_only) {
         if (norm_global) { ymin = J.global_minmax[2]; ymax = J.global_minmax[3]; }
         Normaliser nr;
         nr.init(ymin, ymax);
-        OutT* ro = reinterpret_cast<OutT*>(P.out.rhc_out) + (size_t)MA.slot * W;
-        const bool vec = (WCT > 0 && WCT % 2 == 0) || (((size_t)MA.slot * W) & 1) == 0;     // 8-byte aligned pair stores
+        const long long slotA = use_list ? lo + j : MA.cand;
+        OutT* ro = reinterpret_cast<OutT*>(P.out.rhc_out) + (size_t)slotA * W;
+        const bool vec = (WCT > 0 && WCT % 2 == 0) || (((size_t)slotA * W) & 1) == 0;     // 8-byte aligned pair stores
         bool redo = true;
         if constexpr (sizeof(OutT) == 4) {
           if (!use_list && !norm_global && nr.quick) {         // tier 1, see window_kernel.cuh
@@ -455,8 +454,8 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
           }
         }
       }
-    } else if (tid == 32) {
-      S.bkeep[s] = 0;                                        // drain iterations: nothing enters the pipeline any more
+    } else {
+      khist <<= 1;                                           // drain iterations: nothing enters the pipeline any more
     }
 
     // ================= phase B, after the barrier: normalise the SCG block from registers, store =======================
@@ -486,14 +485,15 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
         if (norm_global) { smin = J.global_minmax[0]; smax = J.global_minmax[1]; }
         Normaliser ns;
         ns.init(smin, smax);
-        OutT* so = reinterpret_cast<OutT*>(P.out.scg_out) + (size_t)MB.slot * C * W;
+        const long long slotB = use_list ? lo + j - 2 : MB.cand;
+        OutT* so = reinterpret_cast<OutT*>(P.out.scg_out) + (size_t)slotB * C * W;
         bool redo = true;
         if constexpr (sizeof(OutT) == 4) {
           if (!use_list && !norm_global && ns.quick) {
             uint32_t acc = 0xffffffffu;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-              const bool vec = (WCT > 0 && WCT % 2 == 0) || ((((size_t)MB.slot * C + c) * W) & 1) == 0;
+              const bool vec = (WCT > 0 && WCT % 2 == 0) || ((((size_t)slotB * C + c) * W) & 1) == 0;
 #pragma unroll
               for (int k = 0; k < PR; ++k) {
                 const int p = tid + k * NTH;
