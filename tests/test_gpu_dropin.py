@@ -205,6 +205,9 @@ def test_streamed_ingest_equals_eager_ingest(tmp_path, monkeypatch):
     monkeypatch.setenv('SCGRHC_LAZY_MIN_RECORDS', '1' if cfg == 'waveform_06' else '4096')   # both ingests through the public entry
     st, _ = recordutil.prepare_cohort(params, record_names=names)
     assert st.n_kept == b.n_kept and torch.equal(st.materialise()[0], y[0])
+  # a rank whose block of records is empty (more ranks than records) still returns a well-formed, empty store
+  empty = recordutil._prepare_eager(params, [], names, len(names), C, dev, 2, None)
+  assert empty.n_kept == 0 and empty.n_cand == 0 and empty.kept_idx.numel() == 0 and empty.materialise()[0].shape[0] == 0
   # a record that lists its signals in another order: not one frame layout -> the streamed ingest declines
   p = synth_ref.gen_record(H.SEED, 799, 20000, kinds=synth_ref.kinds_for(sig))
   order = [3, 0, 1, 2, 4]
