@@ -234,6 +234,11 @@ static int dispatch_nsig(scgrhc_ctx* ctx, const KParams& P, long long items, cud
     }
     return dispatch_out<C, true, false>(ctx, P, items, st);
   }
+  if constexpr (C != 3) {                 // the drop-in uploads exactly the selected columns, in order, then RHC: compile-time row layout
+    bool ident = J.nsig == C + 1 && J.rhc_col == C;
+    for (int c = 0; c < C; ++c) ident = ident && J.scg_cols[c] == c;
+    if (ident) return dispatch_out<C, false, true>(ctx, P, items, st);
+  }
   return dispatch_out<C, false, false>(ctx, P, items, st);
 }
 

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(NT, DECIM ? 5 : 4) window_kernel(const __grid_
   static_assert(SCGRHC_FLAT_WIN == 50, "run detection below is hard-wired to 49 = 32 + 16 + 1 pairs");
   constexpr int R = WCT > 0 ? (WCT + NT - 1) / NT : (WCT < 0 ? -WCT : RMAX);
   static_assert(R * NWARP <= 32 && R <= RMAX, "one mask word per lane");
-  static_assert(!IDENT || (NSIG4 && C == 3), "identity mapping is the 3 SCG + RHC record");
+  static_assert(!IDENT || !NSIG4 || C == 3, "identity mapping: rows are exactly the C SCG columns followed by RHC (nsig == C + 1)");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Scratch& S = *reinterpret_cast<Scratch*>(smem_raw);
   double* stage_base = reinterpret_cast<double*>(smem_raw + ((sizeof(Scratch) + 127) & ~size_t(127)));
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(NT, DECIM ? 5 : 4) window_kernel(const __grid_
   const scgrhc_job& J = P.job;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = WCT > 0 ? WCT : J.W;
-  const int nsig = NSIG4 ? 4 : J.nsig;
+  const int nsig = NSIG4 ? 4 : (IDENT ? C + 1 : J.nsig);   // IDENT: what the drop-in uploads (the selected columns, in order, then RHC)
   const int nstage = P.stages;
   const int wstride = J.stride > 0 ? J.stride : W;
   const bool use_list = (J.flags & SCGRHC_USE_KEPT_LIST) != 0;
@@ -540,10 +540,15 @@ __global__ void __launch_bounds__(NT, DECIM ? 5 : 4) window_kernel(const __grid_
           }
         } else {
           const double* row = win + (size_t)t * nsig;
+          if constexpr (IDENT && C == 1) {           // 16-byte rows: one load for (x, y)
+            const double2 xy = *reinterpret_cast<const double2*>(row);
+            x[k][0] = xy.x; y[k] = xy.y; yn[k] = row[3];
+          } else {
 #pragma unroll
-          for (int c = 0; c < C; ++c) x[k][c] = row[col[c]];
-          y[k] = row[rcol];
-          yn[k] = row[nsig + rcol];
+            for (int c = 0; c < C; ++c) x[k][c] = row[col[c]];
+            y[k] = row[rcol];
+            yn[k] = row[nsig + rcol];
+          }
         }
       }
     }
