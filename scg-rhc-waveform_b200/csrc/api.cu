@@ -215,6 +215,7 @@ template <int C, bool NSIG4, bool IDENT, typename OutT>
 static int dispatch_w(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
   if (P.job.W == 750) return launch_window<C, NSIG4, IDENT, OutT, 750>(ctx, P, items, st);  // int(1.5 * 500): all 37 configs
   if constexpr (NSIG4 && sizeof(OutT) == 4) {
+    if (P.job.W == 375) return launch_window<C, NSIG4, IDENT, OutT, 375>(ctx, P, items, st);    // 1.5 s at 250 Hz: compile-time length
     if (P.job.W <= 3 * NT) return launch_window<C, NSIG4, IDENT, OutT, -3>(ctx, P, items, st);  // resampled cohorts (1.5 s at <= 250 Hz)
   }
   return launch_window<C, NSIG4, IDENT, OutT, 0>(ctx, P, items, st);
@@ -332,9 +333,9 @@ extern "C" int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, co
 }
 
 // ---- the same with the decimating front end (extension): native-rate arena -> model-rate windows inside the kernel --------
-template <int C, bool IDENT, int DDOWN, int DPP, bool DFMA>
+template <int C, bool IDENT, int DDOWN, int DPP, bool DFMA, int WCT = -3>
 static int launch_window_decim_t(scgrhc_ctx* ctx, const KParamsDecim& P, long long items, cudaStream_t st) {
-  auto kern = window_kernel<C, true, IDENT, float, -3, true, DDOWN, DPP, DFMA>;
+  auto kern = window_kernel<C, true, IDENT, float, WCT, true, DDOWN, DPP, DFMA>;
   const size_t smem = ((sizeof(Scratch) + 127) & ~size_t(127)) +
                       ((size_t)P.k.stage_elems + (size_t)(P.k.job.W + 1) * 4 + kDecimMaxTaps) * sizeof(double);
   CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -350,8 +351,11 @@ static int launch_window_decim_t(scgrhc_ctx* ctx, const KParamsDecim& P, long lo
 
 template <int C, bool IDENT>
 static int launch_window_decim(scgrhc_ctx* ctx, const KParamsDecim& P, long long items, bool fma, cudaStream_t st) {
-  if (P.d.down == 2 && P.d.pp == 43)                     // 500 -> 250 Hz, scipy's kaiser-5 design: unrolled, taps as constant operands
+  if (P.d.down == 2 && P.d.pp == 43) {                   // 500 -> 250 Hz, scipy's kaiser-5 design: unrolled, taps as constant operands
+    if (P.k.job.W == 375)                                // ... and 1.5 s windows: compile-time length
+      return fma ? launch_window_decim_t<C, IDENT, 2, 43, true, 375>(ctx, P, items, st) : launch_window_decim_t<C, IDENT, 2, 43, false, 375>(ctx, P, items, st);
     return fma ? launch_window_decim_t<C, IDENT, 2, 43, true>(ctx, P, items, st) : launch_window_decim_t<C, IDENT, 2, 43, false>(ctx, P, items, st);
+  }
   return fma ? launch_window_decim_t<C, IDENT, 0, 0, true>(ctx, P, items, st) : launch_window_decim_t<C, IDENT, 0, 0, false>(ctx, P, items, st);
 }
 

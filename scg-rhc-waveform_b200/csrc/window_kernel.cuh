@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(256) selftest_div_kernel(unsigned long long se
 template <int C, bool NSIG4, bool IDENT, typename OutT, int WCT, bool DECIM = false, int DDOWN = 0, int DPP = 0, bool DFMA = false>
 __global__ void __launch_bounds__(NT, DECIM ? 5 : 4) window_kernel(const __grid_constant__ typename KParamsOf<DECIM>::type PP) {
   const KParams& P = kparams_base(PP);
-  static_assert(!DECIM || (NSIG4 && WCT < 0 && -WCT <= kDecimR), "the decimating front end feeds the 4-signal, <= 3 rows per thread variant");
+  static_assert(!DECIM || (NSIG4 && ((WCT < 0 && -WCT <= kDecimR) || (WCT > 0 && (WCT + NT - 1) / NT <= kDecimR))),
+                "the decimating front end feeds the 4-signal, <= 3 rows per thread variants");
   static_assert(SCGRHC_FLAT_WIN == 50, "run detection below is hard-wired to 49 = 32 + 16 + 1 pairs");
   constexpr int R = WCT > 0 ? (WCT + NT - 1) / NT : (WCT < 0 ? -WCT : RMAX);
   static_assert(R * NWARP <= 32 && R <= RMAX, "one mask word per lane");
