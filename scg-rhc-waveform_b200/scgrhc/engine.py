@@ -107,26 +107,52 @@ class Plan:
     return self._dev
 
 
-def plan_cohort(metas, chamber, T_rows, W, record_names=None, stride=0, fs=0.0, rec0=0):
+class EventTabs:
+  """The chamber-independent part of planning a cohort, once: event times of every side-car flattened into one array with
+  per-record offsets, and the chamber prefix ``key.split('_')[0]`` of every event (recordutil.py:100-108).  A sweep plans
+  the same cohort once per chamber; with this table a plan is one vectorised string compare + one C call."""
+
+  def __init__(self, metas):
+    times, prefix, is_end, off = [], [], [], [0]
+    for meta in metas:
+      kt = event_times(meta)
+      if kt is not None and len(kt[1]) >= 2:
+        times.append(kt[1])
+        prefix.extend(k.split('_')[0] for k in kt[0])
+        is_end.extend(k == 'END' for k in kt[0])
+        off.append(off[-1] + len(kt[0]))
+      else:
+        off.append(off[-1])
+    self.n_rec = len(metas)
+    self.times = np.ascontiguousarray(np.concatenate(times), dtype=np.float64) if times else np.zeros(0, dtype=np.float64)
+    self.prefix = np.array(prefix, dtype=object) if prefix else np.zeros(0, dtype=object)
+    self.is_end = np.array(is_end, dtype=bool) if is_end else np.zeros(0, dtype=bool)
+    self.off = np.asarray(off, dtype=np.int64)
+
+  def match(self, chamber):
+    """uint8 per event: does it open an interval of ``chamber`` ('*' = every chamber event, the waveform_01 extension)."""
+    if chamber == '*':
+      return np.ascontiguousarray(~self.is_end, dtype=np.uint8)
+    return np.ascontiguousarray(self.prefix == chamber, dtype=np.uint8)
+
+
+def event_tabs(metas):
+  return EventTabs(metas)
+
+
+def plan_cohort(metas, chamber, T_rows, W, record_names=None, stride=0, fs=0.0, rec0=0, tabs=None):
   """Plan for records stored back to back in the arena; ``T_rows[r]`` rows each.  One C call for the whole cohort
   (`scgrhc_plan_cohort`).  ``rec0``: record number of the first record (a rank's shard of a larger cohort reports global
-  record ids)."""
-  times, match, off = [], [], [0]
-  for meta in metas:
-    tab = event_table(meta, chamber)
-    if tab is not None and len(tab[0]) >= 2:
-      times.append(tab[0]); match.append(tab[1])
-      off.append(off[-1] + len(tab[0]))
-    else:
-      off.append(off[-1])
+  record ids).  ``tabs``: an ``EventTabs`` of the same side-cars, when several plans are made of one cohort."""
+  if tabs is None:
+    tabs = EventTabs(metas)
+  t, m, off = tabs.times, tabs.match(chamber), tabs.off
   n_rec = len(metas)
   names = list(record_names) if record_names is not None else []
   if off[-1] == 0:
     return Plan(np.zeros(0, dtype=INTERVAL_DTYPE), 0, W, names, stride)
-  t = np.ascontiguousarray(np.concatenate(times), dtype=np.float64)
-  m = np.ascontiguousarray(np.concatenate(match), dtype=np.uint8)
-  o = np.asarray(off, dtype=np.int64)
-  rows = np.ascontiguousarray(np.asarray([int(v) for v in T_rows[:n_rec]], dtype=np.int64))
+  o = off
+  rows = np.ascontiguousarray(np.asarray(T_rows[:n_rec], dtype=np.int64))
   cap = int(m.sum())
   out = np.zeros(max(cap, 1), dtype=INTERVAL_DTYPE)
   n_out, n_cand = C.c_int64(0), C.c_int64(0)

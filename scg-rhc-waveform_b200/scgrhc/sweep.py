@@ -28,13 +28,14 @@ def iter_sweep(arena, sig_name, metas, record_rows, configs, out_dtype=torch.flo
   process ``group`` every rank must iterate the same configs in the same order (they do: the order is a function of
   ``configs`` alone), because configs with ``use_global_min_max`` all-reduce inside."""
   plans = {}
+  tabs = engine.event_tabs(metas)          # event times of every side-car, once for all chambers
   order = sorted(configs, key=lambda k: (str(configs[k].chamber), float(configs[k].segment_size), k))
 
   def plan_for(c):
     W = int(c.segment_size * SAMPLE_FREQ)
     key = (c.chamber, W)
     if key not in plans:
-      plans[key] = engine.plan_cohort(metas, c.chamber, record_rows, W, rec0=rec0)
+      plans[key] = engine.plan_cohort(metas, c.chamber, record_rows, W, rec0=rec0, tabs=tabs)
     return plans[key]
 
   groups = {}
