@@ -367,8 +367,8 @@ def get_record_names():
 
 
 def _read_meta(record_name):
-  with open(os.path.join(PROCESSED_DATA_PATH, f'{record_name}.json'), 'r') as f:
-    return json.load(f)
+  with open(os.path.join(PROCESSED_DATA_PATH, f'{record_name}.json'), 'rb') as f:
+    return json.loads(f.read())
 
 
 def get_chamber_intervals(record_name, chamber):
