@@ -196,9 +196,9 @@ extern "C" int scgrhc_plan_cohort(const double* event_time, const uint8_t* event
 }
 
 // ---- hot path launcher -------------------------------------------------------------------------------
-template <int C, bool NSIG4, bool IDENT, typename OutT, int WCT>
+template <int C, bool NSIG4, bool IDENT, typename OutT, int WCT, bool PLAIN = false>
 static int launch_window(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
-  auto kern = window_kernel<C, NSIG4, IDENT, OutT, WCT>;
+  auto kern = window_kernel<C, NSIG4, IDENT, OutT, WCT, false, 0, 0, false, PLAIN>;
   const size_t smem = ((sizeof(Scratch) + 127) & ~size_t(127)) + (size_t)P.stages * P.stage_elems * sizeof(double);
   CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
@@ -213,7 +213,13 @@ static int launch_window(scgrhc_ctx* ctx, const KParams& P, long long items, cud
 
 template <int C, bool NSIG4, bool IDENT, typename OutT>
 static int dispatch_w(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
-  if (P.job.W == 750) return launch_window<C, NSIG4, IDENT, OutT, 750>(ctx, P, items, st);  // int(1.5 * 500): all 37 configs
+  if (P.job.W == 750) {                                                                       // int(1.5 * 500): all 37 configs
+    constexpr unsigned kModes = SCGRHC_USE_KEPT_LIST | SCGRHC_PREDICATES_ONLY | SCGRHC_NORM_GLOBAL | SCGRHC_KEEP_ALL | SCGRHC_NORM_ZSCORE;
+    if constexpr (IDENT && sizeof(OutT) == 4) {          // what save_dataloaders launches: no mode flag, fp32, the uploaded column layout
+      if ((P.job.flags & kModes) == 0) return launch_window<C, NSIG4, IDENT, OutT, 750, true>(ctx, P, items, st);
+    }
+    return launch_window<C, NSIG4, IDENT, OutT, 750>(ctx, P, items, st);
+  }
   if constexpr (NSIG4 && sizeof(OutT) == 4) {
     if (P.job.W == 375) return launch_window<C, NSIG4, IDENT, OutT, 375>(ctx, P, items, st);    // 1.5 s at 250 Hz: compile-time length
     if (P.job.W <= 3 * NT) return launch_window<C, NSIG4, IDENT, OutT, -3>(ctx, P, items, st);  // resampled cohorts (1.5 s at <= 250 Hz)

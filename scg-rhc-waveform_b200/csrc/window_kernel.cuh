@@ -239,7 +239,11 @@ __global__ void __launch_bounds__(256) selftest_div_kernel(unsigned long long se
 // taps are immediate constant-bank operands and the pad-row bookkeeping folds away (500 -> 250 Hz: down 2, 43 taps).
 // DFMA (DECIM only): one fused multiply-add per tap instead of a separately rounded multiply and add — half the fp64
 // instructions, within ~1e-15 of scipy instead of bit-identical (the `fused` mode of scgrhc_resample_poly).
-template <int C, bool NSIG4, bool IDENT, typename OutT, int WCT, bool DECIM = false, int DDOWN = 0, int DPP = 0, bool DFMA = false>
+// PLAIN: the job has no mode flag set (not USE_KEPT_LIST / PREDICATES_ONLY / NORM_GLOBAL / KEEP_ALL / NORM_ZSCORE): the one-pass
+// local-min-max job of save_dataloaders.  The mode tests then fold away at compile time instead of being uniform branches in
+// the per-window loop.
+template <int C, bool NSIG4, bool IDENT, typename OutT, int WCT, bool DECIM = false, int DDOWN = 0, int DPP = 0, bool DFMA = false,
+          bool PLAIN = false>
 __global__ void __launch_bounds__(NT, DECIM ? 5 : 4) window_kernel(const __grid_constant__ typename KParamsOf<DECIM>::type PP) {
   const KParams& P = kparams_base(PP);
   static_assert(!DECIM || (NSIG4 && ((WCT < 0 && -WCT <= kDecimR) || (WCT > 0 && (WCT + NT - 1) / NT <= kDecimR))),
@@ -258,11 +262,11 @@ __global__ void __launch_bounds__(NT, DECIM ? 5 : 4) window_kernel(const __grid_
   const int nsig = NSIG4 ? 4 : (IDENT ? C + 1 : J.nsig);   // IDENT: what the drop-in uploads (the selected columns, in order, then RHC)
   const int nstage = P.stages;
   const int wstride = J.stride > 0 ? J.stride : W;
-  const bool use_list = (J.flags & SCGRHC_USE_KEPT_LIST) != 0;
-  const bool pred_only = (J.flags & SCGRHC_PREDICATES_ONLY) != 0;
-  const bool norm_global = (J.flags & SCGRHC_NORM_GLOBAL) != 0;
-  const bool keep_all = (J.flags & SCGRHC_KEEP_ALL) != 0;
-  const bool zscore = (J.flags & SCGRHC_NORM_ZSCORE) != 0;
+  const bool use_list = !PLAIN && (J.flags & SCGRHC_USE_KEPT_LIST) != 0;
+  const bool pred_only = !PLAIN && (J.flags & SCGRHC_PREDICATES_ONLY) != 0;
+  const bool norm_global = !PLAIN && (J.flags & SCGRHC_NORM_GLOBAL) != 0;
+  const bool keep_all = !PLAIN && (J.flags & SCGRHC_KEEP_ALL) != 0;
+  const bool zscore = !PLAIN && (J.flags & SCGRHC_NORM_ZSCORE) != 0;
   const double thr = J.flat_threshold, min_rhc = J.min_rhc;
   const int rcol = IDENT ? C : J.rhc_col;
   int col[C];
