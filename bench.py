@@ -9,7 +9,8 @@ A *step* is one pass of the hot path over one synthetic cohort per GPU: BASELINE
 (waveform_01, which BASELINE names, has no `chamber` key and cannot be run by the reference either —
 SURVEY.md §0; waveform_06 is the first config the reference loads and has the same 3-axis shape).
 
-  value      kept windows/s, records resident in HBM when the timed region starts (whole job, all GPUs)
+  value      kept windows/s, records resident in HBM (planar layout: one fp64 plane per signal) when the timed region starts
+             (whole job, all GPUs); roofline.interleaved_variant = the same step on wfdb's interleaved p_signal rows
   e2e        the same metric through the public host API (pinned host records -> H2D -> hot path ->
              D2H of the kept-window list); windows stay device-resident by design (the trainer reads them there).
              Sub-legs: fmt16 (int16 frames as stored on disk), dropin (format-16 files on tmpfs ->
@@ -86,6 +87,7 @@ def config_dict(n_rec, gpus, out_f64=False):
   """The SAME dict from both arms (the driver compares them): only quantities that follow from the command line."""
   return {'workload': workload_name(n_rec), 'records_per_gpu': n_rec, 'candidate_windows_per_step': n_rec * 400 * gpus,
           'out_dtype': 'f64' if out_f64 else 'f32', 'params': 'waveform_06',
+          'hbm_layout': 'planar (one fp64 plane per signal, as the device decode of the on-disk format writes it); roofline.interleaved_variant = wfdb p_signal rows',
           'l2': 'inputs %.1f GB + outputs up to %.1f GB per step per GPU, far larger than the 126 MB L2: no flush needed'
                 % (n_rec * T_ROWS * 4 * 8 / 1e9, n_rec * 400 * W * 4 * (8 if out_f64 else 4) / 1e9)}
 
@@ -437,6 +439,11 @@ def run_b200(args):
   C = len(IN_CHANNELS)
   cols, rcol = scgrhc.resolve_columns(SIG, IN_CHANNELS)
   lo = rank * n_rec                                           # weak scaling: every rank owns n_rec records
+  # the cohort resident in HBM twice: `planes` = one plane per signal (SCGRHC_ARENA_PLANAR, the layout the device decode of the
+  # on-disk format writes and the headline step reads), `arena` = wfdb's interleaved (rows, nsig) p_signal layout (what fp64
+  # host arrays look like; read by the optional stages, the fp64 end-to-end leg and the interleaved comparison step)
+  planes = torch.empty((len(SIG), n_rec * T_ROWS), dtype=torch.float64, device=dev)
+  ops.synth_records(planes, SEED, lo, n_rec, T_ROWS, KINDS, 16, W, n_rec * T_ROWS)
   arena = torch.empty((n_rec * T_ROWS, len(SIG)), dtype=torch.float64, device=dev)
   ops.synth_records(arena, SEED, lo, n_rec, T_ROWS, KINDS, 16, W)
   plan = scgrhc.plan_uniform(meta(), 'PA', T_ROWS, W, n_rec, rec0=lo)
@@ -457,6 +464,10 @@ def run_b200(args):
   n_kept_t = torch.zeros(1, dtype=torch.int64, device=dev)
 
   def kernel_step():
+    ops.process_windows(planes, iv, n, W, 0, cols, rcol, MIN_RHC, 1e-3, flags | N.ARENA_PLANAR, [0.0] * 4, None, 0,
+                        scg, rhc, minmax, keep, reason, cand_win, cand_rec)
+
+  def interleaved_step():
     ops.process_windows(arena, iv, n, W, 0, cols, rcol, MIN_RHC, 1e-3, flags, [0.0] * 4, None, 0,
                         scg, rhc, minmax, keep, reason, cand_win, cand_rec)
 
@@ -534,7 +545,7 @@ def run_b200(args):
   achieved = alg / (ms_kernel * 1e-3) / 1e9
   traffic, traffic_src = None, None
   try:
-    with open(os.path.join(ROOT, 'profiles', 'window_kernel_traffic.json')) as f:
+    with open(os.path.join(ROOT, 'profiles', 'window_planar_kernel_traffic.json')) as f:
       tj = json.load(f)
       traffic, traffic_src = tj.get('dram_bytes_per_launch'), tj.get('source')
   except Exception:
@@ -542,8 +553,9 @@ def run_b200(args):
   roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
               'traffic': traffic,
               'traffic_source': 'NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` '
-                                'capture of the same launch, stored in profiles/window_kernel_traffic.json (%s)' % traffic_src,
-              'kernel': 'scgrhc::window_kernel<C=3,NSIG4,IDENT,%s,W=750>' % ('double' if args.out_f64 else 'float'), 'kernel_ms': ms_kernel,
+                                'capture of the same launch, stored in profiles/window_planar_kernel_traffic.json (%s)' % traffic_src,
+              'kernel': 'scgrhc::window_planar_kernel<C=3,128,3,%s,W=750,PLAIN>' % ('double' if args.out_f64 else 'float'), 'kernel_ms': ms_kernel,
+              'layout': 'planar arena (one plane per signal): a candidate costs its RHC plane, a kept window additionally its SCG planes',
               'algorithmic_bytes_per_launch': alg, 'peak_source': peak_src,
               'bytes_per_kept_window': W * C * 8 + W * 8 + W * (C + 1) * out_bytes + 53}
   if sustained:
@@ -551,21 +563,18 @@ def run_b200(args):
     roofline['sustained_kernel_ms'] = sustained['kernel_ms_second_half']
     roofline['sustained_loop_s'] = sustained['seconds']
 
-  # ---- the same cohort in the PLANAR layout (opt-in: one plane per signal; RHC plane first, SCG planes of kept windows only;
-  #      DRAM traffic == algorithmic bytes): the same step with window_planar_kernel, burst and sustained ----
+  # ---- the same cohort in wfdb's INTERLEAVED (rows, nsig) layout (window_kernel): what the step costs when the records arrive as
+  #      fp64 p_signal arrays; a rejected window then drags its SCG columns through DRAM by sector (traffic 1.089 x algorithmic) ----
   if not args.no_sustained:
     try:
-      planes = torch.empty((len(SIG), n_rec * T_ROWS), dtype=torch.float64, device=dev)
-      ops.synth_records(planes, SEED, lo, n_rec, T_ROWS, KINDS, 16, W, n_rec * T_ROWS)
-      def planar_step():
-        ops.process_windows(planes, iv, n, W, 0, cols, rcol, MIN_RHC, 1e-3, flags | N.ARENA_PLANAR, [0.0] * 4, None, 0,
-                            scg, rhc, minmax, keep, reason, cand_win, cand_rec)
+      def inter_step():
+        interleaved_step()
       for _ in range(3):
-        planar_step()
+        inter_step()
       barrier()
       pe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
       for a, b in pe:
-        a.record(); planar_step(); b.record(); tail_step()
+        a.record(); inter_step(); b.record(); tail_step()
       torch.cuda.synchronize()
       ms_p = sum(a.elapsed_time(b) for a, b in pe) / len(pe)
       n_kept_p = int(n_kept_t.item())
@@ -574,26 +583,23 @@ def run_b200(args):
       for k in range(n_s):
         if k >= n_s // 2:
           pk[k - n_s // 2][0].record()
-        planar_step()
+        inter_step()
         if k >= n_s // 2:
           pk[k - n_s // 2][1].record()
         tail_step()
       torch.cuda.synchronize()
       ms_ps = sum(a.elapsed_time(b) for a, b in pk) / len(pk)
       launches[0] += (args.steps + n_s + 3) * 4
-      roofline['planar_variant'] = {
-          'kernel': 'scgrhc::window_planar_kernel<C=3,128,3,%s,W=750>' % ('double' if args.out_f64 else 'float'),
+      roofline['interleaved_variant'] = {
+          'kernel': 'scgrhc::window_kernel<C=3,NSIG4,IDENT,%s,W=750,PLAIN>' % ('double' if args.out_f64 else 'float'),
           'kernel_ms': ms_p, 'frac': alg / (ms_p * 1e-3) / 1e9 / peak, 'sustained_kernel_ms': ms_ps,
           'sustained_frac': alg / (ms_ps * 1e-3) / 1e9 / peak, 'same_kept_windows': n_kept_p == n_kept,
           'note': 'measured right after the sustained loop, i.e. with the board already at its power cap (its 20-step figure is therefore not a cold burst); '
-                  'opt-in layout (SCGRHC_ARENA_PLANAR): same cohort generated as one plane per signal, same outputs bit for bit; a rejected '
-                  'window costs its RHC plane only, so DRAM traffic equals the algorithmic bytes (ncu: 1.00 x, interleaved 1.089 x)'}
-      del planes
-      kernel_step(); tail_step()                     # the legs below read the interleaved step's outputs
+                  'same cohort, same outputs bit for bit, wfdb\'s interleaved (rows, nsig) layout: the kernel of fp64 host cohorts and of the optional stages'}
+      kernel_step(); tail_step()
       torch.cuda.synchronize()
     except Exception as exc:
-      roofline['planar_variant'] = {'error': str(exc)[:300]}
-    torch.cuda.empty_cache()
+      roofline['interleaved_variant'] = {'error': str(exc)[:300]}
 
   # ---- BASELINE configs[2]: batches of 256 kept windows for the trainer, through the loader the drop-in pickles
   #      (recordutil.WindowLoader: one scgrhc_collate_batch launch per batch, shuffled slots uploaded once per epoch) ----
@@ -1029,7 +1035,7 @@ def run_b200(args):
       e2e = dict(e2e or {}, error=str(exc)[:300])
 
   # the big buffers of the headline leg are no longer needed
-  del arena, scg, rhc, minmax, keep, reason, cand_win, cand_rec, kept_idx, start_idx, stop_idx, rec_id
+  del arena, planes, scg, rhc, minmax, keep, reason, cand_win, cand_rec, kept_idx, start_idx, stop_idx, rec_id
   torch.cuda.empty_cache()
   if not args.no_legs:
     for fn, key in ((leg_sweep, 'sweep36'), (leg_config4, 'config4_100k')):
@@ -1073,7 +1079,7 @@ def run_b200(args):
             'roofline': roofline, 'sustained': sustained, 'cpu_baseline': cpu, 'cpu_baseline_fast': cpu_fast_d, 'e2e': e2e,
             'gpu_launches': n_timed,
             'gpu_launches_all_legs': n_timed + launches[0] + (sustained['steps'] * 4 if sustained else 0),
-            'launches_per_step': 'window_kernel + count_kept + scan_blocks + scatter_kept',
+            'launches_per_step': 'window_planar_kernel + count_kept + scan_blocks + scatter_kept',
             'legs': legs, 'batch256': batch256, 'north_star_pipeline': pipeline, 'numa_bound_cpus': numa_cpus,
             'clocks': clocks, 'clocks_sustained': clocks_sustained, 'clocks_other_legs': clocks_other}
     sys.stdout.flush()

@@ -249,9 +249,9 @@ static int dispatch_nsig(scgrhc_ctx* ctx, const KParams& P, long long items, cud
   return dispatch_out<C, false, false>(ctx, P, items, st);
 }
 
-template <int C, int NTH, int PR, typename OutT, int WCT>
+template <int C, int NTH, int PR, typename OutT, int WCT, bool PLAIN = false>
 static int launch_planar(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
-  auto kern = window_planar_kernel<C, NTH, PR, OutT, WCT>;
+  auto kern = window_planar_kernel<C, NTH, PR, OutT, WCT, PLAIN>;
   const size_t smem = ((sizeof(PScratch<NTH>) + 127) & ~size_t(127)) + (size_t)(PNR + 2 * C) * P.stage_elems * sizeof(double);
   CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
@@ -265,7 +265,13 @@ static int launch_planar(scgrhc_ctx* ctx, const KParams& P, long long items, cud
 }
 template <int C, typename OutT>
 static int dispatch_planar_w(scgrhc_ctx* ctx, const KParams& P, long long items, cudaStream_t st) {
-  if (P.job.W == 750) return launch_planar<C, 128, 3, OutT, 750>(ctx, P, items, st);   // int(1.5 * 500): all 37 configs
+  if (P.job.W == 750) {                                                                  // int(1.5 * 500): all 37 configs
+    constexpr unsigned kModes = SCGRHC_USE_KEPT_LIST | SCGRHC_PREDICATES_ONLY | SCGRHC_NORM_GLOBAL | SCGRHC_KEEP_ALL;
+    if constexpr (sizeof(OutT) == 4) {
+      if ((P.job.flags & kModes) == 0) return launch_planar<C, 128, 3, OutT, 750, true>(ctx, P, items, st);
+    }
+    return launch_planar<C, 128, 3, OutT, 750>(ctx, P, items, st);
+  }
   if (P.job.W <= 384) return launch_planar<C, 64, 3, OutT, 0>(ctx, P, items, st);      // resampled cohorts: 375 samples, 2 warps per window
   if (P.job.W <= 768) return launch_planar<C, 128, 3, OutT, 0>(ctx, P, items, st);
   return launch_planar<C, 128, 4, OutT, 0>(ctx, P, items, st);

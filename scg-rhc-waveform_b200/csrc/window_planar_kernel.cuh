@@ -44,7 +44,8 @@ struct PScratch {
 
 // Window of W samples; NTH threads; every thread owns PR pairs (samples 2p, 2p+1 for p = tid + k*NTH): W <= 2*PR*NTH.
 // WCT > 0: compile-time window length (750 = int(1.5 * 500), all 37 configs): pair validity folds away; 0: runtime length.
-template <int C, int NTH, int PR, typename OutT, int WCT>
+// PLAIN: no mode flag besides the layout (see window_kernel): the mode tests fold away.
+template <int C, int NTH, int PR, typename OutT, int WCT, bool PLAIN = false>
 __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(const __grid_constant__ KParams P) {
   static_assert(WCT == 0 || (WCT + 1) / 2 <= PR * NTH, "window does not fit the pair grid");
   static_assert(SCGRHC_FLAT_WIN == 50, "run detection below is hard-wired to 24 full pairs inside 49 small steps");
@@ -62,10 +63,10 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
   const int W = WCT > 0 ? WCT : J.W;
   const long long rows = J.arena_rows;
   const int wstride = J.stride > 0 ? J.stride : W;
-  const bool use_list = (J.flags & SCGRHC_USE_KEPT_LIST) != 0;
-  const bool pred_only = (J.flags & SCGRHC_PREDICATES_ONLY) != 0;
-  const bool norm_global = (J.flags & SCGRHC_NORM_GLOBAL) != 0;
-  const bool keep_all = (J.flags & SCGRHC_KEEP_ALL) != 0;
+  const bool use_list = !PLAIN && (J.flags & SCGRHC_USE_KEPT_LIST) != 0;
+  const bool pred_only = !PLAIN && (J.flags & SCGRHC_PREDICATES_ONLY) != 0;
+  const bool norm_global = !PLAIN && (J.flags & SCGRHC_NORM_GLOBAL) != 0;
+  const bool keep_all = !PLAIN && (J.flags & SCGRHC_KEEP_ALL) != 0;
   const double thr = J.flat_threshold, min_rhc = J.min_rhc;
   const double* const yplane = J.arena + (long long)J.rhc_col * rows;
   const double* xplane[C];

@@ -281,7 +281,8 @@ def test_planar_arena_equals_interleaved(nsig, chans, W, out_dtype):
 
 
 def test_planar_digital_ingest_equals_interleaved_ingest():
-  """HostIngest(planar=True) decodes format-16 chunks into planar arenas; the interleaved decode + kernel gives the same store."""
+  """HostIngest decodes format-16 chunks into planar arenas (the default for digital cohorts); the interleaved decode + kernel
+  (planar=False) gives the same store."""
   from scgrhc.engine import HostIngest
   sig = synth_ref.DEFAULT_SIG_NAMES
   kinds = synth_ref.kinds_for(sig)
@@ -298,7 +299,8 @@ def test_planar_digital_ingest_equals_interleaved_ingest():
     for kw in (dict(), dict(use_global_min_max=True)):
       a = HostIngest(plan, rows, 4, DEV, chunk_records=chunk, digital_nsig=4, planar=False).run(hostd, [0, 1, 2], 3, -50.0, decode=([0, 1, 2, 3], gains, bases), **kw)
       ing = HostIngest(plan, rows, 4, DEV, chunk_records=chunk, digital_nsig=4, planar=True)
-      assert ing.planar and not HostIngest(plan, rows, 4, DEV, chunk_records=chunk, digital_nsig=4).planar
+      assert ing.planar and HostIngest(plan, rows, 4, DEV, chunk_records=chunk, digital_nsig=4).planar and \
+          not HostIngest(plan, rows, 4, DEV, chunk_records=chunk).planar          # default: on for digital cohorts only
       b = ing.run(hostd, [0, 1, 2], 3, -50.0, decode=([0, 1, 2, 3], gains, bases), **kw)
       _same_store(a, b)
       assert b.n_kept > 0
