@@ -602,11 +602,12 @@ __global__ void __launch_bounds__(NT, DECIM ? 5 : 4) window_kernel(const __grid_
       a_smin = warp_min(a_smin); a_smax = warp_max(a_smax);
       a_ymin = warp_min(a_ymin); a_ymax = warp_max(a_ymax);
       // 0*v is +-0 for finite v, so adding the accumulator leaves s2 unchanged unless some v is NaN/Inf
-      s1 = warp_sum(s1); s2 = warp_sum(__dadd_rn(s2, nanacc)); sxy = warp_sum(sxy);
+      const double s3 = warp_sum3(s1, __dadd_rn(s2, nanacc), sxy, lane);   // lane 0: s1, lane 8: s2, lane 16: sxy
+      double* r = S.red[par2][warp];
+      if ((lane & 7) == 0 && lane < 24) r[4 + (lane >> 3)] = s3;
       if (lane == 0) {
-        double* r = S.red[par2][warp];
-        r[0] = -a_smin; r[1] = a_smax; r[2] = -a_ymin; r[3] = a_ymax; r[4] = s1; r[5] = s2; r[6] = sxy;   // minima negated:
-        r[7] = dense_word ? 1.0 : 0.0;                                                                  // slots 0..3 all take a max
+        r[0] = -a_smin; r[1] = a_smax; r[2] = -a_ymin; r[3] = a_ymax;   // minima negated: slots 0..3 all take a max
+        r[7] = dense_word ? 1.0 : 0.0;
       }
       __syncthreads();  // the only block barrier of the common path; every thread is also done with the stage
 

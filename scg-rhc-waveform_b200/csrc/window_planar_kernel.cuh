@@ -197,18 +197,19 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
         if (pair_ok(k, p)) {
           const bool has1 = has_second(k, p);
           double v0, v1, v2;
-          if (lead == 0) {               // CTA-uniform: 16-byte loads when the window starts on an even element
+          // v2: first sample of the next pair (the buffer is padded past the window).  CTA-uniform: the 16-byte load
+          // covers (v0, v1) when the window starts on an even element of the buffer, (v1, v2) when on an odd one
+          if (lead == 0) {
             const double2 q = *reinterpret_cast<const double2*>(win + i0);
-            v0 = q.x; v1 = q.y;
+            v0 = q.x; v1 = q.y; v2 = win[i0 + 2];
           } else {
-            v0 = win[i0]; v1 = win[i0 + 1];
+            const double2 q = *reinterpret_cast<const double2*>(win + i0 + 1);
+            v0 = win[i0]; v1 = q.x; v2 = q.y;
           }
-          v2 = win[i0 + 2];              // first sample of the next pair (the buffer is padded past the window)
           y0[k] = v0; y1[k] = v1;
           a_ymin = v0 < a_ymin ? v0 : a_ymin;
           a_ymax = v0 > a_ymax ? v0 : a_ymax;
           const double d0 = __dsub_rn(v0, K);
-          s1 = __dadd_rn(s1, d0);
           s2 = __fma_rn(d0, d0, s2);
           double dd = d0;
           bool c0 = false, c1 = false;
@@ -216,7 +217,6 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
             a_ymin = v1 < a_ymin ? v1 : a_ymin;
             a_ymax = v1 > a_ymax ? v1 : a_ymax;
             const double d1 = __dsub_rn(v1, K);
-            s1 = __dadd_rn(s1, d1);
             s2 = __fma_rn(d1, d1, s2);
             sC = __dadd_rn(sC, d1);
             dd = __dadd_rn(d0, d1);
@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
             c0 = fabs(__dsub_rn(v1, v0)) < thr;
             c1 = has_third(k, p) && (fabs(__dsub_rn(v2, v1)) < thr);
           }
+          s1 = __dadd_rn(s1, dd);         // the pair's sum serves both the plain and the k-weighted sum
           sB = __fma_rn((double)k, dd, sB);
           full = c0 && c1;
         }
@@ -235,11 +236,10 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
       // sum_i (i - xbar) dy_i over this thread's samples i = 2(tid + NTH k) + b
       double sxy = __fma_rn(tx, s1, __fma_rn((double)(2 * NTH), sB, sC));
       a_ymin = warp_min(a_ymin); a_ymax = warp_max(a_ymax);
-      s1 = warp_sum(s1); s2 = warp_sum(s2); sxy = warp_sum(sxy);
-      if (lane == 0) {
-        double* r = S.red[s][warp];
-        r[0] = -a_ymin; r[1] = a_ymax; r[4] = s1; r[5] = s2; r[6] = sxy; r[7] = dense_word ? 1.0 : 0.0;
-      }
+      const double s3 = warp_sum3(s1, s2, sxy, lane);        // lane 0: s1, lane 8: s2, lane 16: sxy
+      double* r = S.red[s][warp];
+      if ((lane & 7) == 0 && lane < 24) r[4 + (lane >> 3)] = s3;
+      if (lane == 0) { r[0] = -a_ymin; r[1] = a_ymax; r[7] = dense_word ? 1.0 : 0.0; }
     }
 
     // ================= phase B, before the barrier: SCG planes -> registers, joint min/max ==========================
@@ -279,21 +279,29 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
               v0 = win[i0]; v1 = win[i0 + 1];
             }
             x0[k][c] = v0; x1[k][c] = v1;
-            a_smin = v0 < a_smin ? v0 : a_smin;
-            a_smax = v0 > a_smax ? v0 : a_smax;
-            nanacc = __fma_rn(v0, 0.0, nanacc);   // NaN iff some v is NaN or Inf
             if (has_second(k, p)) {
-              a_smin = v1 < a_smin ? v1 : a_smin;
-              a_smax = v1 > a_smax ? v1 : a_smax;
-              nanacc = __fma_rn(v1, 0.0, nanacc);
+              // joint min / max of a pair with three comparisons instead of four; a NaN can hide its partner from one
+              // of the two extrema, but a window with a NaN gets NaN extrema below whatever these say
+              const bool lt = v0 < v1;
+              const double lo2 = lt ? v0 : v1, hi2 = lt ? v1 : v0;
+              a_smin = lo2 < a_smin ? lo2 : a_smin;
+              a_smax = hi2 > a_smax ? hi2 : a_smax;
+              // one FMA per pair: the accumulator ends non-finite if v0 or v1 is NaN or Inf (Inf * 0 = NaN, Inf * v = Inf,
+              // Inf - Inf = NaN); a finite overflow of the products only sends the window through the exact recheck
+              nanacc = __fma_rn(v0, v1, nanacc);
+            } else {
+              a_smin = v0 < a_smin ? v0 : a_smin;
+              a_smax = v0 > a_smax ? v0 : a_smax;
+              nanacc = __fma_rn(v0, 0.0, nanacc);
             }
           }
         }
       }
-      a_smin = warp_min(a_smin); a_smax = warp_max(a_smax); nanacc = warp_sum(nanacc);
+      a_smin = warp_min(a_smin); a_smax = warp_max(a_smax);
+      const bool odd_b = __any_sync(kFull, !(fabs(nanacc) <= DBL_MAX));      // a vote instead of a sum tree
       if (lane == 0) {
         double* r = S.red[s][warp];
-        r[2] = -a_smin; r[3] = a_smax; r[8] = nanacc;
+        r[2] = -a_smin; r[3] = a_smax; r[8] = odd_b ? qnan : 0.0;
       }
     }
     __syncthreads();  // the barrier of the iteration: partials visible, RHC slot s and SCG slot s are in registers

@@ -9,8 +9,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, 'csrc')
 LIB = os.path.join(HERE, 'libscgrhc.so')
 SOURCES = [os.path.join(CSRC, 'api.cu')]
-HEADERS = [os.path.join(CSRC, f) for f in ('common.cuh', 'window_kernel.cuh', 'aux_kernels.cuh', 'filter_kernels.cuh', 'filter_scan_kernel.cuh', 'subset_kernel.cuh')] + \
-          [os.path.join(ROOT, 'include', 'scgrhc.h')]
+HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))) + [os.path.join(ROOT, 'include', 'scgrhc.h')]
 
 
 def nvcc_path():
