@@ -507,15 +507,17 @@ class HostIngest:
     ``{'sos': (n, 6) sections, 'filter_cols': [...], 'filter_exact': bool, 'resample': (up, down), 'out_rows': [...]}``;
     with ``resample`` the plan's rows are rows AFTER resampling (``out_rows`` per record).
 
-    ``planar`` (default: on for digital cohorts without optional stages): the fp64 chunk arenas on the device are PLANAR (one
-    plane per signal, csrc/window_planar_kernel.cuh): the device decode (digital cohorts) or generator (SynthSource) writes
-    that layout at no extra cost, a rejected window then costs 6 KB of DRAM traffic instead of 24 KB (traffic == the
-    algorithmic bytes) and the kernel is 4 % faster in a burst than the interleaved one.  Not for fp64 host
-    cohorts (they arrive interleaved over PCIe), nor with the optional stages (the filters read interleaved rows), nor with
-    z-score normalisation (those runs decode to interleaved rows)."""
+    ``planar`` (default: on for digital cohorts of three or more SCG channels without optional stages): the fp64 chunk
+    arenas on the device are PLANAR (one plane per signal, csrc/window_planar_kernel.cuh): the device decode (digital
+    cohorts) or generator (SynthSource) writes that layout at no extra cost, a rejected window then costs 6 KB of DRAM
+    traffic instead of 24 KB (traffic == the algorithmic bytes) and the kernel runs at 0.92 of the HBM peak against 0.84-0.89
+    for the interleaved one.  With one or two SCG channels the interleaved kernel is the faster one (its
+    per-window overhead is smaller: 0.79 / 0.89 against 0.65 / 0.83), so those cohorts keep interleaved rows.  Not for fp64
+    host cohorts (they arrive interleaved over PCIe), nor with the optional stages (the filters read interleaved rows), nor
+    with z-score normalisation (those runs decode to interleaved rows)."""
     self.plan, self.nsig, self.device = plan, nsig, torch.device(device)
     self.stages = stages or None
-    self.planar = (digital_nsig is not None and not stages) if planar is None else bool(planar)
+    self.planar = (digital_nsig is not None and not stages and nsig >= 4) if planar is None else bool(planar)
     if self.planar and stages:
       raise ValueError('planar chunk arenas cannot feed the optional filter / resample stages (they read interleaved rows)')
     self.planar_run = False
@@ -782,9 +784,9 @@ class LazyDiskIngest(HostIngest):
   ``(dat_paths, rows, gains, baselines, metas)`` of records r0..r1; ``plan_chunk(metas, rows, r0)`` -> engine.Plan of the
   chunk alone (rows and candidates chunk-local, record ids global)."""
 
-  def __init__(self, rows_est, nsig, device, W, nsig_file, parse_chunk, plan_chunk, chunk_records=32, planar=True):
+  def __init__(self, rows_est, nsig, device, W, nsig_file, parse_chunk, plan_chunk, chunk_records=32, planar=None):
     self.plan, self.nsig, self.device = None, nsig, torch.device(device)
-    self.stages, self.planar, self.planar_run = None, bool(planar), False
+    self.stages, self.planar, self.planar_run = None, (nsig >= 4 if planar is None else bool(planar)), False
     est = [int(v) for v in rows_est]
     self.n_records, self.chunk_records = len(est), int(chunk_records)
     self.record_rows = np.zeros(len(est), dtype=np.int64)
