@@ -1091,7 +1091,7 @@ def run_b200(args):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=50)
+  ap.add_argument('--steps', type=int, default=20)
   ap.add_argument('--warmup', type=int, default=5)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--records', type=int, default=1000, help='records per GPU (BASELINE configs[1]: 1,000)')
