@@ -1014,7 +1014,7 @@ def run_b200(args):
       launches[0] += (reps + 1) * (2 * (n_d // args.dropin_chunk + 1) + 3)
       return {'value': store.shard.total / dt, 'unit': UNIT, 'seconds': dt, 'seconds_each_rep_this_rank': times, 'records': n_d * world, 'kept_windows': store.shard.total,
               'bytes_read_per_rank': n_d * T_ROWS * len(SIG) * 2, 'read_gbs_per_rank': n_d * T_ROWS * len(SIG) * 2 / dt / 1e9,
-              'what': 'wall clock (median of 5 calls, max over ranks) of recordutil.prepare_cohort(params) over %d format-16 records on tmpfs (%d per rank): JSON side-cars + headers parsed, '
+              'what': 'wall clock (median of 5 calls, max over ranks) of recordutil.prepare_cohort(params) over %d format-16 records on tmpfs (%d per rank): JSON side-cars + headers of the shard parsed in one native call (scgrhc_scan_records), '
                       'C planner, reader pool -> ring of pinned chunks -> H2D -> scgrhc_decode_fmt16_records -> fused window kernel -> ordered kept list '
                       'on the host; includes every Python-side cost of the public entry point' % (n_d * world, n_d)}
     finally:

@@ -151,6 +151,29 @@ int scgrhc_plan_cohort(const double* event_time, const uint8_t* event_match, con
                        int64_t n_rec, int32_t W, int32_t stride, double fs, int32_t rec0, scgrhc_interval* out,
                        int64_t out_cap, int64_t* n_out, int64_t* n_cand);
 
+/* ---- host side of the ingest: headers and side-cars of a chunk of records in one call (no device work) -------------
+ * Replaces, for the common shape of both files, the per-record Python of wfdb.rdrecord's header read (recordutil.py:137)
+ * and json.load + strptime of the side-car (recordutil.py:97-101).  status 0: fields valid; 1: not the common shape, send
+ * this record through the general parsers; 2: a file is missing / unreadable.  names_match: the signal descriptions
+ * equal the expected list (the caller's "same layout as record 0" test).  n_events -1: ChamEvents_in_s is not an object
+ * (no intervals, recordutil.py:103). */
+typedef struct scgrhc_record_scan {
+  int32_t status;
+  int32_t nsig;
+  int64_t rows;        /* frames: min(header count, signal file size / (2 nsig)) */
+  double fs;
+  double duration_s;   /* MacEndTime - MacStTime with the date ignored */
+  int32_t n_events;
+  int32_t names_match;
+} scgrhc_record_scan;
+
+/* names_blob: n NUL-terminated record names back to back; expect_sig_blob: nsig_expect NUL-terminated descriptions.
+ * Per record r: gains/baselines[r * nsig_expect + k], ev_time[r * max_events + i], ev_prefix[(r * max_events + i) * 16]
+ * (key.split('_')[0], NUL padded), events in file order.  threads <= 0: up to 8. */
+int scgrhc_scan_records(const char* dir, const char* names_blob, int64_t n, const char* expect_sig_blob, int32_t nsig_expect,
+                        int32_t max_events, int32_t threads, scgrhc_record_scan* out, double* gains, int32_t* baselines,
+                        double* ev_time, char* ev_prefix);
+
 /* ---- the hot path: has_noise + SCGDataset.init_segments fused (recordutil.py:141-148,55-66;
  *      waveform_noise.py:6-49).  Asynchronous. */
 int scgrhc_process_windows(scgrhc_ctx* ctx, const scgrhc_job* job, const scgrhc_outputs* out, void* stream);

@@ -16,6 +16,7 @@
 #include "window_kernel.cuh"
 #include "window_planar_kernel.cuh"
 #include "subset_kernel.cuh"
+#include "host_scan.h"
 
 using namespace scgrhc;
 
@@ -193,6 +194,16 @@ extern "C" int scgrhc_plan_cohort(const double* event_time, const uint8_t* event
   *n_out = k;
   *n_cand = cand;
   return SCGRHC_OK;
+}
+
+extern "C" int scgrhc_scan_records(const char* dir, const char* names_blob, int64_t n, const char* expect_sig_blob, int32_t nsig_expect,
+                                   int32_t max_events, int32_t threads, scgrhc_record_scan* out, double* gains, int32_t* baselines,
+                                   double* ev_time, char* ev_prefix) {
+  try {
+    return hostscan::scan_records(dir, names_blob, n, expect_sig_blob, nsig_expect, max_events, threads, out, gains, baselines, ev_time, ev_prefix);
+  } catch (const std::bad_alloc&) {
+    return SCGRHC_ERR_BAD_ARG;
+  }
 }
 
 // ---- hot path launcher -------------------------------------------------------------------------------

@@ -41,7 +41,7 @@ from timelog import timelog
 from waveform_noise import has_noise  # noqa: F401  (re-exported like the reference, recordutil.py:17)
 
 from scgrhc import _native as N
-from scgrhc import engine, filters, ops
+from scgrhc import engine, filters, hostscan, ops
 
 SAMPLE_FREQ = 500
 
@@ -515,7 +515,19 @@ def _prepare_streamed(params, names, rec0, C, dev, chunk_records, group):
     return None
   sel = cols0 + [rcol0]
 
+  native = getattr(wfdb, 'NATIVE_SCAN', False)
+
   def parse_chunk(r0, r1):
+    if native:                    # headers + side-cars of the chunk in one native call (scgrhc.hostscan)
+      try:
+        rows, g, b, same, metas = hostscan.scan(PROCESSED_DATA_PATH, names[r0:r1], first[0], wfdb.read_header, _read_meta)
+      except hostscan.Unscannable:
+        rows = None
+      if rows is not None:
+        if not same.all():
+          raise _Heterogeneous(names[r0 + int(np.argmin(same))])
+        return ([os.path.join(PROCESSED_DATA_PATH, n + '.dat') for n in names[r0:r1]], [int(v) for v in rows],
+                np.ascontiguousarray(g[:, sel]), np.ascontiguousarray(b[:, sel]), metas)
     paths, rows, gains, bases, metas = [], [], [], [], []
     for name in names[r0:r1]:
       h = wfdb.read_header(os.path.join(PROCESSED_DATA_PATH, name))
@@ -540,10 +552,23 @@ def _prepare_streamed(params, names, rec0, C, dev, chunk_records, group):
 def _prepare_eager(params, names, names_all, lo, C, dev, chunk_records, group):
   """Every side-car and header (or, for readers without digital access, every record) is read first, then one plan for the
   whole shard and a chunked ingest: the path of the optional stages and of readers other than scgrhc.wfdbio."""
-  metas = [_read_meta(name) for name in names]
-  plan = stages = source = decode = host = None
+  plan = stages = source = decode = host = metas = None
   rows = []
-  if hasattr(wfdb, 'read_header'):
+  if getattr(wfdb, 'NATIVE_SCAN', False) and names:
+    try:                          # headers + side-cars of the shard in one native call (scgrhc.hostscan)
+      first = wfdb.read_header(os.path.join(PROCESSED_DATA_PATH, names[0]))
+      cols0, rcol0 = engine.resolve_columns(first[0], params.in_channels)
+      nrows, g, b, same, scanned = hostscan.scan(PROCESSED_DATA_PATH, names, first[0], wfdb.read_header, _read_meta)
+      if same.all():
+        sel = cols0 + [rcol0]
+        rows, metas = [int(v) for v in nrows], scanned
+        source = engine.DiskSource([os.path.join(PROCESSED_DATA_PATH, n + '.dat') for n in names], rows, len(first[0]))
+        decode = (sel, np.ascontiguousarray(g[:, sel]), np.ascontiguousarray(b[:, sel]))
+    except (NotImplementedError, hostscan.Unscannable):
+      source, rows, metas = None, [], None
+  if metas is None:
+    metas = [_read_meta(name) for name in names]
+  if source is None and hasattr(wfdb, 'read_header'):
     try:
       heads = [wfdb.read_header(os.path.join(PROCESSED_DATA_PATH, name)) for name in names]
       sels = [engine.resolve_columns(h[0], params.in_channels) for h in heads]

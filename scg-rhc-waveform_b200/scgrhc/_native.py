@@ -43,6 +43,11 @@ class Decim(C.Structure):
               ('iv_in0', C.c_void_p), ('iv_len', C.c_void_p), ('iv_rel', C.c_void_p)]
 
 
+class RecordScan(C.Structure):
+  _fields_ = [('status', C.c_int32), ('nsig', C.c_int32), ('rows', C.c_int64), ('fs', C.c_double), ('duration_s', C.c_double),
+              ('n_events', C.c_int32), ('names_match', C.c_int32)]
+
+
 class Compact(C.Structure):
   _fields_ = [('kept_idx', C.c_void_p), ('start_idx', C.c_void_p), ('stop_idx', C.c_void_p),
               ('rec_id', C.c_void_p), ('n_kept', C.c_void_p), ('stride', C.c_int32), ('reserved', C.c_int32)]
@@ -59,7 +64,7 @@ _lib = None
 
 # every symbol include/scgrhc.h declares (tests check the library exports all of them)
 SYMBOLS = ['scgrhc_abi_version', 'scgrhc_ctx_create', 'scgrhc_ctx_destroy', 'scgrhc_last_error',
-           'scgrhc_ctx_set_tuning', 'scgrhc_ctx_set_output_planes', 'scgrhc_ctx_sm_count', 'scgrhc_plan_record', 'scgrhc_plan_cohort', 'scgrhc_process_windows', 'scgrhc_process_windows_decim',
+           'scgrhc_ctx_set_tuning', 'scgrhc_ctx_set_output_planes', 'scgrhc_ctx_sm_count', 'scgrhc_plan_record', 'scgrhc_plan_cohort', 'scgrhc_scan_records', 'scgrhc_process_windows', 'scgrhc_process_windows_decim',
            'scgrhc_compact_kept', 'scgrhc_normalize_subsets', 'scgrhc_global_minmax', 'scgrhc_check_errors', 'scgrhc_ambiguous_count', 'scgrhc_gather_windows',
            'scgrhc_window_metrics', 'scgrhc_sosfiltfilt', 'scgrhc_sosfiltfilt_scan', 'scgrhc_resample_poly', 'scgrhc_gather_windows_noise', 'scgrhc_collate_batch', 'scgrhc_philox_words', 'scgrhc_rolling_range_lt', 'scgrhc_decode_fmt16', 'scgrhc_decode_fmt16_records', 'scgrhc_waveform_stats', 'scgrhc_synth_records', 'scgrhc_selftest_div']
 
@@ -89,6 +94,7 @@ def lib():
                                    C.POINTER(i64), C.c_int, C.POINTER(C.c_int)]
   L.scgrhc_plan_cohort.argtypes = [C.POINTER(dbl), C.POINTER(C.c_uint8), C.POINTER(i64), C.POINTER(i64), i64, i32, i32, dbl, i32,
                                    C.POINTER(Interval), i64, C.POINTER(i64), C.POINTER(i64)]
+  L.scgrhc_scan_records.argtypes = [C.c_char_p, C.c_char_p, i64, C.c_char_p, i32, i32, i32, vp, vp, vp, vp, vp]
   L.scgrhc_process_windows.argtypes = [vp, C.POINTER(Job), C.POINTER(Outputs), vp]
   L.scgrhc_process_windows_decim.argtypes = [vp, C.POINTER(Job), C.POINTER(Outputs), C.POINTER(Decim), vp]
   L.scgrhc_normalize_subsets.argtypes = [vp, C.POINTER(Job), C.POINTER(Subset), i32, vp, vp]

@@ -17,6 +17,7 @@ import os
 import numpy as np
 
 INVALID_16 = -32768
+NATIVE_SCAN = True      # scgrhc.hostscan parses the same header shape as _fast_header below, natively and in bulk
 
 
 class Record:
