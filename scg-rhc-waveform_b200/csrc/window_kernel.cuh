@@ -109,8 +109,12 @@ struct Normaliser {
     // residuals and the quotient stay normal): true when |mn| >= 2^-900 (a is then either >= |mn|/2
     // or a multiple of ulp(mn)/2) and d is within [2^-14, 2^60].  Anything else (mn == 0, tiny, NaN,
     // Inf, huge ranges) takes the IEEE-division loop.
-    slow = !(d >= 0x1p-14 && d <= 0x1p60 && fabs(mn_) >= 0x1p-900);
-    quick = !slow && fabs(mn_) >= 0x1p-10;   // see tier 1 of the normalisation below
+    // The three range tests on the exponent fields (integer pipe; every thread of the CTA evaluates them for every window):
+    // 2^-14 <= d < 2^60 (negative, NaN and Inf fall outside: the subtraction wraps), |mn| >= 2^-900, |mn| >= 2^-10.  A NaN / Inf
+    // minimum passes the |mn| tests but makes d NaN / Inf, which the first test rejects.
+    const uint32_t hd = (uint32_t)__double2hiint(d), hm = (uint32_t)__double2hiint(mn_) & 0x7fffffffu;
+    slow = !((hd - 0x3f100000u) < (0x43b00000u - 0x3f100000u) && hm >= 0x07b00000u);
+    quick = !slow && hm >= 0x3f500000u;      // see tier 1 of the normalisation below
   }
   // extension (absent from the reference): (x - mean) / (std + 0.0001); same tiers, same validity conditions
   __device__ __forceinline__ void init_z(double mean, double sd) {

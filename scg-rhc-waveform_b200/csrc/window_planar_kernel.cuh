@@ -40,6 +40,9 @@ struct PScratch {
   uint32_t cmask[2][8 * (NTH / 32)];
   uint32_t a24[8 * (NTH / 32)];
   int slow_cnt;
+  // the RHC producer's interval cursor (thread 0 only): shared memory instead of seven registers in every thread
+  long long p_cand0, p_row0;
+  int p_nwin, p_rec, p_iv;
 };
 
 // Window of W samples; NTH threads; every thread owns PR pairs (samples 2p, 2p+1 for p = tid + k*NTH): W <= 2*PR*NTH.
@@ -68,16 +71,16 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
   const bool norm_global = !PLAIN && (J.flags & SCGRHC_NORM_GLOBAL) != 0;
   const bool keep_all = !PLAIN && (J.flags & SCGRHC_KEEP_ALL) != 0;
   const double thr = J.flat_threshold, min_rhc = J.min_rhc;
-  const double* const yplane = J.arena + (long long)J.rhc_col * rows;
-  const double* xplane[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) xplane[c] = J.arena + (long long)J.scg_cols[c] * rows;
+  // plane bases are recomputed where they are used (the producers and the capacity-edge loads): job fields are constant-bank
+  // operands, pointers held across the loop would be eight more live registers
+  auto yplane_of = [&]() { return J.arena + (long long)J.rhc_col * rows; };
+  auto xplane_of = [&](int c) { return J.arena + (long long)J.scg_cols[c] * rows; };
 
   const long long items = use_list ? J.n_items : J.n_cand;
   const long long lo = items * (long long)blockIdx.x / gridDim.x;
   const long long hi = items * (long long)(blockIdx.x + 1) / gridDim.x;
   if (lo >= hi) return;
-  const long long cnt = hi - lo;
+  const int cnt = (int)(hi - lo);               // a CTA's share of the items: far below 2^31
 
   if (tid == 0) {
     for (int i = 0; i < PNR; ++i) mbar_init(&S.rfull[i], 1);
@@ -87,18 +90,14 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
   }
   __syncthreads();
 
-  int ppar[C];                                    // parity of the plane base c * rows: lead = (ppar ^ row) & 1
-#pragma unroll
-  for (int c = 0; c < C; ++c) ppar[c] = (int)(((long long)J.scg_cols[c] * rows) & 1);
-  const int ypar = (int)(((long long)J.rhc_col * rows) & 1);
+  // parity of the plane base c * rows (lead = (parity ^ row) & 1): one AND of two job fields where it is needed, not a register each
+  auto ppar_of = [&](int c) { return (int)(J.scg_cols[c] & (int)rows & 1); };
+  auto ypar_of = [&]() { return (int)(J.rhc_col & (int)rows & 1); };
 
   // ---- producer state (thread 0 only) -----------------------------------------------------------
-  int p_iv = 0;
-  long long p_cand0 = 0, p_row0 = 0;
-  int p_nwin = 0, p_rec = 0;
   auto load_iv = [&](int iv) {
     const scgrhc_interval I = J.intervals[iv];
-    p_cand0 = I.cand0; p_row0 = I.row0; p_nwin = I.n_win; p_rec = I.rec_id;
+    S.p_cand0 = I.cand0; S.p_row0 = I.row0; S.p_nwin = I.n_win; S.p_rec = I.rec_id; S.p_iv = iv;
   };
   // one plane window -> shared memory: 16-byte aligned start (the element before when the offset is odd), even length.
   // A window within two rows of the end of the planes takes cooperative plain loads instead (the copy of the LAST plane
@@ -107,9 +106,10 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
   const bool tail_ok = (long long)J.arena_capacity_bytes >= (long long)J.nsig * rows * 8 + 16;   // room behind the last plane
   auto issue_rhc = [&](long long item, int s) {
     const long long cand = use_list ? J.kept_list[item] : item;
-    while (cand >= p_cand0 + p_nwin) load_iv(++p_iv);
-    const int i = (int)(cand - p_cand0);
-    const long long row = p_row0 + (long long)i * wstride;
+    while (cand >= S.p_cand0 + S.p_nwin) load_iv(S.p_iv + 1);
+    const int i = (int)(cand - S.p_cand0);
+    const long long row = S.p_row0 + (long long)i * wstride;
+    const int p_rec = S.p_rec;
     const bool fb = !tail_ok && row + W + 2 > rows;
     PMeta m;
     m.cand = cand; m.rowf = row | (fb ? kPFallback : 0);
@@ -118,10 +118,10 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
     if (fb) {
       mbar_arrive(&S.rfull[s]);
     } else {
-      const int lead = (ypar ^ (int)row) & 1;
+      const int lead = (ypar_of() ^ (int)row) & 1;
       const uint32_t bytes = lead ? bytes_odd : bytes_even;
       mbar_arrive_expect_tx(&S.rfull[s], bytes);
-      bulk_g2s(rbase + (size_t)s * wpad, yplane + (row - lead), bytes, &S.rfull[s]);
+      bulk_g2s(rbase + (size_t)s * wpad, yplane_of() + (row - lead), bytes, &S.rfull[s]);
     }
   };
   auto issue_scg = [&](const PMeta& m, int s) {      // the SCG planes of a kept window; plain loads in phase B if the item is at the edge
@@ -130,12 +130,12 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
     const long long row = m.rowf;
     int odd = 0;
 #pragma unroll
-    for (int c = 0; c < C; ++c) odd += (ppar[c] ^ (int)row) & 1;
+    for (int c = 0; c < C; ++c) odd += (ppar_of(c) ^ (int)row) & 1;
     mbar_arrive_expect_tx(&S.sfull[s], (uint32_t)C * bytes_even + (uint32_t)odd * (bytes_odd - bytes_even));
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const int lead = (ppar[c] ^ (int)row) & 1;
-      bulk_g2s(sbase + ((size_t)s * C + c) * wpad, xplane[c] + (row - lead), lead ? bytes_odd : bytes_even, &S.sfull[s]);
+      const int lead = (ppar_of(c) ^ (int)row) & 1;
+      bulk_g2s(sbase + ((size_t)s * C + c) * wpad, xplane_of(c) + (row - lead), lead ? bytes_odd : bytes_even, &S.sfull[s]);
     }
   };
   if (tid == 0) {
@@ -145,7 +145,6 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
       const int mid = (a + b + 1) >> 1;
       if (J.intervals[mid].cand0 <= first) a = mid; else b = mid - 1;
     }
-    p_iv = a;
     load_iv(a);
     for (int i = 0; i < PNR && i < cnt; ++i) issue_rhc(lo + i, i);
   }
@@ -165,7 +164,7 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
   uint32_t khist = 0u;        // bit k: the item of iteration j - 1 - k was kept (its SCG planes were requested)
   int rs = 0;                 // RHC slot of item j: j % PNR, parity (j / PNR) & 1
   uint32_t rparity = 0u;
-  for (long long j = 0; j < cnt + 2; ++j) {
+  for (int j = 0; j < cnt + 2; ++j) {
     const int s = (int)(j & 1);
     const bool doA = j < cnt;
     const bool doB = ((khist >> 1) & 1u) != 0;         // the (CTA-uniform) decision of iteration j - 2
@@ -179,9 +178,9 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
       MA = S.rmeta[rs];
       double* buf = rbase + (size_t)rs * wpad;
       const long long rowA = MA.rowf & ~kPFallback;
-      const int lead = (ypar ^ (int)rowA) & 1;
+      const int lead = (ypar_of() ^ (int)rowA) & 1;
       if (MA.rowf & kPFallback) {
-        for (int e = tid; e < W; e += NTH) buf[lead + e] = yplane[rowA + e];
+        for (int e = tid; e < W; e += NTH) buf[lead + e] = yplane_of()[rowA + e];
         __syncthreads();
       }
       const double* win = buf + lead;
@@ -255,15 +254,15 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
       } else {                                   // capacity edge: plain loads
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          const int lead = (ppar[c] ^ (int)rowB) & 1;
-          for (int e = tid; e < W; e += NTH) buf[(size_t)c * wpad + lead + e] = xplane[c][rowB + e];
+          const int lead = (ppar_of(c) ^ (int)rowB) & 1;
+          for (int e = tid; e < W; e += NTH) buf[(size_t)c * wpad + lead + e] = xplane_of(c)[rowB + e];
         }
         __syncthreads();
       }
       double a_smin = CUDART_INF, a_smax = -CUDART_INF, nanacc = 0.0;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const int lead = (ppar[c] ^ (int)rowB) & 1;
+        const int lead = (ppar_of(c) ^ (int)rowB) & 1;
         const double* win = buf + (size_t)c * wpad + lead;
 #pragma unroll
         for (int k = 0; k < PR; ++k) {
@@ -351,7 +350,7 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
         if (run || s2_bad) {                    // CTA-uniform and rare: exact work on the RHC window still in shared memory
           if (warp == 0 && lane < NWORDS) S.a24[lane] = a24;
           __syncthreads();
-          const double* win = rbase + (size_t)rs * wpad + ((ypar ^ (int)MA.rowf) & 1);
+          const double* win = rbase + (size_t)rs * wpad + ((ypar_of() ^ (int)MA.rowf) & 1);
           int c = 0, fl = 0;
           if (run) {
             for (int k = 0; k < PR; ++k) {
