@@ -14,6 +14,7 @@
 #pragma once
 #include <atomic>
 #include <cerrno>
+#include <charconv>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -46,6 +47,13 @@ inline bool read_file(const std::string& path, std::string& out) {
   const bool ok = !std::ferror(f) && out.size() <= (1u << 24);
   std::fclose(f);
   return ok;
+}
+
+// Correctly rounded and independent of the process locale (strtod follows LC_NUMERIC; Python's float() does not).  Values
+// out of double range (float() gives inf) and anything from_chars does not take whole are left to the Python parsers.
+inline bool to_double(const char* s, const char* t, double& v) {
+  const auto r = std::from_chars(s, t, v);
+  return r.ec == std::errc() && r.ptr == t;
 }
 
 // ---- JSON: a structural skipper plus the three fields ------------------------------------------------
@@ -209,11 +217,7 @@ inline int parse_sidecar(const std::string& text, int max_events, SideCar& sc, d
               char* dst = ev_prefix + (size_t)sc.n_events * kPrefixBytes;
               std::memset(dst, 0, kPrefixBytes);
               std::memcpy(dst, s, pl2);
-              char* endp = nullptr;
-              const std::string num(j.p, ne);
-              errno = 0;
-              ev_time[sc.n_events] = std::strtod(num.c_str(), &endp);
-              if (endp != num.c_str() + num.size()) return 1;
+              if (!to_double(j.p, ne, ev_time[sc.n_events])) return 1;
               j.p = ne;
               ++sc.n_events;
               j.ws();
@@ -257,15 +261,12 @@ inline bool parse_int64(const char* s, const char* t, long long& v) {
   return true;
 }
 
-// plain decimal / exponent float, nothing Python's float() and strtod() could read differently
+// plain decimal / exponent float, nothing Python's float() and from_chars could read differently
 inline bool parse_float(const char* s, const char* t, double& v) {
   if (s == t || t - s > 64) return false;
   for (const char* q = s; q < t; ++q)
     if (!((*q >= '0' && *q <= '9') || *q == '.' || *q == '-' || *q == '+' || *q == 'e' || *q == 'E')) return false;
-  const std::string tmp(s, t);
-  char* endp = nullptr;
-  v = std::strtod(tmp.c_str(), &endp);
-  return endp == tmp.c_str() + tmp.size();
+  return to_double(s, t, v);
 }
 
 struct Tokens {
