@@ -51,7 +51,7 @@ struct PScratch {
 template <int C, int NTH, int PR, typename OutT, int WCT, bool PLAIN = false>
 __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(const __grid_constant__ KParams P) {
   static_assert(WCT == 0 || (WCT + 1) / 2 <= PR * NTH, "window does not fit the pair grid");
-  static_assert(SCGRHC_FLAT_WIN == 50, "run detection below is hard-wired to 24 full pairs inside 49 small steps");
+  static_assert(SCGRHC_FLAT_WIN == 50, "run detection below is hard-wired to 24 whole pairs inside a flat run of 50 samples");
   constexpr int NW = NTH / 32;
   constexpr int NWORDS = PR * NW;
   static_assert(NWORDS <= 32, "one mask word per lane");
@@ -158,7 +158,6 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
   // pair p = tid + k*NTH exists / has its second sample: compile-time for all but the last k when the length is known
   auto pair_ok = [&](int k, int p) { return WCT > 0 ? ((k + 1) * NTH <= (WCT + 1) / 2 || p < (WCT + 1) / 2) : (p < npairs); };
   auto has_second = [&](int k, int p) { return WCT > 0 ? (WCT % 2 == 0 || (k + 1) * NTH <= WCT / 2 || 2 * p + 1 < WCT) : (2 * p + 1 < W); };
-  auto has_third = [&](int k, int p) { return WCT > 0 ? ((k + 1) * NTH < (WCT + 1) / 2 - (WCT % 2) || 2 * p + 2 < WCT) : (2 * p + 2 < W); };
 
   uint32_t spar[2] = {0u, 0u};
   uint32_t khist = 0u;        // bit k: the item of iteration j - 1 - k was kept (its SCG planes were requested)
@@ -195,15 +194,12 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
         bool full = false;
         if (pair_ok(k, p)) {
           const bool has1 = has_second(k, p);
-          double v0, v1, v2;
-          // v2: first sample of the next pair (the buffer is padded past the window).  CTA-uniform: the 16-byte load
-          // covers (v0, v1) when the window starts on an even element of the buffer, (v1, v2) when on an odd one
-          if (lead == 0) {
+          double v0, v1;
+          if (lead == 0) {               // CTA-uniform: 16-byte loads when the window starts on an even element of the buffer
             const double2 q = *reinterpret_cast<const double2*>(win + i0);
-            v0 = q.x; v1 = q.y; v2 = win[i0 + 2];
+            v0 = q.x; v1 = q.y;
           } else {
-            const double2 q = *reinterpret_cast<const double2*>(win + i0 + 1);
-            v0 = win[i0]; v1 = q.x; v2 = q.y;
+            v0 = win[i0]; v1 = win[i0 + 1];
           }
           y0[k] = v0; y1[k] = v1;
           a_ymin = v0 < a_ymin ? v0 : a_ymin;
@@ -211,7 +207,6 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
           const double d0 = __dsub_rn(v0, K);
           s2 = __fma_rn(d0, d0, s2);
           double dd = d0;
-          bool c0 = false, c1 = false;
           if (has1) {
             a_ymin = v1 < a_ymin ? v1 : a_ymin;
             a_ymax = v1 > a_ymax ? v1 : a_ymax;
@@ -219,17 +214,16 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
             s2 = __fma_rn(d1, d1, s2);
             sC = __dadd_rn(sC, d1);
             dd = __dadd_rn(d0, d1);
-            // c[i] = fl(|y[i+1] - y[i]|) < thr: necessary for any flat 50-window covering (i, i+1)
-            c0 = fabs(__dsub_rn(v1, v0)) < thr;
-            c1 = has_third(k, p) && (fabs(__dsub_rn(v2, v1)) < thr);
+            // fl(|y[2p+1] - y[2p]|) < thr is necessary for any flat 50-window that holds the pair (rounding is monotone and
+            // the step cannot exceed the window's range); the steps BETWEEN pairs are left to the exact recheck
+            full = fabs(__dsub_rn(v1, v0)) < thr;
           }
           s1 = __dadd_rn(s1, dd);         // the pair's sum serves both the plain and the k-weighted sum
           sB = __fma_rn((double)k, dd, sB);
-          full = c0 && c1;
         }
         const uint32_t word = __ballot_sync(kFull, full);
         if (lane == 0) S.cmask[s][k * NW + warp] = word;
-        // 49 consecutive small steps contain 24 consecutive full pairs, which span at most 2 mask words
+        // a flat run of 50 samples holds 24 consecutive whole pairs, which span at most 2 mask words
         dense_word |= __popc(word) >= 12;
       }
       // sum_i (i - xbar) dy_i over this thread's samples i = 2(tid + NTH k) + b
