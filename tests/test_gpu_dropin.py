@@ -205,6 +205,22 @@ def test_streamed_ingest_equals_eager_ingest(tmp_path, monkeypatch):
     monkeypatch.setenv('SCGRHC_LAZY_MIN_RECORDS', '1' if cfg == 'waveform_06' else '4096')   # both ingests through the public entry
     st, _ = recordutil.prepare_cohort(params, record_names=names)
     assert st.n_kept == b.n_kept and torch.equal(st.materialise()[0], y[0])
+  # the native header / side-car scanner (scgrhc.hostscan) against the Python parsers, end to end: same store with the scanner
+  # off; and with files outside its common shape (a comment line in a header, an event time given as a string) mixed in
+  hea = (root / 'rec1.hea').read_text()
+  (root / 'rec1.hea').write_text('# exported by a tool that comments\n' + hea)
+  (root / 'rec3.json').write_text(json.dumps(synth_ref.record_meta(100, events={'PA_1': '3.2', 'PCW_1': 40, 'PA_2': 55})))
+  for streamed in (False, True):
+    got = []
+    for native in (True, False):
+      monkeypatch.setattr(wfdbio, 'NATIVE_SCAN', native)
+      got.append(recordutil._prepare_streamed(params, names, 0, C, dev, 3, None) if streamed
+                 else recordutil._prepare_eager(params, names, names, 0, C, dev, 3, None))
+    a, b2 = got
+    assert a.n_kept == b2.n_kept == b.n_kept and torch.equal(a.kept_idx, b2.kept_idx) and torch.equal(a.rec_id, b2.rec_id)
+    assert torch.equal(a.kept_minmax(), b2.kept_minmax()) and torch.equal(a.materialise()[0], b2.materialise()[0])
+    assert torch.equal(a.materialise()[0], y[0])
+  monkeypatch.setattr(wfdbio, 'NATIVE_SCAN', True)
   # a rank whose block of records is empty (more ranks than records) still returns a well-formed, empty store
   empty = recordutil._prepare_eager(params, [], names, len(names), C, dev, 2, None)
   assert empty.n_kept == 0 and empty.n_cand == 0 and empty.kept_idx.numel() == 0 and empty.materialise()[0].shape[0] == 0
