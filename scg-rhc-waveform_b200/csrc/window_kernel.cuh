@@ -810,7 +810,7 @@ __global__ void __launch_bounds__(NT, DECIM ? 5 : 4) window_kernel(const __grid_
       else { ns.init(smin, smax); nr.init(ymin, ymax); }
       OutT* so = reinterpret_cast<OutT*>(P.out.scg_out) + (size_t)M.slot * C * W + tid;
       OutT* ro = reinterpret_cast<OutT*>(P.out.rhc_out) + (size_t)M.slot * W + tid;
-      // Tier 1 (fp32 output, per-window pairs): q0 = RN(a * RN(1/d)) is within 2.5 ulp64 of the correctly
+      // Tier 1 (fp32 output): q0 = RN(a * RN(1/d)) is within 2.5 ulp64 of the correctly
       // rounded quotient, so both round to the same float unless q0 sits within a few ulp64 of a float
       // rounding boundary (low 29 mantissa bits == 0x10000000).  Track the smallest distance to that
       // pattern with integer ops; a thread that saw a risky element (p ~ 3e-8 per element) falls through
@@ -838,7 +838,7 @@ __global__ void __launch_bounds__(NT, DECIM ? 5 : 4) window_kernel(const __grid_
         redo = false;
       }
       if constexpr (sizeof(OutT) == 4) {
-        if (!zscore && !use_list && !norm_global && ns.quick && nr.quick) {
+        if (!zscore && ns.quick && nr.quick) {      // the pairs may be this window's, an earlier pass's or the dataset's: tier 1 only looks at mn and d
           uint32_t acc = 0xffffffffu;
 #pragma unroll
           for (int k = 0; k < R; ++k) {

@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
         const bool vec = (WCT > 0 && WCT % 2 == 0) || (((size_t)slotA * W) & 1) == 0;     // 8-byte aligned pair stores
         bool redo = true;
         if constexpr (sizeof(OutT) == 4) {
-          if (!use_list && !norm_global && nr.quick) {         // tier 1, see window_kernel.cuh
+          if (nr.quick) {         // tier 1, see window_kernel.cuh (whatever the pairs' origin: this window, an earlier pass, the dataset)
             uint32_t acc = 0xffffffffu;
 #pragma unroll
             for (int k = 0; k < PR; ++k) {
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(NTH, NTH == 64 ? 8 : 4) window_planar_kernel(c
         OutT* so = reinterpret_cast<OutT*>(P.out.scg_out) + (size_t)slotB * C * W;
         bool redo = true;
         if constexpr (sizeof(OutT) == 4) {
-          if (!use_list && !norm_global && ns.quick) {
+          if (ns.quick) {
             uint32_t acc = 0xffffffffu;
 #pragma unroll
             for (int c = 0; c < C; ++c) {

@@ -513,7 +513,7 @@ class HostIngest:
     ``{'sos': (n, 6) sections, 'filter_cols': [...], 'filter_exact': bool, 'resample': (up, down), 'out_rows': [...]}``;
     with ``resample`` the plan's rows are rows AFTER resampling (``out_rows`` per record).
 
-    ``planar`` (default: on for digital cohorts of three or more SCG channels without optional stages, per-window pairs): the fp64 chunk
+    ``planar`` (default: on for digital cohorts of three or more SCG channels without optional stages): the fp64 chunk
     arenas on the device are PLANAR (one plane per signal, csrc/window_planar_kernel.cuh): the device decode (digital
     cohorts) or generator (SynthSource) writes that layout at no extra cost, a rejected window then costs 6 KB of DRAM
     traffic instead of 24 KB (traffic == the algorithmic bytes) and the kernel runs at 0.92 of the HBM peak against 0.84-0.89
@@ -524,7 +524,6 @@ class HostIngest:
     self.plan, self.nsig, self.device = plan, nsig, torch.device(device)
     self.stages = stages or None
     self.planar = (digital_nsig is not None and not stages and nsig >= 4) if planar is None else bool(planar)
-    self._planar_auto = planar is None
     if self.planar and stages:
       raise ValueError('planar chunk arenas cannot feed the optional filter / resample stages (they read interleaved rows)')
     self.planar_run = False
@@ -704,9 +703,7 @@ class HostIngest:
     cand_win, cand_rec = buf('cand_win', (n,), torch.int32), buf('cand_rec', (n,), torch.int32)
     kept_idx, start_idx, stop_idx = (buf(k, (n,), torch.int64) for k in ('kept_idx', 'start_idx', 'stop_idx'))
     rec_id, n_kept_t = buf('rec_id', (n,), torch.int32), buf('n_kept', (1,), torch.int64)
-    # the two-pass job (dataset-level pairs) is faster on interleaved rows (3.9 against 5.0 ms per 1,000 records: its pass A wants
-    # predicates and pairs only, which the planar kernel's two phases do not shorten), so the automatic choice leaves it there
-    planar = self.planar and normalisation in (None, 'minmax') and not (getattr(self, '_planar_auto', False) and use_global_min_max)
+    planar = self.planar and normalisation in (None, 'minmax')
     if planar and self.digital_nsig is None and isinstance(host_arena, (torch.Tensor, PinnedArenaSource)):
       raise ValueError('planar=True needs a source that writes planes (digital cohort or SynthSource); fp64 host rows are interleaved')
     base_flags = (N.OUT_F64 if out_dtype == torch.float64 else 0) | _norm_flag(normalisation, use_global_min_max) | \
@@ -796,7 +793,6 @@ class LazyDiskIngest(HostIngest):
   def __init__(self, rows_est, nsig, device, W, nsig_file, parse_chunk, plan_chunk, chunk_records=32, planar=None):
     self.plan, self.nsig, self.device = None, nsig, torch.device(device)
     self.stages, self.planar, self.planar_run = None, (nsig >= 4 if planar is None else bool(planar)), False
-    self._planar_auto = planar is None
     est = [int(v) for v in rows_est]
     self.n_records, self.chunk_records = len(est), int(chunk_records)
     self.record_rows = np.zeros(len(est), dtype=np.int64)
