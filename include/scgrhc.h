@@ -334,7 +334,8 @@ int scgrhc_synth_records(scgrhc_ctx* ctx, uint64_t seed, int64_t rec0, int64_t n
  *      mismatches after the fp32 cast, pairs evaluated.  mode 0: operands shaped like the
  *      normalisation (min <= x <= max, ranges 2^-14..2^10); mode 1: exponents up to +-1000, zeros (selects the
  *      IEEE loop); mode 2: the integer-checked fp32 tier, half of the quotients planted within 8 ulp64 of float
- *      rounding boundaries — counts = {operands not eligible, fp32 mismatches among unflagged, flagged}. */
+ *      rounding boundaries — counts = {operands not eligible, fp32 mismatches among unflagged, flagged}; mode 3: the
+ *      same with minima down to 2^-86 and a third of the samples a few ulp above the minimum. */
 int scgrhc_selftest_div(scgrhc_ctx* ctx, uint64_t seed, int64_t n, int32_t mode, uint64_t* counts, void* stream);
 
 #ifdef __cplusplus

@@ -110,11 +110,14 @@ struct Normaliser {
     // or a multiple of ulp(mn)/2) and d is within [2^-14, 2^60].  Anything else (mn == 0, tiny, NaN,
     // Inf, huge ranges) takes the IEEE-division loop.
     // The three range tests on the exponent fields (integer pipe; every thread of the CTA evaluates them for every window):
-    // 2^-14 <= d < 2^60 (negative, NaN and Inf fall outside: the subtraction wraps), |mn| >= 2^-900, |mn| >= 2^-10.  A NaN / Inf
-    // minimum passes the |mn| tests but makes d NaN / Inf, which the first test rejects.
+    // 2^-14 <= d < 2^60 (negative, NaN and Inf fall outside: the subtraction wraps), |mn| >= 2^-900, e_mn - e_d >= -70.  A NaN /
+    // Inf minimum passes the |mn| test but makes d NaN / Inf, which the first test rejects.
     const uint32_t hd = (uint32_t)__double2hiint(d), hm = (uint32_t)__double2hiint(mn_) & 0x7fffffffu;
     slow = !((hd - 0x3f100000u) < (0x43b00000u - 0x3f100000u) && hm >= 0x07b00000u);
-    quick = !slow && hm >= 0x3f500000u;      // see tier 1 of the normalisation below
+    // Tier 1 (below) needs every non-zero quotient to be a NORMAL float with room to spare (>= 2^-124): a non-zero numerator is
+    // at least ulp(mn) / 2 = 2^(e_mn - 53), the quotient therefore at least 2^(e_mn - e_d - 54), so e_mn - e_d >= -70 is enough
+    // (|mn| >= 2^-10 with d <= 2^60, the earlier form of this test, is the special case at the edge of the range).
+    quick = !slow && (hm >> 20) + 70u >= (hd >> 20);
   }
   // extension (absent from the reference): (x - mean) / (std + 0.0001); same tiers, same validity conditions
   __device__ __forceinline__ void init_z(double mean, double sd) {
@@ -193,15 +196,20 @@ __global__ void __launch_bounds__(256) selftest_div_kernel(unsigned long long se
       x = mn + (mx - mn) * m2;
       if (h2 & 0x2000) mn = 0.0;
     }
-    if (mode == 2) {         // tier 1 of the fp32 normalisation, half of the quotients planted next to float midpoints
+    if (mode >= 2) {         // tier 1 of the fp32 normalisation, half of the quotients planted next to float midpoints
       const double range = ldexp(m1, (int)(h1 & 0xFFF) % 24 - 14);
-      mn = ldexp((double)((h2 >> 3) & 0xFFFFF) - 524288.5, (int)(h1 >> 52) % 20 - 15);
+      // mode 2: |mn| from 2^-16 up; mode 3: minima down to 2^-86 (tier 1's eligibility compares the exponents of mn and d) and
+      // a third of the samples a few ulp(mn) above the minimum: the smallest non-zero quotients there are
+      mn = mode == 2 ? ldexp((double)((h2 >> 3) & 0xFFFFF) - 524288.5, (int)(h1 >> 52) % 20 - 15)
+                     : ldexp((double)((h2 >> 3) & 0xFFFFF) - 524288.5, (int)(h1 >> 52) % 70 - 85);
       mx = mn + range;
       const double d = __dadd_rn(__dsub_rn(mx, mn), 0.0001);
       if (h2 & 4) {
         const float f = (float)m2;
         const double mid = 0.5 * ((double)f + (double)nextafterf(f, 2.0f));
         x = mn + mid * d * (1.0 + ((double)((h1 >> 40) & 15) - 8.0) * 0x1p-53);
+      } else if (mode == 3 && (h2 & 3) == 1) {
+        x = mn + fabs(mn) * 0x1p-53 * (double)(1 + ((h1 >> 40) & 1023));
       } else {
         x = mn + range * m2;
       }
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(256) selftest_div_kernel(unsigned long long se
     Normaliser nz;
     nz.init(mn, mx);
     const double ref = __ddiv_rn(__dsub_rn(x, mn), __dadd_rn(__dsub_rn(mx, mn), 0.0001));
-    if (mode == 2) {
+    if (mode >= 2) {
       if (nz.quick) {
         const double q0 = __dmul_rn(__dsub_rn(x, nz.mn), nz.inv);
         if (tier1_key(q0) <= kTier1Risky) ++cnt;      // risky: the kernel recomputes these exactly
@@ -814,7 +822,7 @@ __global__ void __launch_bounds__(NT, DECIM ? 5 : 4) window_kernel(const __grid_
       // rounded quotient, so both round to the same float unless q0 sits within a few ulp64 of a float
       // rounding boundary (low 29 mantissa bits == 0x10000000).  Track the smallest distance to that
       // pattern with integer ops; a thread that saw a risky element (p ~ 3e-8 per element) falls through
-      // to tier 2 and rewrites its elements.  |mn| >= 2^-10 keeps every non-zero quotient >= 2^-124, above
+      // to tier 2 and rewrites its elements.  Normaliser::quick keeps every non-zero quotient >= 2^-124, above
       // the float subnormal range where the boundary pattern differs.
       bool redo = true;
       if (zscore && !(ns.slow || nr.slow)) {

@@ -53,8 +53,12 @@ def test_division_by_reciprocal_is_correctly_rounded():
   # fp32 tier: every element the integer check lets through must round to the reference's float;
   # elements planted on float rounding boundaries must be flagged (and only about that many)
   ineligible, bad32, flagged = ops.selftest_div(0, 77, 1 << 28, 2)
-  assert bad32 == 0 and ineligible < 1e-4 * (1 << 28), (bad32, ineligible)   # |min| < 2^-10 falls to the next tier
+  assert bad32 == 0 and ineligible == 0, (bad32, ineligible)
   assert 1e-3 * (1 << 28) < flagged < 0.55 * (1 << 28), flagged   # planted boundaries survive rounding of x only in part
+  # the same with minima down to 2^-86 and samples a few ulp above the minimum (the smallest non-zero quotients): eligibility
+  # is decided by the exponents of min and range, and most of these windows still qualify
+  ineligible, bad32, flagged = ops.selftest_div(0, 78, 1 << 28, 3)
+  assert bad32 == 0 and ineligible < 0.35 * (1 << 28), (bad32, ineligible)
 
 
 def test_predicates_match_reference_golden():
