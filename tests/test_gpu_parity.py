@@ -594,3 +594,64 @@ def test_nonfinite_scg_does_not_change_the_rhc_predicates():
   mm = st.minmax.cpu().numpy()
   assert np.isnan(mm[kept[0], :2]).all() and mm[kept[1], 0] == -np.inf and np.isfinite(mm[kept[1], 1])
   assert (mm[:, 2:] == base.minmax.cpu().numpy()[:, 2:]).all()
+
+
+@pytest.mark.parametrize('seed', list(range(16)))
+def test_fuzz_shapes_both_layouts_against_the_oracle(seed):
+  """Seeded random jobs — signal count, channel subset and order, window length, ragged records, side-car events, floor,
+  output type — through the interleaved kernel, the planar kernel and the numpy oracle (scan_record / normalise_record, the
+  restatement pinned to the unmodified reference): decisions, indices, pairs and samples bit for bit."""
+  rng = np.random.default_rng(1000 + seed)
+  nsig = int(rng.integers(2, 9))
+  acc = ['patch_ACC_lat', 'patch_ACC_hf', 'patch_ACC_dv']
+  rest = ['patch_ECG', 'x5', 'x6', 'x7']
+  if seed % 2 == 0:     # the three axes first (so that two-, three-channel subsets occur), else one axis guaranteed and the rest at random
+    others = [str(s) for s in rng.permutation(acc)] + [str(s) for s in rng.permutation(rest)]
+  else:
+    first = str(rng.choice(acc))
+    others = [first] + [str(s) for s in rng.permutation([a for a in acc if a != first] + rest)]
+  sig = [str(s) for s in rng.permutation(others[:nsig - 1] + ['RHC_pressure'])]        # columns in any order, at least one SCG axis
+  if nsig == 4 and seed % 2:
+    sig = list(synth_ref.DEFAULT_SIG_NAMES)                                             # wfdb's usual layout: the IDENT instantiations
+  scg_pool = [s for s in sig if s.startswith('patch_ACC')]
+  C = int(rng.integers(1, min(4, len(scg_pool)) + 1))
+  chans = [str(s) for s in rng.permutation(scg_pool)[:C]]
+  seg = float(rng.choice([1.5, 1.5, 1.0, 0.75, 0.25, 2.0, 0.102, 1.234]))
+  W = int(seg * 500)
+  out_dtype = torch.float64 if seed % 5 == 0 else torch.float32
+  floor = float(rng.choice([-50.0, -50.0, 0.0, 12.5]))
+  n_rec = int(rng.integers(2, 6))
+  rows = [int(rng.integers(3 * W + 1, 30 * W + 7)) for _ in range(n_rec)]
+  chamber = str(rng.choice(['PA', 'RV']))
+  metas = []
+  for T in rows:
+    dur = T / 500.0
+    ts = np.sort(rng.uniform(0, dur, size=int(rng.integers(1, 5))))
+    ev = {'%s_%d' % (rng.choice(['PA', 'RV', 'RA']), k + 1): float(np.round(t, int(rng.integers(0, 4)))) for k, t in enumerate(ts)}
+    ev[chamber + '_9'] = 0.002 * float(rng.integers(0, 3))
+    metas.append(synth_ref.record_meta(int(dur) + 1, events=ev))
+  kinds = synth_ref.kinds_for(sig)
+  recs = [synth_ref.gen_record(7000 + seed, r, T, kinds=kinds) for r, T in enumerate(rows)]
+  cols, rcol = scgrhc.resolve_columns(sig, chans)
+  host = np.concatenate(recs)
+  arena = torch.from_numpy(host).to(DEV)
+  planes = arena.t().contiguous()
+  plan = scgrhc.plan_cohort(metas, chamber, rows, W)
+  a = scgrhc.prepare_windows(arena, plan, cols, rcol, floor, out_dtype=out_dtype)
+  b = scgrhc.prepare_windows(planes, plan, cols, rcol, floor, out_dtype=out_dtype, planar=True)
+  _same_store(a, b)
+  scg, rhc = b.materialise()
+  scg, rhc = scg.cpu().numpy(), rhc.cpu().numpy()
+  rec_id, start, mm = b.rec_id.cpu().numpy(), b.start_idx.cpu().numpy(), b.kept_minmax().cpu().numpy()
+  npdt = np.float64 if out_dtype == torch.float64 else np.float32
+  total = 0
+  for r, p in enumerate(recs):
+    rw = orc.scan_record(p, sig, metas[r], chans, chamber, seg, floor)
+    k = np.nonzero(rw.keep)[0]
+    m = rec_id == r
+    assert start[m].tolist() == rw.rel_start[k].tolist(), (seed, r)
+    s_o, r_o, mm_o = orc.normalise_record(p, sig, chans, rw, out_dtype=npdt)
+    assert (mm[m] == mm_o).all(), (seed, r)
+    assert scg[m].tobytes() == s_o.tobytes() and rhc[m].tobytes() == r_o.tobytes(), (seed, r)
+    total += len(k)
+  assert total == b.n_kept
