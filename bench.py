@@ -98,21 +98,56 @@ def algorithmic_bytes(n_cand, n_kept, C, out_bytes, w=W):
 
 
 class ClockSampler:
-  """nvidia-smi clocks / throttle reasons sampled while the GPU is under load."""
+  """SM clock, board power and throttle reasons sampled while the GPU is under load: NVML polled every 2 ms from a thread
+  (the device-resident timed region is ~40 ms: nvidia-smi's own loop, 50 ms at best, would see it once or not at all), with
+  `nvidia-smi -lms` as the fallback when pynvml is missing.  Both read the same driver counters."""
   Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
        'clocks_event_reasons.sw_power_cap')
+  NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
   def __init__(self, device):
-    self.samples, self.proc, self.device = [], None, device
+    self.samples, self.proc, self.device, self.source, self._stop = [], None, device, None, False
+
+  def _start_nvml(self):
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+    sm_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+    reasons_fn = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+    def bit(name_new, name_old):
+      return getattr(pynvml, name_new, None) or getattr(pynvml, name_old)
+    masks = [bit('nvmlClocksEventReasonHwSlowdown', 'nvmlClocksThrottleReasonHwSlowdown'),
+             bit('nvmlClocksEventReasonHwThermalSlowdown', 'nvmlClocksThrottleReasonHwThermalSlowdown'),
+             bit('nvmlClocksEventReasonSwThermalSlowdown', 'nvmlClocksThrottleReasonSwThermalSlowdown'),
+             bit('nvmlClocksEventReasonSwPowerCap', 'nvmlClocksThrottleReasonSwPowerCap')]
+    pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM); reasons_fn(h)                 # fail here, not in the thread
+    def loop():
+      while not self._stop:
+        try:
+          r = reasons_fn(h)
+          f = [str(self.device), str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(sm_max),
+               '%.2f' % (pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)] + ['Active' if r & m else 'Not Active' for m in masks]
+          self.samples.append((time.time(), f))
+        except Exception:
+          pass
+        time.sleep(0.002)
+    threading.Thread(target=loop, daemon=True).start()
+    self.source = 'nvml, 2 ms'
 
   def start(self):
     try:
+      self._start_nvml()
+      return
+    except Exception:
+      pass
+    try:
       self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                    '-lms', '50', '-i', str(self.device)], stdout=subprocess.PIPE,
+                                    '-lms', '20', '-i', str(self.device)], stdout=subprocess.PIPE,
                                    stderr=subprocess.DEVNULL, text=True)
     except OSError:
       return
+    self.source = 'nvidia-smi -lms 20'
     def reader():
       for line in self.proc.stdout:
         f = [x.strip() for x in line.split(',')]
@@ -121,25 +156,32 @@ class ClockSampler:
     threading.Thread(target=reader, daemon=True).start()
 
   def stop(self):
+    self._stop = True
     if self.proc:
       self.proc.terminate()
 
   def summary(self, windows):
-    """windows: list of (t0, t1) host-time intervals during which the GPU was under our load."""
-    sel = [f for (t, f) in self.samples if any(a <= t <= b for a, b in windows)] or [f for _, f in self.samples]
+    """windows: list of (t0, t1) host-time intervals during which the GPU was under our load.  A window too short to hold a
+    sample takes the samples within 60 ms of it and says so."""
+    sel = [f for (t, f) in self.samples if any(a <= t <= b for a, b in windows)]
+    widened = False
     if not sel:
-      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+      sel, widened = [f for (t, f) in self.samples if any(a - 0.06 <= t <= b + 0.06 for a, b in windows)], True
+    if not sel:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0, 'source': self.source}
     def num(x):
       try:
         return float(x)
       except ValueError:
         return None
     sm = [num(f[1]) for f in sel if num(f[1]) is not None]
-    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    reasons = [n for i, n in enumerate(names) if any(f[4 + i].lower().startswith('active') for f in sel)]
+    reasons = [n for i, n in enumerate(self.NAMES) if any(f[4 + i].lower().startswith('active') for f in sel)]
     pw = [num(f[3]) for f in sel if num(f[3]) is not None]
-    return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': num(sel[0][2]), 'reasons': reasons,
-            'samples': len(sel), 'power_w_max': max(pw) if pw else None}
+    out = {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': num(sel[0][2]), 'reasons': reasons,
+           'samples': len(sel), 'power_w_max': max(pw) if pw else None, 'source': self.source}
+    if widened:
+      out['window'] = 'no sample inside the timed region: samples within 60 ms of it'
+    return out
 
 
 def bind_to_gpu_numa(local):
