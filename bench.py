@@ -108,6 +108,7 @@ class ClockSampler:
 
   def __init__(self, device):
     self.samples, self.proc, self.device, self.source, self._stop = [], None, device, None, False
+    self.period = 0.002          # the main thread relaxes it to 20 ms once the short device-resident regions are over
 
   def _start_nvml(self):
     import pynvml
@@ -131,7 +132,7 @@ class ClockSampler:
           self.samples.append((time.time(), f))
         except Exception:
           pass
-        time.sleep(0.002)
+        time.sleep(self.period)
     threading.Thread(target=loop, daemon=True).start()
     self.source = 'nvml, 2 ms'
 
@@ -645,6 +646,7 @@ def run_b200(args):
 
   # ---- BASELINE configs[2]: batches of 256 kept windows for the trainer, through the loader the drop-in pickles
   #      (recordutil.WindowLoader: one scgrhc_collate_batch launch per batch, shuffled slots uploaded once per epoch) ----
+  sampler.period = 0.02          # the host-side legs below are long; a 2 ms poll would only take GIL slices from them
   batch256 = None
   if not args.out_f64:
     import numpy as np
